@@ -1,0 +1,146 @@
+// libhssb.so: error reporting, device check, metric counters.
+#include "hssb_common.cuh"
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace hssb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+int require_sm100()
+{
+    static thread_local int checked_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(HSSB_E_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+    if (dev == checked_dev) return 0;
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(HSSB_E_DEVICE, "cannot query device %d: %s", dev, cudaGetErrorString(e)); }
+    if (major != 10) return fail(HSSB_E_DEVICE, "device %d is sm_%dx; libhssb is built for sm_100a only (no fallback)", dev, major);
+    checked_dev = dev;
+    return 0;
+}
+
+// ---- per-launch timing -------------------------------------------------------------------------
+namespace {
+struct ProfRec { const char *name; cudaEvent_t start, stop; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+bool g_prof_on = false;
+}  // namespace
+
+ProfScope::ProfScope(const char *name, cudaStream_t s) : slot(-1), st(s)
+{
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+    cudaEventRecord(r.start, st);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+
+ProfScope::~ProfScope()
+{
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].stop, st);
+}
+
+// 4x4 confusion counts (replaces the torchmetrics state of reference main.py:36-62).
+__global__ void confusion_kernel(const int32_t *__restrict__ pred, const int64_t *__restrict__ target,
+                                 long long n, unsigned long long *__restrict__ cm)
+{
+    __shared__ unsigned int local[16];
+    if (threadIdx.x < 16) local[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int p = pred[i];
+        const long long t = target[i];
+        if (p >= 0 && p < 4 && t >= 0 && t < 4) atomicAdd(&local[(int)t * 4 + p], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && local[threadIdx.x]) atomicAdd(&cm[threadIdx.x], (unsigned long long)local[threadIdx.x]);
+}
+
+}  // namespace hssb
+
+extern "C" int hssb_version(void) { return HSSB_VERSION; }
+extern "C" const char *hssb_last_error(void) { return hssb::g_err; }
+
+extern "C" int hssb_prof_enable(int on)
+{
+    std::lock_guard<std::mutex> lock(hssb::g_prof_mu);
+    hssb::g_prof_on = on != 0;
+    return 0;
+}
+
+// Writes one line per kernel name: "<name> <launches> <total_ms>\n"; clears the records.
+extern "C" int hssb_prof_read(char *buf, size_t n)
+{
+    using namespace hssb;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    std::map<std::string, std::pair<long long, double>> acc;
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            auto &a = acc[r.name];
+            a.first += 1;
+            a.second += ms;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_prof.clear();
+    std::string out;
+    for (auto &kv : acc) {
+        char line[160];
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (!buf || n == 0) return (int)out.size();
+    snprintf(buf, n, "%s", out.c_str());
+    return (int)out.size();
+}
+
+extern "C" int hssb_confusion(const int32_t *pred, const int64_t *target, int64_t n, int64_t *cm16, void *stream)
+{
+    using namespace hssb;
+    if (!pred || !target || !cm16) return fail(HSSB_E_NULL, "hssb_confusion: null pointer");
+    if (n < 0) return fail(HSSB_E_SHAPE, "hssb_confusion: n=%lld", (long long)n);
+    if (n == 0) return 0;
+    if (int rc = require_sm100()) return rc;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ProfScope prof("confusion", as_stream(stream));
+    confusion_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pred, target, n, reinterpret_cast<unsigned long long *>(cm16));
+    HSSB_LAUNCH_OK("confusion_kernel");
+    return 0;
+}

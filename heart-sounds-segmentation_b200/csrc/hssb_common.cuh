@@ -1,0 +1,44 @@
+// Shared helpers for libhssb.so (error reporting, launch checks).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/hssb.h"
+
+namespace hssb {
+
+// thread-local message of the last failure (returned by hssb_last_error()).
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);          // sets the message, returns code
+int cuda_fail(cudaError_t e, const char *what);    // sets the message, returns (int)e
+
+#define HSSB_CUDA_OK(expr)                                                    \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return ::hssb::cuda_fail(_e, #expr);           \
+    } while (0)
+
+#define HSSB_LAUNCH_OK(name)                                                  \
+    do {                                                                      \
+        cudaError_t _e = cudaGetLastError();                                  \
+        if (_e != cudaSuccess) return ::hssb::cuda_fail(_e, name);            \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// fails with HSSB_E_DEVICE unless the current device is compute capability 10.x
+int require_sm100();
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Optional per-launch timing (hssb_prof_*): a pair of CUDA events recorded on the launching stream
+// around one kernel launch.  Costs nothing when disabled.
+struct ProfScope {
+    ProfScope(const char *name, cudaStream_t st);
+    ~ProfScope();
+    int slot;
+    cudaStream_t st;
+};
+
+}  // namespace hssb

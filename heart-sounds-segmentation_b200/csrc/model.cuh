@@ -1,0 +1,42 @@
+// Packed, HBM-resident weights of the BiLSTM segmenter and the internal kernel entry points.
+#pragma once
+#include "hssb_common.cuh"
+#include <cuda_fp16.h>
+
+struct hssb_model {
+    int F;          // input features (44)
+    int H;          // hidden units (240)
+    int device;
+    // ---- SIMT fp32 validation path: transposed weights, folded biases -------------------------
+    float *w_ihT[2][2];   // [Kin][4H]   (Kin = F for layer 0, 2H for layer 1)
+    float *w_hhT[2][2];   // [H][4H]
+    float *bias[2][2];    // [4H] = b_ih + b_hh
+    float *lin_w;         // [4][2H]
+    float *lin_b;         // [4]
+    // ---- tcgen05 path (H == 240 only): split-fp16 operands in "cluster gate order" -------------
+    // gate row index g' = rank*128 + gate*32 + u  (rank 0..7, gate 0..3 = i,f,g,o, u 0..31; u >= 30 is padding)
+    bool tc_ready;
+    __half *tc_wih[2];        // layer l: [2 planes hi/lo][2 dirs][1024 g'][KinP]   KinP = 64 (l=0) / 512 (l=1)
+    __half *tc_whh[2];        // layer l: [2 planes][2 dirs][1024 g'][256]  (k index = rank*32+u order, padded)
+    float *tc_bias[2];        // layer l: [2 dirs][1024]
+    void *all;                // single allocation backing everything above
+    size_t all_bytes;
+};
+
+namespace hssb {
+
+// SIMT path (lstm_simt.cu)
+int simt_inproj(const float *A, int64_t M, int K, const float *Wt, const float *bias, int N, float *C, cudaStream_t st);
+int simt_recurrent(const float *xproj /*[2][B*T][4H]*/, const float *const w_hhT[2], const float *h0, const float *c0,
+                   int64_t B, int64_t T, int H, float *out /*[B,T,2H] relu'd*/, float *hn, float *cn, cudaStream_t st);
+int head_forward(const float *act /*[M,2H] already relu'd*/, int64_t M, int H2, const float *lin_w, const float *lin_b,
+                 float *logp, int32_t *labels, cudaStream_t st);
+
+// tcgen05 path (lstm_tc.cu)
+size_t tc_pack_bytes(int F, int H);
+int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t st);
+size_t tc_workspace_bytes(const hssb_model *m, int64_t B, int64_t T);
+int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
+               float *logp, int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace hssb

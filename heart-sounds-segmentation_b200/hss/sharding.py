@@ -1,0 +1,65 @@
+"""Data-parallel plumbing: windows shard across ranks, the only collective is the metric all-reduce.
+
+Every window / recording is independent in FSST (per-window z-score, reference
+hss/transforms/synchrosqueeze.py:78-81) and in the BiLSTM (batch rows, reference
+hss/model/segmenter.py:38-41), so ranks own contiguous blocks of windows and exchange nothing
+until the 4x4 confusion counts (reference main.py:36-62, torchmetrics state) are summed.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block ``[lo, hi)`` of ``n`` windows owned by ``rank`` (sizes differ by at most 1)."""
+    if world < 1 or not (0 <= rank < world) or n < 0:
+        raise ValueError(f"bad shard request n={n} rank={rank} world={world}")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def confusion_counts(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """4x4 int64 counts ``cm[target, pred]`` of this rank's labels (CUDA kernel ``hssb_confusion``)."""
+    if not pred.is_cuda:
+        raise RuntimeError("confusion_counts runs on the GPU (no CPU fallback)")
+    pred = pred.to(torch.int32).contiguous().reshape(-1)
+    target = target.to(device=pred.device, dtype=torch.int64).contiguous().reshape(-1)
+    if pred.numel() != target.numel():
+        raise ValueError("pred / target size mismatch")
+    cm = torch.zeros(16, dtype=torch.int64, device=pred.device)
+    with torch.cuda.device(pred.device):
+        rc = _lib.lib().hssb_confusion(pred.data_ptr(), target.data_ptr(), pred.numel(), cm.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "hssb_confusion")
+    return cm.reshape(4, 4)
+
+
+def allreduce_counts(cm: torch.Tensor) -> torch.Tensor:
+    """Sum the per-rank counters over the job (NCCL on GPUs, gloo in CPU tests); no-op single-process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(cm, op=dist.ReduceOp.SUM)
+    return cm
+
+
+def metrics_from_counts(cm: torch.Tensor) -> dict:
+    """Per-class and macro accuracy(=recall) / precision / F1 from ``cm[target, pred]``.
+
+    Same definitions as the torchmetrics multiclass collection of reference main.py:36-62
+    (``Accuracy(average=None)`` is per-class recall; zero-division -> 0).
+    """
+    cm = cm.to(torch.float64).cpu()
+    tp = cm.diag()
+    support = cm.sum(dim=1)
+    predicted = cm.sum(dim=0)
+    recall = torch.where(support > 0, tp / support.clamp(min=1), torch.zeros_like(tp))
+    precision = torch.where(predicted > 0, tp / predicted.clamp(min=1), torch.zeros_like(tp))
+    denom = precision + recall
+    f1 = torch.where(denom > 0, 2 * precision * recall / denom.clamp(min=1e-300), torch.zeros_like(tp))
+    return {
+        "accuracy_per_class": recall, "recall_per_class": recall, "precision_per_class": precision, "f1_per_class": f1,
+        "accuracy": float(recall.mean()), "recall": float(recall.mean()), "precision": float(precision.mean()),
+        "f1": float(f1.mean()), "micro_accuracy": float(tp.sum() / cm.sum().clamp(min=1)),
+    }

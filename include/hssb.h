@@ -1,0 +1,144 @@
+/* hssb.h -- C-ABI of libhssb.so: the B200 (sm_100a) FSST -> BiLSTM hot path.
+ *
+ * Drop-in boundary for alvgaona/heart-sounds-segmentation.  Every entry point names the reference
+ * interface it replaces (file:line relative to the reference repository):
+ *
+ *   FSST      ssq.fsst(x, fs, window) -> (s, f, t)       hss/transforms/synchrosqueeze.py:48
+ *                                                          scripts/visualize_signals.py:14
+ *             band mask / abs / z-score+stack              hss/transforms/synchrosqueeze.py:56-111
+ *             streaming mean / M2 recurrences              hss/moments/__init__.py:16,35-36
+ *   BiLSTM    HeartSoundSegmenter.forward                  hss/model/segmenter.py:70-87
+ *   metrics   multiclass confusion counts                  main.py:36-62 (torchmetrics)
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, no torch / C++ types.
+ *   - "device" pointers are caller-owned CUDA device memory; the library never frees them and all
+ *     work is ordered on the caller's stream (a cudaStream_t passed as void*).  It never
+ *     synchronises unless the entry point says "host".
+ *   - "host" entry points take host buffers, do the H2D / D2H copies themselves and synchronise
+ *     before returning (this is what a binding replacing ssq.fsst would call).
+ *   - return 0 on success; <0 = argument error (HSSB_E_*); >0 = cudaError_t.  The message of the
+ *     last failure on the calling thread is returned by hssb_last_error().
+ *   - there is no CPU fallback: without a usable sm_100 device every compute entry point fails.
+ */
+#ifndef HSSB_H
+#define HSSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSSB_VERSION 1
+
+enum {
+    HSSB_OK = 0,
+    HSSB_E_NULL = -1,      /* required pointer is NULL */
+    HSSB_E_SHAPE = -2,     /* negative / inconsistent sizes */
+    HSSB_E_NWIN = -3,      /* unsupported window length (supported: 128, 256) */
+    HSSB_E_BAND = -4,      /* k_lo / k_hi outside [0, nwin/2] or k_hi < k_lo */
+    HSSB_E_MODE = -5,      /* unknown output mode */
+    HSSB_E_WORKSPACE = -6, /* workspace too small / misaligned */
+    HSSB_E_MODEL = -7,     /* unsupported model geometry */
+    HSSB_E_DEVICE = -8     /* no sm_100 device / wrong architecture */
+};
+
+/* output modes of the FSST wrapper (branch precedence of synchrosqueeze.py:56-65) */
+enum { HSSB_MODE_RAW = 0, HSSB_MODE_ABS = 1, HSSB_MODE_STACK = 2 };
+
+typedef struct { float re, im; } hssb_c32; /* complex64, layout of torch.complex64 / numpy.complex64 */
+
+int hssb_version(void);
+const char *hssb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * FSST: three kernels + one fused convenience call.
+ * Shapes: x [B,N] f32; g, dg [nwin] f32 (window and its dtwin derivative, computed by the host
+ * in float64 and rounded); nfft = nwin; K = nwin/2+1; Kt = k_hi-k_lo+1.
+ * ------------------------------------------------------------------------------------------ */
+
+/* K1  replaces the STFT half of ssq.fsst (synchrosqueeze.py:48): hop-1 STFT of every window with
+ * g and g'.  Sg, Sdg: [B,K,N] complex64 (frequency-major, time contiguous). */
+int hssb_fsst_stft(const float *x, int64_t B, int64_t N, const float *g, const float *dg, int nwin,
+                   hssb_c32 *Sg, hssb_c32 *Sdg, void *stream);
+
+/* number of float64 words of the per-tile moment partials written by hssb_fsst_reassign */
+size_t hssb_fsst_stats_words(int64_t B, int64_t N);
+
+/* K2  replaces the IF-estimate + reassignSpectrum half of ssq.fsst (synchrosqueeze.py:48) fused
+ * with the band mask (synchrosqueeze.py:107-111): T [B,Kt,N] complex64 holds rows k_lo..k_hi of
+ * the synchrosqueezed transform.  stats (nullable) receives per-tile (n, mean, M2) partials of Re
+ * and Im -- the hss/moments/__init__.py recurrences, parallelised -- for hssb_fsst_finish. */
+int hssb_fsst_reassign(const hssb_c32 *Sg, const hssb_c32 *Sdg, int64_t B, int64_t N, int nwin,
+                       float fs, int k_lo, int k_hi, hssb_c32 *T, double *stats, void *stream);
+
+/* K3  replaces synchrosqueeze.py:59-60 (mode ABS: out f32 [B,N,Kt]) and synchrosqueeze.py:78-89
+ * (mode STACK: out f32 [B,N,2*Kt] = [(Re-mean)/std , (Im-mean)/std], unbiased std). */
+int hssb_fsst_finish(const hssb_c32 *T, const double *stats, int64_t B, int64_t N, int Kt, int mode,
+                     float *out, void *stream);
+
+/* K1+K2(+K3) on device buffers.  out: RAW -> hssb_c32 [B,Kt,N]; ABS -> f32 [B,N,Kt];
+ * STACK -> f32 [B,N,2*Kt].  workspace: hssb_fsst_workspace_bytes() bytes, 256-byte aligned. */
+size_t hssb_fsst_workspace_bytes(int64_t B, int64_t N, int nwin, int k_lo, int k_hi, int mode);
+int hssb_fsst_forward(const float *x, int64_t B, int64_t N, const float *g, const float *dg, int nwin,
+                      float fs, int k_lo, int k_hi, int mode, void *out, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* HOST entry point: the call a binding replacing ssq.fsst makes.  x, window, dwindow and out are
+ * host buffers; copies + kernels + synchronisation happen inside.  Same `out` layouts as above. */
+int hssb_fsst_host(const float *x, int64_t B, int64_t N, double fs, const double *window,
+                   const double *dwindow, int nwin, int k_lo, int k_hi, int mode, void *out);
+
+/* ------------------------------------------------------------------------------------------
+ * BiLSTM segmenter: replaces HeartSoundSegmenter.forward (segmenter.py:70-87), eval mode.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hssb_model hssb_model; /* opaque: packed weights resident in HBM */
+
+/* Parameters in torch layout, HOST or DEVICE pointers are both accepted (cudaMemcpyDefault):
+ * per layer l in {0,1} and direction d in {0 fwd, 1 reverse}: w_ih [4H,Kin_l], w_hh [4H,H],
+ * b_ih [4H], b_hh [4H] (gate order i,f,g,o; segmenter.py:43-58); lin_w [4,2H], lin_b [4]
+ * (segmenter.py:61-67).  input_size = Kin_0, Kin_1 = 2H. */
+typedef struct {
+    int input_size;
+    int hidden_size;
+    const float *w_ih[2][2];
+    const float *w_hh[2][2];
+    const float *b_ih[2][2];
+    const float *b_hh[2][2];
+    const float *lin_w;
+    const float *lin_b;
+} hssb_model_params;
+
+int hssb_model_create(const hssb_model_params *params, hssb_model **out, void *stream);
+void hssb_model_destroy(hssb_model *m);
+
+size_t hssb_model_workspace_bytes(const hssb_model *m, int64_t B, int64_t T);
+
+/* x [B,T,input_size] f32 device; h0, c0 [2,B,H] f32 device (segmenter.py:38-41);
+ * logp [B,T,4] f32 device (nullable); labels [B,T] int32 device (nullable) = argmax over classes.
+ * impl: 0 = default (tcgen05 kernels when hidden_size == 240, else the generic SIMT CUDA kernels),
+ *       1 = force the SIMT fp32 kernels (on-device validation path). */
+int hssb_model_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0,
+                       const float *c0, float *logp, int32_t *labels, void *workspace,
+                       size_t workspace_bytes, int impl, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Metric counters: replaces the torchmetrics confusion statistics of main.py:36-62.
+ * cm16 [4,4] int64 device, cm[target][pred] += 1 (accumulates; caller zeroes).
+ * ------------------------------------------------------------------------------------------ */
+int hssb_confusion(const int32_t *pred, const int64_t *target, int64_t n, int64_t *cm16, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-launch timing for bench.py: when enabled, every kernel launch is bracketed by CUDA events on
+ * the launching stream.  hssb_prof_read() synchronises on them, writes one line per kernel
+ * ("<name> <launches> <total_ms>\n") into buf, clears the records and returns the text length.
+ * ------------------------------------------------------------------------------------------ */
+int hssb_prof_enable(int on);
+int hssb_prof_read(char *buf, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSSB_H */

@@ -1,0 +1,99 @@
+"""Host-side logic of the drop-in layer (no GPU): window preparation, band selection, API surface,
+moments, sharding and metric definitions."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsst_oracle as fo
+
+
+def test_derivative_window_matches_oracle_dtwin():
+    from hss.transforms._window import derivative_window
+
+    for w, fs in ((fo.reference_window(), 1000.0), (np.kaiser(256, 10.0), 2000.0)):
+        assert np.abs(derivative_window(w, fs) - fo.dtwin(w, fs)).max() < 1e-12
+
+
+def test_band_rows_match_reference_mask():
+    from hss.transforms._window import band_rows
+
+    assert band_rows(1000, 128, (25, 200)) == (4, 25)          # 22 rows -> 44 features (test_dataset.py:67-69)
+    assert band_rows(2000, 128, (50, 400)) == (4, 25)          # config 5
+    assert band_rows(1000, 128, (31.25, 195.3125)) == (4, 25)  # inclusive on both ends (synchrosqueeze.py:109)
+    assert band_rows(1000, 256, (25, 200)) == fo.band_rows(1000, 256, (25, 200))
+    with pytest.raises(ValueError):
+        band_rows(1000, 128, (1, 2))
+
+
+def test_fsst_signature_matches_reference():
+    from hss.transforms import FSST
+
+    params = list(inspect.signature(FSST.__init__).parameters)
+    assert params == ["self", "fs", "window", "abs", "stack", "truncate_freq", "dtype"]   # synchrosqueeze.py:13-21
+    f = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True)
+    assert f.num_rows == 22 and f.fs == 1000 and f.stack and not f.abs
+    assert torch.allclose(f.frequencies(), torch.arange(4, 26) * 7.8125)
+    with pytest.raises(ValueError):
+        FSST(1000, window=np.ones(100))
+
+
+def test_segmenter_signature_state_dict_and_rng_order():
+    from hss.model.segmenter import HeartSoundSegmenter
+    from oracle import lstm_oracle as lo
+
+    sig = inspect.signature(HeartSoundSegmenter.__init__)
+    assert list(sig.parameters) == ["self", "input_size", "batch_size", "hidden_size", "bidirectional", "device", "dtype"]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for n, p in sig.parameters.items() if n != "self")
+    torch.manual_seed(68)
+    m = HeartSoundSegmenter(input_size=44, batch_size=3)
+    params, h0, c0 = lo.reference_params(68, 44, 3, 240)
+    assert list(m.state_dict().keys()) == lo.PARAM_NAMES
+    assert torch.equal(m.h0, h0) and torch.equal(m.c0, c0)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, params[k])
+    assert sum(p.numel() for p in m.parameters()) == 1_937_284
+    m.eval()
+    with pytest.raises(RuntimeError, match="Expected hidden"):
+        m(torch.zeros(2, 5, 44))                                      # batch mismatch raises like the reference
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(3, 5, 44))
+
+
+def test_moments_api():
+    from hss.moments import update_mean, update_variance
+
+    v = np.random.default_rng(2).standard_normal(200)
+    m = m2 = 0.0
+    for k, x in enumerate(v, 1):
+        m2 = update_variance(x, m, m2, k)
+        m = update_mean(m, x, k)
+        assert update_variance(x, 0.0, 0.0, 1) == 0.0 or k > 1
+    assert abs(m - v.mean()) < 1e-12 and abs(m2 / 199 - v.var(ddof=1)) < 1e-12
+    assert fo.update_mean(1.0, 3.0, 2) == update_mean(1.0, 3.0, 2)
+
+
+def test_shard_range_partitions():
+    from hss.sharding import shard_range
+
+    for n, w in ((4096, 8), (50, 8), (7, 2), (0, 4), (3, 5)):
+        parts = [shard_range(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def test_metrics_from_counts():
+    from hss.sharding import metrics_from_counts
+
+    cm = torch.tensor([[8, 2, 0, 0], [1, 9, 0, 0], [0, 0, 5, 5], [0, 0, 0, 10]])
+    m = metrics_from_counts(cm)
+    assert torch.allclose(m["recall_per_class"], torch.tensor([0.8, 0.9, 0.5, 1.0], dtype=torch.float64))
+    assert torch.allclose(m["precision_per_class"], torch.tensor([8 / 9, 9 / 11, 1.0, 10 / 15], dtype=torch.float64))
+    assert abs(m["micro_accuracy"] - 32 / 40) < 1e-12
+    assert metrics_from_counts(torch.zeros(4, 4))["f1"] == 0.0

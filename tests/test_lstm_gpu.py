@@ -1,0 +1,118 @@
+"""Parity of the BiLSTM CUDA path (through hssb_model_forward) against the reference's outputs
+(golden, generated from the real reference module) and the torch-CPU oracle restatement.
+
+Tolerance (north star): labels identical to the reference on identical weights / h0 / c0 / inputs;
+log-probabilities within 2e-5 absolute.  Where a label differs, the reference's own top-2 margin at
+that position must be below the fp32 re-ordering noise (1e-5) -- reported, not hidden.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsst_oracle as fo
+from oracle import lstm_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+LOGP_TOL = 2e-5
+MARGIN_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def lib(built):
+    from hss import _lib
+
+    assert torch.cuda.is_available()
+    return _lib.lib()
+
+
+def make_model(seed, F, B, H, params=None):
+    from hss.model.segmenter import HeartSoundSegmenter
+
+    torch.manual_seed(seed)
+    m = HeartSoundSegmenter(input_size=F, batch_size=B, hidden_size=H).eval()
+    if params is not None:
+        m.load_state_dict(params)
+    return m
+
+
+def check(logp, labels, ref_logp):
+    rep = lo.label_report(logp, ref_logp)
+    assert rep["max_abs_dlogp"] < LOGP_TOL, rep
+    assert rep["flips"] == 0 or rep["max_margin_flipped"] < MARGIN_TOL, rep
+    assert torch.equal(labels.long(), logp.argmax(-1))
+    return rep
+
+
+@pytest.mark.parametrize("impl", ["auto", "simt"])
+@pytest.mark.parametrize("name", ["lstm_small.npz", "lstm_h240.npz"])
+def test_golden_reference_outputs(lib, golden_dir, name, impl, monkeypatch):
+    monkeypatch.setenv("HSSB_LSTM_IMPL", impl)
+    g = np.load(os.path.join(golden_dir, name))
+    seed, B, F, H = int(g["seed"]), int(g["B"]), int(g["F"]), int(g["H"])
+    m = make_model(seed, F, B, H)
+    assert np.array_equal(m.h0.numpy(), g["h0"])                     # same RNG draw order as the reference ctor
+    x = torch.from_numpy(g["x"])
+    logp, labels = m.forward_with_labels(x)
+    assert logp.shape == (B, int(g["T"]), 4) and not logp.is_cuda
+    check(logp, labels, torch.from_numpy(g["logp"]))
+    assert torch.equal(m(x), logp)                                    # forward() == forward_with_labels()[0]
+    assert torch.equal(m.predict(x), labels)
+
+
+@pytest.mark.parametrize("impl", ["auto", "simt"])
+def test_config3_shape_vs_torch_cpu(lib, impl, monkeypatch):
+    """BASELINE config 3 geometry (batch 50, 44 features, H 240) on FSST features, shorter T for the CPU oracle."""
+    from hss.transforms import FSST
+
+    monkeypatch.setenv("HSSB_LSTM_IMPL", impl)
+    B, T = 50, 400
+    x = torch.from_numpy(fo.synth_pcg_batch(B, T, seed=68))
+    feats = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True).batch(x.cuda())
+    m = make_model(68, 44, B, 240)
+    logp, labels = m.forward_with_labels(feats)
+    assert logp.is_cuda
+    params, h0, c0 = lo.reference_params(68, 44, B, 240)
+    ref = lo.forward_torch(params, h0, c0, feats.cpu())
+    rep = check(logp.cpu(), labels.cpu(), ref)
+    truth = lo.forward_manual(params, h0, c0, feats.cpu(), torch.float64)
+    rep2 = lo.label_report(logp.cpu(), ref, truth)
+    print("config3 report", rep, rep2)
+
+
+def test_odd_batch_and_short_sequences(lib):
+    for B, T in ((1, 1), (3, 2), (5, 17), (9, 33)):
+        m = make_model(B * 31 + T, 44, B, 240)
+        x = torch.randn(B, T, 44)
+        params, h0, c0 = lo.reference_params(B * 31 + T, 44, B, 240)
+        logp, labels = m.forward_with_labels(x)
+        check(logp, labels, lo.forward_torch(params, h0, c0, x))
+    m = make_model(1, 44, 2, 240)
+    assert m(torch.zeros(2, 0, 44)).shape == (2, 0, 4)
+
+
+def test_state_dict_reload_repacks_weights(lib):
+    m = make_model(3, 44, 2, 240)
+    x = torch.randn(2, 20, 44)
+    a = m(x)
+    params, h0, c0 = lo.reference_params(99, 44, 2, 240)
+    m.load_state_dict(params)
+    m.h0, m.c0 = h0, c0                       # h0/c0 are plain tensors, not in the state_dict
+    b = m(x)
+    assert not torch.equal(a, b)
+    assert (b - lo.forward_torch(params, h0, c0, x)).abs().max() < LOGP_TOL
+
+
+def test_confusion_kernel_and_metrics(lib):
+    from hss.sharding import confusion_counts, metrics_from_counts
+
+    g = torch.Generator().manual_seed(1)
+    pred = torch.randint(0, 4, (50, 2000), generator=g, dtype=torch.int32)
+    target = torch.randint(0, 4, (50, 2000), generator=g)
+    cm = confusion_counts(pred.cuda(), target.cuda()).cpu()
+    ref = torch.zeros(4, 4, dtype=torch.int64)
+    ref.index_put_((target.reshape(-1), pred.reshape(-1).long()), torch.ones(pred.numel(), dtype=torch.int64), accumulate=True)
+    assert torch.equal(cm, ref)
+    assert abs(metrics_from_counts(cm)["micro_accuracy"] - float((pred == target).float().mean())) < 1e-9
