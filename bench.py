@@ -278,7 +278,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(50)
             xs = make_windows(50, 68)
-            ref.step(xs[:8])
+            ref.step(xs)
             t0 = time.perf_counter()
             _, tf_, tl_ = ref.step(xs)
             dt = time.perf_counter() - t0

@@ -1,12 +1,376 @@
-// tcgen05 path of the BiLSTM segmenter (placeholder until the kernels land).
+// tcgen05 / TMEM / TMA kernels of the BiLSTM segmenter (hidden_size = 240).
+//
+// Precision: every gate contraction runs as a split-fp16 "3-pass" product on the 5th-gen tensor
+// cores with fp32 accumulation in TMEM:  x = hi + lo (hi = fp16(x), lo = fp16(x - hi), 22 mantissa
+// bits together), and  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (the dropped lo*lo term is 2^-22
+// relative).  That keeps log-probabilities within ~1e-6 of the fp32 reference, which is what the
+// bit-identical-labels requirement needs, at 3 fp16 MMAs per product.
+//
+// "Cluster gate order": the 960 gate rows of one direction are permuted to g' = r*120 + q*30 + u
+// (r = CTA rank in the 8-CTA recurrence cluster, q = gate i/f/g/o, u = unit 0..29 of that rank;
+// torch row = q*240 + 30*r + u), so that every recurrence CTA owns one contiguous 120-wide slice.
+//
+// K4  tc_inproj_kernel : xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']
+//     128(t) x 192(g') output tile per CTA, K blocks of 64 through a 2-stage TMA ring (SW128),
+//     accumulators in TMEM, epilogue TMEM -> regs -> swizzled smem -> TMA store.
 #include "model.cuh"
+#include "tc_ptx.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
 namespace hssb {
-size_t tc_pack_bytes(int, int) { return 0; }
-int tc_pack(hssb_model *m, const hssb_model_params *, void *, cudaStream_t) { m->tc_ready = false; return 0; }
-size_t tc_workspace_bytes(const hssb_model *, int64_t, int64_t) { return 0; }
-int tc_forward(const hssb_model *, const float *, int64_t, int64_t, const float *, const float *, float *, int32_t *,
-               void *, size_t, cudaStream_t)
+
+using namespace ptx;
+
+constexpr int TC_H = 240;
+constexpr int TC_G = 960;          // gate rows per direction
+constexpr int TC_NG = 2 * TC_G;    // both directions
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 {
-    return fail(HSSB_E_MODEL, "tcgen05 path not built");
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
 }
+
+static int make_tmap(CUtensorMap *m, CUtensorMapDataType dt, int rank, const void *base, const uint64_t *dims,
+                     const uint64_t *strides_bytes, const uint32_t *box, CUtensorMapSwizzle sw)
+{
+    auto enc = get_encode();
+    if (!enc) return fail(HSSB_E_DEVICE, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t gd[5], gs[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HSSB_E_SHAPE, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo)
+{
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// x[M,F] fp32 -> hi/lo fp16 planes [M,Kp] (zero padded columns)
+__global__ void split_planes_kernel(const float *__restrict__ x, long long M, int F, int Kp, __half *__restrict__ hi,
+                                    __half *__restrict__ lo)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * Kp) return;
+    const long long m = i / Kp;
+    const int k = (int)(i % Kp);
+    __half h = __float2half_rn(0.f), l = h;
+    if (k < F) split_f16(x[m * F + k], h, l);
+    hi[i] = h;
+    lo[i] = l;
+}
+
+// torch W_ih[960][Kin] (rows q*240 + unit) -> planes [dir*960 + g'][Kp]; bias[dir*960 + g'] = b_ih + b_hh
+__global__ void pack_wih_kernel(const float *__restrict__ w, const float *__restrict__ b_ih, const float *__restrict__ b_hh, int Kin,
+                                int Kp, int dir, __half *__restrict__ hi, __half *__restrict__ lo, float *__restrict__ bias)
+{
+    const int gp = blockIdx.x;                     // g' = r*120 + q*30 + u
+    const int r = gp / 120, q = (gp % 120) / 30, u = gp % 30;
+    const int row = q * TC_H + 30 * r + u;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        __half h = __float2half_rn(0.f), l = h;
+        if (k < Kin) split_f16(w[(size_t)row * Kin + k], h, l);
+        hi[((size_t)dir * TC_G + gp) * Kp + k] = h;
+        lo[((size_t)dir * TC_G + gp) * Kp + k] = l;
+    }
+    if (threadIdx.x == 0) bias[dir * TC_G + gp] = b_ih[row] + b_hh[row];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4
+// ------------------------------------------------------------------------------------------------
+constexpr int IP_BM = 128, IP_BN = 192, IP_BK = 64, IP_STAGES = 2;
+constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (16 KB)
+constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (24 KB)
+constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 80 KB
+constexpr int IP_OUT_BYTES = IP_BM * 32 * 4;             // epilogue staging tile 128 x 32 fp32 (16 KB)
+constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + 2 * IP_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int IP_TMEM_COLS = 256;
+
+struct InprojParams {
+    CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (64,128,1), SW128
+    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (64,192), SW128
+    CUtensorMap out;          // [g'(960), b, t, dir] fp32, box (32,1,128,1), SW128
+    const float *bias;        // [1920]
+    int k_real;               // true K (44->64 padded planes use 64; 480)
+    int t_tiles;              // ceil(T/128)
+};
+
+__global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant__ InprojParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *stage_base = smem;
+    unsigned char *out_base = smem + IP_STAGES * IP_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + 2 * IP_OUT_BYTES);
+    uint64_t *full = bars, *empty = bars + IP_STAGES, *tmem_full = bars + 2 * IP_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * IP_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.t_tiles;
+    const int t0 = (blockIdx.x % p.t_tiles) * IP_BM;
+    const int n0 = blockIdx.y * IP_BN;              // over 1920 = both directions
+    const int kblocks = (p.k_real + IP_BK - 1) / IP_BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.a_hi); prefetch_tmap(&p.a_lo); prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo); prefetch_tmap(&p.out);
+        for (int s = 0; s < IP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<IP_TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % IP_STAGES;
+                const uint32_t ph = (kb / IP_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char *st = stage_base + s * IP_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], IP_STAGE_BYTES);
+                tma_load_3d(st, &p.a_hi, &full[s], kb * IP_BK, t0, b);
+                tma_load_3d(st + IP_A_BYTES, &p.a_lo, &full[s], kb * IP_BK, t0, b);
+                tma_load_2d(st + 2 * IP_A_BYTES, &p.w_hi, &full[s], kb * IP_BK, n0);
+                tma_load_2d(st + 2 * IP_A_BYTES + IP_B_BYTES, &p.w_lo, &full[s], kb * IP_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(IP_BM, IP_BN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % IP_STAGES;
+                const uint32_t ph = (kb / IP_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(stage_base + s * IP_STAGE_BYTES);
+                const uint32_t a_lo = a_hi + IP_A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * IP_A_BYTES;
+                const uint32_t b_lo = b_hi + IP_B_BYTES;
+                const int ksteps = min(IP_BK, p.k_real - kb * IP_BK + 15) / 16;   // skip all-padding K16 steps
+                for (int ks = 0; ks < ksteps && ks < IP_BK / 16; ++ks) {
+                    const uint32_t off = ks * 32;   // 16 fp16 = 32 bytes inside the 128-byte swizzle row
+                    const uint64_t da_hi = make_smem_desc(a_hi + off, 16, 1024, LAYOUT_SW128);
+                    const uint64_t da_lo = make_smem_desc(a_lo + off, 16, 1024, LAYOUT_SW128);
+                    const uint64_t db_hi = make_smem_desc(b_hi + off, 16, 1024, LAYOUT_SW128);
+                    const uint64_t db_lo = make_smem_desc(b_lo + off, 16, 1024, LAYOUT_SW128);
+                    mma_f16_ss(tmem_base, da_hi, db_hi, idesc, (kb | ks) != 0);
+                    mma_f16_ss(tmem_base, da_lo, db_hi, idesc, 1);
+                    mma_f16_ss(tmem_base, da_hi, db_lo, idesc, 1);
+                }
+                mma_commit(&empty[s]);          // frees the smem stage when these MMAs retire
+            }
+            mma_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;          // tile row = time index t0 + row
+        const int et = threadIdx.x - 64;        // 0..127
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int dir = n0 / TC_G, nl0 = n0 % TC_G;
+        for (int c = 0; c < IP_BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+            tmem_ld_wait();
+            unsigned char *ob = out_base + (c & 1) * IP_OUT_BYTES;
+            if (c >= 2 && et == 0) tma_store_wait_read<1>();     // the store that last used this buffer has read it
+            named_barrier(1, 128);
+            const float *bias = p.bias + n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 o;
+                o.x = __uint_as_float(v[4 * j + 0]) + __ldg(bias + 4 * j + 0);
+                o.y = __uint_as_float(v[4 * j + 1]) + __ldg(bias + 4 * j + 1);
+                o.z = __uint_as_float(v[4 * j + 2]) + __ldg(bias + 4 * j + 2);
+                o.w = __uint_as_float(v[4 * j + 3]) + __ldg(bias + 4 * j + 3);
+                *reinterpret_cast<float4 *>(ob + row * 128 + ((j ^ (row & 7)) << 4)) = o;   // 128B swizzle
+            }
+            fence_proxy_async_smem();
+            named_barrier(1, 128);
+            if (et == 0) {
+                tma_store_4d(&p.out, ob, nl0 + c * 32, b, t0, dir);
+                tma_store_commit();
+            }
+        }
+        if (et == 0) tma_store_wait<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<IP_TMEM_COLS>(tmem_base);
+}
+
+// xproj[dir][t][b][g'] -> canonical [dir][b*T + t][q*240 + unit]   (debug / validation only)
+__global__ void unpermute_xproj_kernel(const float *__restrict__ src, long long B, long long T, float *__restrict__ dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = 2 * B * T * TC_G;
+    if (i >= total) return;
+    const int gp = (int)(i % TC_G);
+    const long long rest = i / TC_G;
+    const long long b = rest % B, t = (rest / B) % T, dir = rest / (B * T);
+    const int r = gp / 120, q = (gp % 120) / 30, u = gp % 30;
+    dst[((size_t)dir * B * T + b * T + t) * TC_G + q * TC_H + 30 * r + u] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int kp_of_layer(int layer, int F) { return layer == 0 ? 64 : 512; }
+static int kreal_of_layer(int layer, int F) { return layer == 0 ? ((F + 15) / 16) * 16 : 2 * TC_H; }
+
+size_t tc_pack_bytes(int F, int H)
+{
+    if (H != TC_H || F > 64) return 0;
+    size_t n = 0;
+    for (int l = 0; l < 2; ++l) {
+        n += align_up(sizeof(__half) * 2 * TC_NG * kp_of_layer(l, F), 256);   // wih hi+lo
+        n += align_up(sizeof(float) * TC_NG, 256);                             // bias
+    }
+    return n;
+}
+
+int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t st)
+{
+    m->tc_ready = false;
+    if (m->H != TC_H || m->F > 64) return 0;
+    char *base = static_cast<char *>(dst);
+    size_t off = 0;
+    const int kin[2] = {m->F, 2 * TC_H};
+    // the raw torch tensors may be host pointers: stage them through a temporary device buffer
+    float *tmp = nullptr;
+    const size_t tmp_floats = (size_t)TC_G * (2 * TC_H) + 2 * TC_G;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&tmp), sizeof(float) * tmp_floats, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tc_pack)");
+    int rc = 0;
+    for (int l = 0; l < 2 && !rc; ++l) {
+        const int Kp = kp_of_layer(l, m->F);
+        m->tc_wih[l] = reinterpret_cast<__half *>(base + off);
+        off += align_up(sizeof(__half) * 2 * TC_NG * Kp, 256);
+        m->tc_bias[l] = reinterpret_cast<float *>(base + off);
+        off += align_up(sizeof(float) * TC_NG, 256);
+        __half *hi = m->tc_wih[l], *lo = hi + (size_t)TC_NG * Kp;
+        for (int d = 0; d < 2 && !rc; ++d) {
+            float *w = tmp, *bi = tmp + (size_t)TC_G * kin[l], *bh = bi + TC_G;
+            if ((e = cudaMemcpyAsync(w, p->w_ih[l][d], sizeof(float) * TC_G * kin[l], cudaMemcpyDefault, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(bi, p->b_ih[l][d], sizeof(float) * TC_G, cudaMemcpyDefault, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(bh, p->b_hh[l][d], sizeof(float) * TC_G, cudaMemcpyDefault, st)) != cudaSuccess) {
+                rc = cuda_fail(e, "cudaMemcpyAsync(tc_pack)");
+                break;
+            }
+            pack_wih_kernel<<<TC_G, 128, 0, st>>>(w, bi, bh, kin[l], Kp, d, hi, lo, m->tc_bias[l]);
+            if ((e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e, "pack_wih_kernel");
+        }
+    }
+    cudaFreeAsync(tmp, st);
+    if (rc) return rc;
+    m->tc_ready = false;   // flipped to true once the recurrence kernel lands
+    return 0;
+}
+
+// One layer's input projection on the tensor cores.  a_hi/a_lo: [B*T][pitch] fp16 planes.
+int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *a_lo, int pitch_elems, int64_t B, int64_t T,
+              float *xproj /*[2][T][B][960]*/, cudaStream_t st)
+{
+    InprojParams prm;
+    const int Kp = kp_of_layer(layer, m->F);
+    const int kreal = kreal_of_layer(layer, m->F);
+    {
+        const uint64_t dims[3] = {(uint64_t)(layer == 0 ? Kp : kreal), (uint64_t)T, (uint64_t)B};
+        const uint64_t strides[2] = {(uint64_t)pitch_elems * 2, (uint64_t)T * pitch_elems * 2};
+        const uint32_t box[3] = {IP_BK, IP_BM, 1};
+        if (int rc = make_tmap(&prm.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        if (int rc = make_tmap(&prm.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)TC_NG};
+        const uint64_t strides[1] = {(uint64_t)Kp * 2};
+        const uint32_t box[2] = {IP_BK, IP_BN};
+        const __half *hi = m->tc_wih[layer], *lo = hi + (size_t)TC_NG * Kp;
+        if (int rc = make_tmap(&prm.w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        if (int rc = make_tmap(&prm.w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)TC_G, (uint64_t)B, (uint64_t)T, 2};
+        const uint64_t strides[3] = {(uint64_t)TC_G * 4, (uint64_t)B * TC_G * 4, (uint64_t)T * B * TC_G * 4};
+        const uint32_t box[4] = {32, 1, IP_BM, 1};
+        if (int rc = make_tmap(&prm.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xproj, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    prm.bias = m->tc_bias[layer];
+    prm.k_real = kreal;
+    prm.t_tiles = (int)((T + IP_BM - 1) / IP_BM);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(tc_inproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IP_SMEM_BYTES); });
+    dim3 grid((unsigned)(B * prm.t_tiles), TC_NG / IP_BN);
+    ProfScope prof("tc_inproj", st);
+    tc_inproj_kernel<<<grid, 192, IP_SMEM_BYTES, st>>>(prm);
+    HSSB_LAUNCH_OK("tc_inproj_kernel");
+    return 0;
+}
+
+size_t tc_workspace_bytes(const hssb_model *, int64_t, int64_t) { return 0; }
+
+int tc_forward(const hssb_model *, const float *, int64_t, int64_t, const float *, const float *, float *, int32_t *, void *, size_t,
+               cudaStream_t)
+{
+    return fail(HSSB_E_MODEL, "tcgen05 recurrence not built yet");
+}
+
 }  // namespace hssb
+
+// ------------------------------------------------------------------------------------------------
+// Diagnostic entry point: layer-1 input projection only, canonical layout, for kernel-level parity
+// tests (impl 0 = tcgen05 kernel, 1 = SIMT kernel).  xproj: [2][B*T][960] fp32 (torch gate order).
+// workspace: 2*B*T*960*4 + 2*B*T*64*2*2 bytes.
+// ------------------------------------------------------------------------------------------------
+extern "C" int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B, int64_t T, int impl, float *xproj, void *workspace,
+                                 size_t workspace_bytes, void *stream)
+{
+    using namespace hssb;
+    if (!m || !x || !xproj) return fail(HSSB_E_NULL, "hssb_debug_inproj: null pointer");
+    if (B <= 0 || T <= 0) return fail(HSSB_E_SHAPE, "hssb_debug_inproj: bad shape");
+    cudaStream_t st = as_stream(stream);
+    const int64_t M = B * T;
+    if (impl == 1) {
+        for (int d = 0; d < 2; ++d)
+            if (int rc = simt_inproj(x, M, m->F, m->w_ihT[0][d], m->bias[0][d], 4 * m->H, xproj + (size_t)d * M * 4 * m->H, st)) return rc;
+        return 0;
+    }
+    if (m->H != TC_H || m->F > 64 || !m->tc_wih[0]) return fail(HSSB_E_MODEL, "tcgen05 kernels need hidden_size 240");
+    const size_t need = sizeof(float) * 2 * M * TC_G + sizeof(__half) * 2 * M * 64;
+    if (!workspace || workspace_bytes < need) return fail(HSSB_E_WORKSPACE, "hssb_debug_inproj: workspace %zu < %zu", workspace_bytes, need);
+    float *raw = static_cast<float *>(workspace);
+    __half *hi = reinterpret_cast<__half *>(raw + 2 * M * TC_G), *lo = hi + M * 64;
+    split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, hi, lo);
+    HSSB_LAUNCH_OK("split_planes_kernel");
+    if (int rc = tc_inproj(m, 0, hi, lo, 64, B, T, raw, st)) return rc;
+    unpermute_xproj_kernel<<<(unsigned)((2 * M * TC_G + 255) / 256), 256, 0, st>>>(raw, B, T, xproj);
+    HSSB_LAUNCH_OK("unpermute_xproj_kernel");
+    return 0;
+}

@@ -124,6 +124,12 @@ int hssb_model_forward(const hssb_model *m, const float *x, int64_t B, int64_t T
                        const float *c0, float *logp, int32_t *labels, void *workspace,
                        size_t workspace_bytes, int impl, void *stream);
 
+/* Diagnostic: layer-1 input projection only (kernel-level parity tests of K4).  impl 0 = tcgen05
+ * kernel, 1 = SIMT kernel.  xproj [2,B*T,4H] f32 device, torch gate order.  workspace >=
+ * 2*B*T*(4H*4 + 256) bytes. */
+int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B, int64_t T, int impl, float *xproj,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Metric counters: replaces the torchmetrics confusion statistics of main.py:36-62.
  * cm16 [4,4] int64 device, cm[target][pred] += 1 (accumulates; caller zeroes).

@@ -115,4 +115,32 @@ def test_confusion_kernel_and_metrics(lib):
     ref = torch.zeros(4, 4, dtype=torch.int64)
     ref.index_put_((target.reshape(-1), pred.reshape(-1).long()), torch.ones(pred.numel(), dtype=torch.int64), accumulate=True)
     assert torch.equal(cm, ref)
-    assert abs(metrics_from_counts(cm)["micro_accuracy"] - float((pred == target).float().mean())) < 1e-9
+    assert abs(metrics_from_counts(cm)["micro_accuracy"] - float((pred == target).double().mean())) < 1e-9
+
+
+@pytest.mark.parametrize("B,T", [(2, 128), (3, 200), (50, 333)])
+def test_k4_tcgen05_inproj_matches_simt(lib, B, T):
+    """Kernel-level parity of K4 (split-fp16 x3 tcgen05 GEMM) against the fp32 SIMT projection and float64."""
+    from hss import _lib
+
+    m = make_model(5, 44, B, 240)
+    x = (torch.randn(B, T, 44) * 3).cuda()
+    handle = m._packed(x.device)
+    M = B * T
+    ws = torch.empty(2 * M * (960 * 4 + 256), dtype=torch.uint8, device="cuda")
+    outs = []
+    for impl in (0, 1):
+        out = torch.full((2, M, 960), float("nan"), device="cuda")
+        rc = lib.hssb_debug_inproj(handle, x.data_ptr(), B, T, impl, out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "hssb_debug_inproj")
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    xd = x.cpu().double().reshape(M, 44)
+    for d, suffix in enumerate(("", "_reverse")):
+        w = getattr(m.lstm_1, f"weight_ih_l0{suffix}").double()
+        bias = (getattr(m.lstm_1, f"bias_ih_l0{suffix}") + getattr(m.lstm_1, f"bias_hh_l0{suffix}")).double()
+        truth = xd @ w.T + bias
+        err_tc = (outs[0][d].double() - truth).abs().max().item()
+        err_simt = (outs[1][d].double() - truth).abs().max().item()
+        assert not torch.isnan(outs[0][d]).any()
+        assert err_simt < 5e-6 and err_tc < 5e-6, (err_tc, err_simt)
