@@ -6,9 +6,10 @@
 // relative).  That keeps log-probabilities within ~1e-6 of the fp32 reference, which is what the
 // bit-identical-labels requirement needs, at 3 fp16 MMAs per product.
 //
-// "Cluster gate order": the 960 gate rows of one direction are permuted to g' = r*120 + q*30 + u
-// (r = CTA rank in the 8-CTA recurrence cluster, q = gate i/f/g/o, u = unit 0..29 of that rank;
-// torch row = q*240 + 30*r + u), so that every recurrence CTA owns one contiguous 120-wide slice.
+// "Cluster gate order": the 960 gate rows of one direction are permuted to g' = r*120 + 4*u + q
+// (r = CTA rank in the 8-CTA recurrence cluster, u = unit 0..29 of that rank, q = gate i/f/g/o;
+// torch row = q*240 + 30*r + u), so that every recurrence CTA owns one contiguous 120-wide slice and
+// the four gates of a unit sit in four adjacent TMEM lanes (= four adjacent threads of one warp).
 //
 // K4  tc_inproj_kernel : xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']
 //     128(t) x 192(g') output tile per CTA, K blocks of 64 through a 2-stage TMA ring (SW128),
@@ -17,6 +18,8 @@
 #include "tc_ptx.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
+#include <algorithm>
 
 namespace hssb {
 
@@ -85,8 +88,8 @@ __global__ void split_planes_kernel(const float *__restrict__ x, long long M, in
 __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__restrict__ b_ih, const float *__restrict__ b_hh, int Kin,
                                 int Kp, int dir, __half *__restrict__ hi, __half *__restrict__ lo, float *__restrict__ bias)
 {
-    const int gp = blockIdx.x;                     // g' = r*120 + q*30 + u
-    const int r = gp / 120, q = (gp % 120) / 30, u = gp % 30;
+    const int gp = blockIdx.x;                     // g' = r*120 + 4*u + q
+    const int r = gp / 120, u = (gp % 120) / 4, q = gp % 4;
     const int row = q * TC_H + 30 * r + u;
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
         __half h = __float2half_rn(0.f), l = h;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % IP_STAGES;
                 const uint32_t ph = (kb / IP_STAGES) & 1;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(IP_BM, IP_BN);
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % IP_STAGES;
@@ -236,7 +239,7 @@ __global__ void unpermute_xproj_kernel(const float *__restrict__ src, long long 
     const int gp = (int)(i % TC_G);
     const long long rest = i / TC_G;
     const long long b = rest % B, t = (rest / B) % T, dir = rest / (B * T);
-    const int r = gp / 120, q = (gp % 120) / 30, u = gp % 30;
+    const int r = gp / 120, u = (gp % 120) / 4, q = gp % 4;
     dst[((size_t)dir * B * T + b * T + t) * TC_G + q * TC_H + 30 * r + u] = src[i];
 }
 
@@ -349,20 +352,24 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
 //
 // Orientation: gates are the MMA M dimension and stay put, the batch is N:
 //     G^T[g' (128 lanes), b (NB cols)] = W_hh,slice[g', k] . h_{t-1}^T[k, b]  (+ xproj^T added in the epilogue)
-// CTA rank r owns units 30r..30r+29 -> gate rows q*32+u (q = i,f,g,o; u < 30; rows 30,31 of every
-// quadrant are zero padding) so every gate of a unit sits in one warp's TMEM lane quadrant.
+// CTA rank r owns units 30r..30r+29 -> gate rows (TMEM lanes) 4*u + q (q = i,f,g,o; lanes 120..127 are zero
+// padding), so the four gates of a unit are four adjacent lanes of one warp.
 //   * W_hh slice (hi and lo fp16 planes, K padded 240 -> 8*32) is loaded ONCE into TMEM columns
 //     [0,256) and is the A operand of every MMA (tcgen05.mma with A in TMEM) -- weights never move.
 //   * h_{t-1}^T lives in shared memory as the B operand (K-major, no swizzle, [rank][plane][k-chunk][b][8]).
 //     After its epilogue each CTA owns 30 fresh h values per batch column; it writes them as an fp16
-//     hi/lo "image" and its producer thread pushes that image into the B buffer of all 8 CTAs with
+//     hi/lo "image" and one elected thread pushes that image into the B buffer of all 8 CTAs with
 //     cp.async.bulk shared::cta -> shared::cluster, completing on the receiver's mbarrier
 //     (the all-gather of the recurrence, no global memory round trip, no cluster barrier).
-//   * Epilogue per step: tcgen05.ld the 128 x NB accumulator, add xproj (TMA-prefetched tile),
-//     sigmoid/tanh per quadrant, exchange the activated gates through smem, then c/h update with the
-//     cell state in registers.
+//   * Epilogue per step (4 warps per sub-tile, one TMEM lane quadrant each): tcgen05.ld the 32 x NB
+//     accumulator slice, add xproj (plain coalesced 128-byte loads, prefetched one step ahead into
+//     registers), branch-free sigmoid / tanh (tanh x = 2 sigmoid 2x - 1; MUFU.EX2 + MUFU.RCP), 4x4
+//     lane transposes (shfl.xor 1, 2) that hand thread (u, j) the four gates of unit u for the batch
+//     columns b = j (mod 4), then the c/h update with the cell state in registers.  No shared-memory
+//     round trip and no block barrier between the gate activations and the cell update.
 // Sub-tiles: S independent groups of NB batch columns are interleaved per cluster so that the tensor
-// pipe (sub-tile A's MMAs) overlaps the MUFU/LSU work of sub-tile B's epilogue and the DSMEM hops.
+// pipe (one sub-tile's MMAs) overlaps the MUFU work of another's epilogue and the DSMEM all-gather of
+// the third.
 // ------------------------------------------------------------------------------------------------
 constexpr int RC_CL = 8;            // CTAs per cluster
 constexpr int RC_U = 30;            // real units per CTA
@@ -373,18 +380,17 @@ template <int NB, int S>
 struct RcCfg {
     static constexpr int HBUF_BYTES = NB * RC_KP * 2 * 2;       // one B-operand buffer: hi+lo planes (NB KB)
     static constexpr int SLICE_BYTES = NB * 32 * 2 * 2;         // one rank's image: [plane][4 chunks][NB][8] fp16
-    static constexpr int XP_BYTES = NB * RC_XW * 4;
-    static constexpr int GBUF_BYTES = 4 * NB * 32 * 4;
-    static constexpr int PER_SUB = 2 * HBUF_BYTES + 2 * SLICE_BYTES + XP_BYTES + GBUF_BYTES;
-    static constexpr int BAR_BYTES = 512;
+    static constexpr int PER_SUB = 2 * HBUF_BYTES + 2 * SLICE_BYTES;
+    static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = S * PER_SUB + BAR_BYTES + 1024;
-    static constexpr int THREADS = 32 * (1 + S) + 128 * S;
+    static constexpr int THREADS = 32 * S + 128 * S;         // S MMA-issuer warps + S epilogue groups of 4 warps
     static_assert(NB % 16 == 0 && NB <= 64, "NB must be 16, 32, 48 or 64");
     static_assert(S * NB <= 256, "accumulators must fit in the TMEM columns left of the weights");
+    static_assert(3 * S * 8 <= BAR_BYTES - 8, "barrier area too small");
 };
 
 struct RecurParams {
-    CUtensorMap xproj;          // [g'(960), b, t, dir] fp32, box (120, NB, 1, 1), no swizzle
+    const float *xproj;         // [dir][t][b][g'(960)] fp32 (cluster gate order)
     const __half *whh;          // [dir][rank][plane][128][256] fp16 (cluster gate order, zero padded)
     const float *h0, *c0;       // [2][B][240]
     float *hn, *cn;             // [2][B][240]  raw final state
@@ -392,10 +398,46 @@ struct RecurParams {
     float *out_f32;             // layer 2: relu(h) [B*T][480]         (nullptr for layer 1)
     long long B, T;
     int b_base;                 // first batch column handled by this launch
+    int groups;                 // groups of S*NB columns per direction in this launch
+    int stagger_ns;             // initial phase offset between the sub-tiles of a cluster
+    unsigned long long *trace;  // diagnostic (hssb_debug_trace): clock64 stamps of cluster 0 / rank 0, or nullptr
+    int trace_steps;
 };
 
-__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float fast_tanh(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
+// trace events (per step, per sub-tile): see scripts/trace_recurrent.py
+enum { TR_MMA_HFULL = 0, TR_MMA_ISSUED, TR_EPI_DFULL, TR_EPI_ACT, TR_EPI_CELL, TR_EPI_IMAGE, TR_EPI_COPIES, TR_EVENTS = 16 };
+#define HSSB_TRACE(ev, step, sub)                                                                         \
+    do {                                                                                                  \
+        if (p.trace && blockIdx.x == 0 && (step) >= 0 && (step) < p.trace_steps)                          \
+            p.trace[(((step) * 4 + (sub)) * TR_EVENTS) + (ev)] = clock64();                               \
+    } while (0)
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 4x4 transpose across the 4 lanes of a quad: in r[c] = a[lane j][c]  ->  out r[g] = a[lane g][j]
+__device__ __forceinline__ void quad_transpose(float (&r)[4], int j)
+{
+    const bool o1 = (j & 1) != 0, o2 = (j & 2) != 0;
+    float s0 = o1 ? r[0] : r[1], s1 = o1 ? r[2] : r[3];
+    s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+    s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (o1) { r[0] = s0; r[2] = s1; } else { r[1] = s0; r[3] = s1; }
+    s0 = o2 ? r[0] : r[2];
+    s1 = o2 ? r[1] : r[3];
+    s0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    if (o2) { r[0] = s0; r[1] = s1; } else { r[2] = s0; r[3] = s1; }
+}
 
 template <int NB, int S>
 __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(const __grid_constant__ RecurParams p)
@@ -403,18 +445,12 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
     using C = RcCfg<NB, S>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    // per sub-tile regions
     auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * C::HBUF_BYTES; };
     auto image = [&](int s, int par) { return smem + s * C::PER_SUB + 2 * C::HBUF_BYTES + par * C::SLICE_BYTES; };
-    auto xpst = [&](int s) { return reinterpret_cast<float *>(smem + s * C::PER_SUB + 2 * C::HBUF_BYTES + 2 * C::SLICE_BYTES); };
-    auto gbuf = [&](int s) { return reinterpret_cast<float *>(smem + s * C::PER_SUB + 2 * C::HBUF_BYTES + 2 * C::SLICE_BYTES + C::XP_BYTES); };
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S * C::PER_SUB);
     uint64_t *h_full = bars;                 // [S][2]
     uint64_t *d_full = bars + 2 * S;         // [S]
-    uint64_t *xp_full = bars + 3 * S;        // [S]
-    uint64_t *xp_empty = bars + 4 * S;       // [S]
-    uint64_t *img_ready = bars + 5 * S;      // [S]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 * S);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -422,17 +458,14 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
     const int dir = cid & 1;
     const int group = cid >> 1;
     const long long T = p.T, B = p.B;
+    auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * NB; };
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&p.xproj);
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&h_full[2 * s], 1); mbar_init(&h_full[2 * s + 1], 1);
-            mbar_init(&d_full[s], 1); mbar_init(&xp_full[s], 1); mbar_init(&xp_empty[s], 4); mbar_init(&img_ready[s], 4);
-        }
+        for (int s = 0; s < S; ++s) { mbar_init(&h_full[2 * s], 1); mbar_init(&h_full[2 * s + 1], 1); mbar_init(&d_full[s], 1); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
-    // zero the images (padding slots u = 30, 31 must be finite zeros forever)
+    // zero the buffers (padding slots u = 30, 31 of every image must be finite zeros forever)
     for (int i = threadIdx.x; i < S * C::PER_SUB / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
@@ -440,67 +473,48 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
     const uint32_t tmem_base = *tmem_slot;
     cluster_sync();     // every CTA's barriers are initialised before any remote copy can target them
 
-    constexpr int EPI0 = 1 + S;   // first epilogue warp
-    if (warp == 0) {
-        // ================= MMA issuer =================
-        // wait until the weights are in TMEM (loaded by epilogue group 0, signalled through a named barrier)
-        named_barrier(8, 32 + 128);
+    if (warp < S) {
+        // ================= MMA issuer of sub-tile s = warp (one elected thread) =================
+        const int s = warp;
+        named_barrier(S + 1, 32 * S + 128);      // weights are in TMEM (loaded by epilogue group 0)
         tc_fence_after();
-        if (lane == 0) {
+        if (sub_b0(s) < B && elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, NB);
+            const uint32_t d_tmem = tmem_base + 256 + s * NB;
             for (long long t = 0; t < T; ++t) {
-                for (int s = 0; s < S; ++s) {
-                    const int par = (int)(t & 1);
-                    mbar_wait_cluster(&h_full[2 * s + par], (uint32_t)((t >> 1) & 1));
-                    tc_fence_after();
-                    const uint32_t hb = smem_u32(hbuf(s, par));
-                    const uint32_t d_tmem = tmem_base + 256 + s * NB;
+                const int par = (int)(t & 1);
+                mbar_wait_cluster(&h_full[2 * s + par], (uint32_t)((t >> 1) & 1));
+                tc_fence_after();
+                HSSB_TRACE(TR_MMA_HFULL, t, s);
+                const uint32_t hb = smem_u32(hbuf(s, par));
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t blk = hb + (j >> 1) * (NB * 128) + (j & 1) * (NB * 32);
-                        const uint64_t b_hi = make_smem_desc(blk, NB * 16, 128, LAYOUT_NONE);
-                        const uint64_t b_lo = make_smem_desc(blk + NB * 64, NB * 16, 128, LAYOUT_NONE);
-                        const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
-                        mma_f16_ts(d_tmem, a_hi, b_hi, idesc, j != 0);
-                        mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                        mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
-                    }
-                    mma_commit(&d_full[s]);
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t blk = hb + (j >> 1) * (NB * 128) + (j & 1) * (NB * 32);
+                    const uint64_t b_hi = make_smem_desc(blk, NB * 16, 128, LAYOUT_NONE);
+                    const uint64_t b_lo = make_smem_desc(blk + NB * 64, NB * 16, 128, LAYOUT_NONE);
+                    const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
+                    mma_f16_ts(d_tmem, a_hi, b_hi, idesc, j != 0);
+                    mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                    mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
                 }
-            }
-        }
-    } else if (warp < EPI0) {
-        // ================= producer for sub-tile s: xproj TMA prefetch + all-gather pushes =================
-        const int s = warp - 1;
-        if (lane == 0) {
-            const int b0 = p.b_base + (group * S + s) * NB;
-            for (long long t = -1; t + 1 < T; ++t) {
-                const long long n = t + 1;                         // the step being prepared
-                const int tt = (int)(dir ? (T - 1 - n) : n);
-                mbar_wait(&xp_empty[s], (uint32_t)((n & 1) ^ 1));
-                mbar_arrive_expect_tx(&xp_full[s], C::XP_BYTES);
-                tma_load_4d(xpst(s), &p.xproj, &xp_full[s], rank * RC_XW, b0, tt, dir);
-                const int par = (int)(n & 1);                      // buffer that receives h_t for step n
-                mbar_arrive_expect_tx(&h_full[2 * s + par], C::HBUF_BYTES);
-                mbar_wait(&img_ready[s], (uint32_t)(n & 1));
-                const unsigned char *img = image(s, (int)(t & 1));
-                unsigned char *dst = hbuf(s, par) + rank * C::SLICE_BYTES;
-#pragma unroll
-                for (uint32_t j = 0; j < RC_CL; ++j) bulk_copy_to_cta(dst, img, C::SLICE_BYTES, &h_full[2 * s + par], j);
+                mma_commit(&d_full[s]);
+                HSSB_TRACE(TR_MMA_ISSUED, t, s);
             }
         }
     } else {
-        // ================= epilogue group s =================
-        const int s = (warp - EPI0) >> 2;
-        const int q = warp & 3;                  // TMEM lane quadrant == gate (i, f, g, o)
-        const int u = lane;
+        // ================= epilogue group s: warps S+4s .. S+4s+3 =================
+        const int s = (warp - S) >> 2;
+        const int q = warp & 3;                  // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;           // TMEM lane = gate row 4*u + j of this CTA
+        const int u = row >> 2, j = lane & 3;    // unit 0..31 (30, 31 padding), gate / column residue
         const bool unit_ok = u < RC_U;
-        const int b0 = p.b_base + (group * S + s) * NB;
+        const long long b0 = sub_b0(s);
         const int hcol = dir * TC_H + (int)rank * RC_U + u;      // column in the [.., 480] outputs
+        const bool leader = (warp == S + 4 * s);
 
         if (s == 0) {
-            // one-time: W_hh slice -> TMEM.  Thread (q,u) owns lane q*32+u; column c holds k' = 2c, 2c+1.
-            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + (q * 32 + u)) * RC_KP;
+            // one-time: W_hh slice -> TMEM.  This thread owns lane `row`; column c holds k' = 2c, 2c+1.
+            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + row) * RC_KP;
 #pragma unroll 1
             for (int plane = 0; plane < 2; ++plane) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
@@ -513,80 +527,132 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
             }
             tmem_st_wait();
             tc_fence_before();
-            named_barrier(8, 32 + 128);
+            named_barrier(S + 1, 32 * S + 128);
         }
 
-        float c_state[NB / 4];
-        float *gb = gbuf(s);
-        const float *xp = xpst(s);
-        for (long long t = -1; t < T; ++t) {
-            const int tt = (int)(dir ? (T - 1 - t) : t);
-            if (t >= 0) {
-                mbar_wait(&d_full[s], (uint32_t)(t & 1));
-                tc_fence_after();
-                mbar_wait(&xp_full[s], (uint32_t)(t & 1));
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * NB;
+        if (b0 < B) {
+            constexpr int NI = NB / 4;
+            constexpr float LOG2E = 1.4426950408889634f;
+            // sigmoid for i, f, o; tanh x = 2 sigmoid(2x) - 1 for g: act = ksc * rcp(1 + 2^(nsc * x)) + kof
+            const float ksc = (j == 2) ? 2.0f : 1.0f, nsc = -ksc * LOG2E, kof = 1.0f - ksc;
+            const int ncols = (int)((B - b0 < NB) ? (B - b0) : NB);
+            const bool full = ncols == NB;
+            const int ni_valid = (ncols - j + 3) / 4;                   // columns 4i + j < ncols  <=>  i < ni_valid
+            // xproj of this thread's gate row (padding lanes re-read row 119, result unused):
+            // element (t, b) at xp_base + (t*B + b)*960
+            const int xrow = unit_ok ? row : RC_XW - 1;
+            const float *xp_base = p.xproj + (size_t)dir * T * B * TC_G + (size_t)b0 * TC_G + rank * RC_XW + xrow;
+            const long long xstep = (dir ? -1 : 1) * B * TC_G;          // one time step
+            const float *xp_next = xp_base + (dir ? (size_t)(T - 1) * B * TC_G : 0);
+            float c_state[NI], hv[NI], xnext[NB];
+            auto load_x = [&]() {                                        // xproj of the next step -> registers
+                if (full) {
 #pragma unroll
-                for (int c16 = 0; c16 < NB / 16; ++c16) {
-                    uint32_t v[16];
-                    tmem_ld_x16(taddr + c16 * 16, v);
+                    for (int b = 0; b < NB; ++b) xnext[b] = __ldcs(xp_next + b * TC_G);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) xnext[b] = (b < ncols) ? __ldcs(xp_next + b * TC_G) : 0.0f;
+                }
+                xp_next += xstep;
+            };
+            load_x();
+            // outputs of (unit u, column 4i + j): element offset of step tt = o_base + i*o_stride + tt*480
+            const size_t o_stride = (size_t)4 * T * (2 * TC_H);
+            size_t o_next = ((size_t)(b0 + j) * T + (dir ? T - 1 : 0)) * (2 * TC_H) + hcol;
+            const long long o_step = (dir ? -1 : 1) * (2 * TC_H);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * NB;
+            if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const long long bg = b0 + 4 * i + j;
+                const bool ok = unit_ok && i < ni_valid;
+                hv[i] = ok ? __ldg(p.h0 + ((size_t)dir * B + bg) * TC_H + rank * RC_U + u) : 0.f;
+                c_state[i] = ok ? __ldg(p.c0 + ((size_t)dir * B + bg) * TC_H + rank * RC_U + u) : 0.f;
+            }
+            for (long long t = -1; t < T; ++t) {
+                if (t >= 0) {
+                    mbar_wait(&d_full[s], (uint32_t)(t & 1));
+                    tc_fence_after();
+                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_DFULL, t, s);
+                    uint32_t v[NB];
+#pragma unroll
+                    for (int c16 = 0; c16 < NB / 16; ++c16) tmem_ld_x16(taddr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
                     tmem_ld_wait();
+                    tc_fence_before();
+                    float act[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) act[b] = (__uint_as_float(v[b]) + xnext[b]) * nsc;
+                    if (t + 1 < T) load_x();               // lands during this step's math and the all-gather
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) act[b] = fmaf(rcp_approx(1.0f + ex2_approx(act[b])), ksc, kof);
+                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_ACT, t, s);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        float g4[4] = {act[4 * i], act[4 * i + 1], act[4 * i + 2], act[4 * i + 3]};
+                        quad_transpose(g4, j);                         // -> i, f, g, o of (unit u, column 4i + j)
+                        const float c = fmaf(g4[1], c_state[i], g4[0] * g4[2]);
+                        c_state[i] = c;
+                        const float th = fmaf(rcp_approx(1.0f + ex2_approx(c * (-2.0f * LOG2E))), 2.0f, -1.0f);
+                        hv[i] = unit_ok ? g4[3] * th : 0.0f;
+                    }
+                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_CELL, t, s);
+                }
+                // h_t of (unit u, columns 4i + j) -> fp16 hi/lo image [plane][k-chunk q][b][8 units]
+                if (t + 1 < T) {
+                    __half *img_hi = reinterpret_cast<__half *>(image(s, (int)(t & 1))) + q * (NB * 8) + j * 8 + (lane >> 2);
+                    __half *img_lo = img_hi + NB * 32;
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        __half hh, hl;
+                        split_f16(hv[i], hh, hl);
+                        img_hi[i * 32] = hh;
+                        img_lo[i * 32] = hl;
+                    }
+                    fence_proxy_async_smem();
+                    named_barrier(1 + s, 128);
+                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_IMAGE, t, s);
+                    if (leader) {
+                        // all-gather: this CTA's image -> slot `rank` of every CTA's B buffer for step t+1;
+                        // lane r pushes to CTA r
+                        const int par = (int)((t + 1) & 1);
+                        if (lane == 0) mbar_arrive_expect_tx(&h_full[2 * s + par], C::HBUF_BYTES);
+                        __syncwarp();
+                        if (lane < RC_CL)
+                            bulk_copy_to_cta(hbuf(s, par) + rank * C::SLICE_BYTES, image(s, (int)(t & 1)), C::SLICE_BYTES, &h_full[2 * s + par], lane);
+                    }
+                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_COPIES, t, s);
+                }
+                // ---- off the critical path: this step's outputs to global memory ----
+                if (t >= 0) {
                     if (unit_ok) {
+                        size_t o = o_next;
+                        if (p.out_f32) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int b = c16 * 16 + i;
-                            const float pre = __uint_as_float(v[i]) + xp[b * RC_XW + q * RC_U + u];
-                            gb[(q * NB + b) * 32 + u] = (q == 2) ? fast_tanh(pre) : fast_sigmoid(pre);
+                            for (int i = 0; i < NI; ++i, o += o_stride)
+                                if (i < ni_valid) p.out_f32[o] = fmaxf(hv[i], 0.f);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < NI; ++i, o += o_stride)
+                                if (i < ni_valid) {
+                                    __half hh, hl;
+                                    split_f16(fmaxf(hv[i], 0.f), hh, hl);
+                                    p.out_hi[o] = hh;
+                                    p.out_lo[o] = hl;
+                                }
                         }
                     }
+                    o_next += o_step;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&xp_empty[s]);
-                tc_fence_before();
-                named_barrier(1 + s, 128);
             }
-            // ---- phase 2: thread (q,u) updates unit u for batch columns b = q, q+4, ... ----
-            __half *img_hi = reinterpret_cast<__half *>(image(s, (int)(t & 1)));
-            __half *img_lo = img_hi + NB * 32;
+            if (unit_ok) {
 #pragma unroll
-            for (int i = 0; i < NB / 4; ++i) {
-                const int b = q + 4 * i;
-                const long long bg = b0 + b;
-                float h = 0.f;
-                if (t < 0) {
-                    const bool ok = unit_ok && bg < B;
-                    h = ok ? __ldg(p.h0 + ((size_t)dir * B + bg) * TC_H + rank * RC_U + u) : 0.f;
-                    c_state[i] = ok ? __ldg(p.c0 + ((size_t)dir * B + bg) * TC_H + rank * RC_U + u) : 0.f;
-                } else if (unit_ok) {
-                    const float ig = gb[(0 * NB + b) * 32 + u], fg = gb[(1 * NB + b) * 32 + u];
-                    const float gg = gb[(2 * NB + b) * 32 + u], og = gb[(3 * NB + b) * 32 + u];
-                    const float c = fmaf(fg, c_state[i], ig * gg);
-                    c_state[i] = c;
-                    h = og * fast_tanh(c);
-                    if (bg < B) {
-                        const size_t o = ((size_t)bg * T + tt) * (2 * TC_H) + hcol;
-                        const float hr = fmaxf(h, 0.f);
-                        if (p.out_f32) p.out_f32[o] = hr;
-                        else { __half hh, hl; split_f16(hr, hh, hl); p.out_hi[o] = hh; p.out_lo[o] = hl; }
-                        if (t == T - 1) {
-                            p.hn[((size_t)dir * B + bg) * TC_H + rank * RC_U + u] = h;
-                            p.cn[((size_t)dir * B + bg) * TC_H + rank * RC_U + u] = c;
-                        }
+                for (int i = 0; i < NI; ++i)
+                    if (i < ni_valid) {
+                        const size_t o = ((size_t)dir * B + b0 + 4 * i + j) * TC_H + rank * RC_U + u;
+                        p.hn[o] = hv[i];
+                        p.cn[o] = c_state[i];
                     }
-                }
-                if (unit_ok) {
-                    __half hh, hl;
-                    split_f16(h, hh, hl);
-                    const int off = (u >> 3) * (NB * 8) + b * 8 + (u & 7);
-                    img_hi[off] = hh;
-                    img_lo[off] = hl;
-                }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&img_ready[s]);
-            // gbuf is rewritten in the next step's phase 1 only after d_full, i.e. after every thread's
-            // phase-2 reads of this step (the image of this step gates the next MMA).
         }
     }
     tc_fence_before();
@@ -595,11 +661,11 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-// torch W_hh[960][240] -> planes [dir][rank][plane][128 rows q*32+u][256 k' = 32 r' + u']
+// torch W_hh[960][240] -> planes [dir][rank][plane][128 rows 4*u+q][256 k' = 32 r' + u']
 __global__ void pack_whh_kernel(const float *__restrict__ w, int dir, __half *__restrict__ dst)
 {
     const int rank = blockIdx.x / 128, row = blockIdx.x % 128;
-    const int q = row / 32, u = row % 32;
+    const int u = row / 4, q = row % 4;              // TMEM lane = 4*unit + gate
     __half *hi = dst + ((((size_t)dir * RC_CL + rank) * 2 + 0) * 128 + row) * RC_KP;
     __half *lo = dst + ((((size_t)dir * RC_CL + rank) * 2 + 1) * 128 + row) * RC_KP;
     for (int kp = threadIdx.x; kp < RC_KP; kp += blockDim.x) {
@@ -611,31 +677,67 @@ __global__ void pack_whh_kernel(const float *__restrict__ w, int dir, __half *__
     }
 }
 
+static unsigned long long *g_trace_buf = nullptr;
+static int g_trace_steps = 0;
+
 template <int NB, int S>
-static int launch_recurrent(const RecurParams &prm_in, int groups, float *xproj, cudaStream_t st)
+static cudaLaunchConfig_t recurrent_config(int clusters, cudaStream_t st, cudaLaunchAttribute *attr)
 {
     using C = RcCfg<NB, S>;
-    RecurParams prm = prm_in;
-    {
-        const uint64_t dims[4] = {(uint64_t)TC_G, (uint64_t)prm.B, (uint64_t)prm.T, 2};
-        const uint64_t strides[3] = {(uint64_t)TC_G * 4, (uint64_t)prm.B * TC_G * 4, (uint64_t)prm.T * prm.B * TC_G * 4};
-        const uint32_t box[4] = {RC_XW, NB, 1, 1};
-        if (int rc = make_tmap(&prm.xproj, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xproj, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-    }
-    cudaError_t e = cudaFuncSetAttribute(tc_recurrent_kernel<NB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_kernel)");
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
+    cfg.gridDim = dim3((unsigned)(clusters * RC_CL));
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    return cfg;
+}
+
+// How many 8-CTA clusters of this geometry are co-resident on the current device (cached per geometry).
+template <int NB, int S>
+static int max_resident_clusters(int *out)
+{
+    using C = RcCfg<NB, S>;
+    static int cached = 0;
+    if (!cached) {
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_kernel<NB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_kernel)");
+        cudaLaunchAttribute attr[1];
+        cudaLaunchConfig_t cfg = recurrent_config<NB, S>(16, nullptr, attr);
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_kernel<NB, S>, &cfg);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_kernel)");
+        if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
+        cached = n;
+    }
+    *out = cached;
+    return 0;
+}
+
+template <int NB, int S>
+static int launch_recurrent(const RecurParams &prm_in, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
+{
+    RecurParams prm = prm_in;
+    prm.trace = g_trace_buf;
+    prm.trace_steps = g_trace_steps;
+    int max_clusters = 0;
+    if (int rc = max_resident_clusters<NB, S>(&max_clusters)) return rc;
+    // one cluster per (direction, group): never launch more groups than are co-resident, a second wave
+    // of clusters would double the latency of the whole launch
+    const int per = NB * S;
+    const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);
+    *cols_done = groups * per;
+    prm.xproj = xproj;
+    prm.groups = groups;
+    prm.stagger_ns = 800;
+    if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = recurrent_config<NB, S>(2 * groups, st, attr);
     ProfScope prof("tc_recurrent", st);
-    e = cudaLaunchKernelEx(&cfg, tc_recurrent_kernel<NB, S>, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_kernel<NB, S>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_kernel)");
     return 0;
 }
@@ -651,14 +753,36 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
     prm.B = B; prm.T = T;
     // at most 8 groups per direction are co-resident (16 clusters of 8 CTAs on 148 SMs); larger batches
     // run as successive launches over blocks of batch columns
+    // Geometry: as few batch columns per cluster as the co-resident clusters allow (the DSMEM all-gather
+    // volume per CTA and step is 1 KB per column), S sub-tiles of NB columns each.
+    // HSSB_RC_GEOM="NB,S" forces one geometry (experiments).
+    int force_nb = 0, force_s = 0;
+    if (const char *e = getenv("HSSB_RC_GEOM")) sscanf(e, "%d,%d", &force_nb, &force_s);
+    int max_clusters = 0;
+    if (int rc = max_resident_clusters<32, 3>(&max_clusters)) return rc;
+    const int max_groups = max_clusters / 2;
     for (int64_t base = 0; base < B;) {
         const int64_t rem = B - base;
         prm.b_base = (int)base;
-        int rc;
-        if (rem <= 8 * 16) { const int g = (int)((rem + 15) / 16); rc = launch_recurrent<16, 1>(prm, g, xproj, st); base += (int64_t)g * 16; }
-        else if (rem <= 8 * 32) { const int g = (int)((rem + 31) / 32); rc = launch_recurrent<32, 1>(prm, g, xproj, st); base += (int64_t)g * 32; }
-        else { const int g = (int)std::min<int64_t>(8, (rem + 63) / 64); rc = launch_recurrent<32, 2>(prm, g, xproj, st); base += (int64_t)g * 64; }
+        const int64_t per_group = (rem + max_groups - 1) / max_groups;
+        int nb, s;
+        if (force_nb) { nb = force_nb; s = force_s; }
+        else if (per_group <= 16) { nb = 16; s = 1; }
+        else if (per_group <= 32) { nb = 16; s = 2; }
+        else if (per_group <= 48) { nb = 16; s = 3; }
+        else if (per_group <= 64) { nb = 32; s = 2; }
+        else { nb = 32; s = 3; }
+        int rc, done = 0;
+        if (nb == 16 && s == 1) rc = launch_recurrent<16, 1>(prm, rem, &done, xproj, st);
+        else if (nb == 16 && s == 2) rc = launch_recurrent<16, 2>(prm, rem, &done, xproj, st);
+        else if (nb == 16 && s == 3) rc = launch_recurrent<16, 3>(prm, rem, &done, xproj, st);
+        else if (nb == 32 && s == 1) rc = launch_recurrent<32, 1>(prm, rem, &done, xproj, st);
+        else if (nb == 32 && s == 2) rc = launch_recurrent<32, 2>(prm, rem, &done, xproj, st);
+        else if (nb == 32 && s == 3) rc = launch_recurrent<32, 3>(prm, rem, &done, xproj, st);
+        else if (nb == 48 && s == 2) rc = launch_recurrent<48, 2>(prm, rem, &done, xproj, st);
+        else return fail(HSSB_E_MODE, "HSSB_RC_GEOM=%d,%d unsupported", nb, s);
         if (rc) return rc;
+        base += done;
     }
     return 0;
 }
@@ -710,6 +834,22 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
 }
 
 }  // namespace hssb
+
+// Diagnostic: clock64 stamps of the recurrence roles (cluster 0, rank 0) for the first `steps` steps of every
+// following recurrence launch; buf = steps*4*16 uint64 on the device, nullptr disables.
+extern "C" int hssb_debug_max_clusters(void)
+{
+    int n = 0;
+    if (hssb::max_resident_clusters<32, 3>(&n)) return -1;
+    return n;
+}
+
+extern "C" int hssb_debug_trace(unsigned long long *buf, int steps)
+{
+    hssb::g_trace_buf = buf;
+    hssb::g_trace_steps = buf ? steps : 0;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Diagnostic entry point: layer-1 input projection only, canonical layout, for kernel-level parity

@@ -48,13 +48,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta)
         "r"(cta)
         : "memory");
 }
+// upper bound (ns) the hardware may keep a waiting thread suspended before try_wait returns false:
+// long enough that waiting warps do not burn issue slots; completion of the phase wakes the thread
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
         : "memory");
     return ok != 0;
 }
@@ -68,9 +71,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
     uint32_t ok;
     do {
         asm volatile(
-            "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+            "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
             : "memory");
     } while (!ok);
 }

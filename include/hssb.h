@@ -130,6 +130,13 @@ int hssb_model_forward(const hssb_model *m, const float *x, int64_t B, int64_t T
 int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B, int64_t T, int impl, float *xproj,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Diagnostic: clock64 stamps of the recurrence kernel's roles (cluster 0, CTA rank 0) for the first
+ * `steps` steps of every following recurrence launch.  buf: steps*4*16 uint64 on the device; NULL
+ * disables.  Read by scripts/trace_recurrent.py. */
+int hssb_debug_trace(unsigned long long *buf, int steps);
+/* Diagnostic: co-resident 8-CTA recurrence clusters (geometry 32x3) on the current device; <0 on error. */
+int hssb_debug_max_clusters(void);
+
 /* ------------------------------------------------------------------------------------------
  * Metric counters: replaces the torchmetrics confusion statistics of main.py:36-62.
  * cm16 [4,4] int64 device, cm[target][pred] += 1 (accumulates; caller zeroes).
