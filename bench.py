@@ -33,7 +33,9 @@ NWIN = 128
 BAND = (25, 200)
 K_BINS, KT = 65, 22
 WINDOWS_PER_GPU = 512       # BASELINE config 4 shard
-FLOP_PER_SAMPLE = {"inproj": 2.012e6, "recurrent": 1.843e6, "head": 3.84e3}   # SURVEY 8a (useful, 1x)
+# useful FLOPs (1x, the fp32 contraction) per PCG sample of every launch of the kernel in one step
+FLOP_PER_SAMPLE = {"tc_inproj_l0": 2 * 44 * 1920.0, "tc_inproj_l1": 2 * 480 * 1920.0, "simt_inproj": 2 * (44 + 480) * 1920.0,
+                   "tc_recurrent": 2 * 2 * 240 * 1920.0, "simt_recurrent": 2 * 2 * 240 * 1920.0}
 BYTES_PER_SAMPLE = {"stft_hop1": 4 + 2 * K_BINS * 8, "if_reassign": 2 * K_BINS * 8 + KT * 8, "normalise": 16 * KT * 2}
 
 
@@ -264,9 +266,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             if name in BYTES_PER_SAMPLE:
                 gbs = BYTES_PER_SAMPLE[name] * units / (per_launch_ms * 1e-3) / 1e9
                 entry.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]})
-            elif name.endswith("inproj") or name.endswith("recurrent"):
-                kind = "inproj" if name.endswith("inproj") else "recurrent"
-                tf = FLOP_PER_SAMPLE[kind] * units / (tot / args.steps * 1e-3) / 1e12
+            elif name in FLOP_PER_SAMPLE:
+                tf = FLOP_PER_SAMPLE[name] * units / (tot / args.steps * 1e-3) / 1e12
                 entry.update({"bound": "tensor", "achieved": tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tensor_tflops"],
                               "note": "useful FLOPs (1x) over all launches of this kernel in a step"})
             per_kernel[name] = entry

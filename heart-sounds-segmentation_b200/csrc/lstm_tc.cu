@@ -11,9 +11,8 @@
 // torch row = q*240 + 30*r + u), so that every recurrence CTA owns one contiguous 120-wide slice and
 // the four gates of a unit sit in four adjacent TMEM lanes (= four adjacent threads of one warp).
 //
-// K4  tc_inproj_kernel : xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']
-//     128(t) x 192(g') output tile per CTA, K blocks of 64 through a 2-stage TMA ring (SW128),
-//     accumulators in TMEM, epilogue TMEM -> regs -> swizzled smem -> TMA store.
+// K4  tc_inproj_kernel : xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']   (see the kernel)
+// K5  tc_recurrent_kernel : the T sequential steps, 8-CTA clusters, weights resident in TMEM (see the kernel)
 #include "model.cuh"
 #include "tc_ptx.cuh"
 #include <cudaTypedefs.h>
@@ -101,23 +100,41 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4
+// K4: input projection GEMM, persistent + warp specialised, clusters of 8 CTAs (4 along M x 2 along N).
+//
+//   xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']          M = B*T, N = 1920, K = 48 / 480
+//
+// Per CTA one 128(t) x 192(g') output tile at a time; three fp16 MMAs per product (hi*hi, lo*hi, hi*lo).
+// The operands come out of L2, whose bandwidth (~7 TB/s, the same order as HBM) is what bounded the first
+// version of this kernel: a lone CTA re-reads (128 + 192) x K x 4 bytes per tile.  Here the eight CTAs of a
+// cluster work on 4 consecutive m-tiles x 2 consecutive n-tiles and share their loads by TMA multicast:
+// the A stage (128 rows) is fetched in two halves by the two CTAs of a column and multicast to both, the
+// W stage (192 rows) in four quarters by the four CTAs of a row -> (128/2 + 192/4) rows per CTA and stage.
+//   warp 0   : TMA producer (2-stage ring of 80 KB stages, BK = 64, SW128)
+//   warp 1   : tcgen05.mma issuer; accumulators double-buffered in TMEM (2 x 192 columns) so that the
+//              epilogue of tile i overlaps the main loop of tile i+1; smem stages are released to all
+//              CTAs that write into this one with a multicast tcgen05.commit
+//   warps 2-5: epilogue TMEM -> registers (+bias) -> swizzled smem -> TMA store
 // ------------------------------------------------------------------------------------------------
 constexpr int IP_BM = 128, IP_BN = 192, IP_BK = 64, IP_STAGES = 2;
+constexpr int IP_CM = 4, IP_CN = 2, IP_CL = IP_CM * IP_CN;   // cluster shape
 constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (16 KB)
 constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (24 KB)
 constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 80 KB
 constexpr int IP_OUT_BYTES = IP_BM * 32 * 4;             // epilogue staging tile 128 x 32 fp32 (16 KB)
 constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + 2 * IP_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int IP_TMEM_COLS = 256;
+constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 192 columns (at 0 and 256)
+constexpr int IP_N_TILES = TC_NG / IP_BN;                // 10
+static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
 
 struct InprojParams {
-    CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (64,128,1), SW128
-    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (64,192), SW128
+    CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (64, 64, 1), SW128   (half of the A stage)
+    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (64, 48), SW128  (quarter of the W stage)
     CUtensorMap out;          // [g'(960), b, t, dir] fp32, box (32,1,128,1), SW128
     const float *bias;        // [1920]
-    int k_real;               // true K (44->64 padded planes use 64; 480)
+    int k_real;               // true K rounded up to 16 (48 / 480)
     int t_tiles;              // ceil(T/128)
+    int m_groups;             // ceil(B * t_tiles / 4)
 };
 
 __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant__ InprojParams p)
@@ -127,19 +144,22 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
     unsigned char *stage_base = smem;
     unsigned char *out_base = smem + IP_STAGES * IP_STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + 2 * IP_OUT_BYTES);
-    uint64_t *full = bars, *empty = bars + IP_STAGES, *tmem_full = bars + 2 * IP_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * IP_STAGES + 1);
+    uint64_t *full = bars, *empty = bars + IP_STAGES, *tmem_full = bars + 2 * IP_STAGES, *tmem_empty = bars + 2 * IP_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * IP_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / p.t_tiles;
-    const int t0 = (blockIdx.x % p.t_tiles) * IP_BM;
-    const int n0 = blockIdx.y * IP_BN;              // over 1920 = both directions
+    const uint32_t rank = cluster_ctarank();
+    const int cx = rank % IP_CM, cy = rank / IP_CM;                // position in the cluster: m / n
+    const uint16_t mask_a = (uint16_t)((1u << cx) | (1u << (cx + IP_CM)));          // CTAs sharing my A tile
+    const uint16_t mask_w = (uint16_t)(((1u << IP_CM) - 1u) << (IP_CM * cy));       // CTAs sharing my W tile
     const int kblocks = (p.k_real + IP_BK - 1) / IP_BK;
+    const int cluster_id = blockIdx.x / IP_CL, n_clusters = gridDim.x / IP_CL;
+    const int n_items = p.m_groups * (IP_N_TILES / IP_CN);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.a_hi); prefetch_tmap(&p.a_lo); prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo); prefetch_tmap(&p.out);
-        for (int s = 0; s < IP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < IP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], IP_CM + IP_CN - 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<IP_TMEM_COLS>(tmem_slot);
@@ -147,86 +167,115 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    cluster_sync();     // barriers of every CTA exist before any multicast can target them
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % IP_STAGES;
-                const uint32_t ph = (kb / IP_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                unsigned char *st = stage_base + s * IP_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[s], IP_STAGE_BYTES);
-                tma_load_3d(st, &p.a_hi, &full[s], kb * IP_BK, t0, b);
-                tma_load_3d(st + IP_A_BYTES, &p.a_lo, &full[s], kb * IP_BK, t0, b);
-                tma_load_2d(st + 2 * IP_A_BYTES, &p.w_hi, &full[s], kb * IP_BK, n0);
-                tma_load_2d(st + 2 * IP_A_BYTES + IP_B_BYTES, &p.w_lo, &full[s], kb * IP_BK, n0);
+            uint32_t it = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int m_tile = (item / (IP_N_TILES / IP_CN)) * IP_CM + cx;
+                const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * IP_BM;
+                const int n0 = ((item % (IP_N_TILES / IP_CN)) * IP_CN + cy) * IP_BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % IP_STAGES;
+                    mbar_wait_cluster(&empty[s], ((it / IP_STAGES) & 1) ^ 1);
+                    unsigned char *st = stage_base + s * IP_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[s], IP_STAGE_BYTES);
+                    // my half of the A tile (rows cy*64 ..) -> both CTAs of my cluster column
+                    tma_load_3d_mc(st + cy * (IP_A_BYTES / 2), &p.a_hi, &full[s], kb * IP_BK, t0 + cy * (IP_BM / 2), b, mask_a);
+                    tma_load_3d_mc(st + IP_A_BYTES + cy * (IP_A_BYTES / 2), &p.a_lo, &full[s], kb * IP_BK, t0 + cy * (IP_BM / 2), b, mask_a);
+                    // my quarter of the W tile (rows cx*48 ..) -> the four CTAs of my cluster row
+                    tma_load_2d_mc(st + 2 * IP_A_BYTES + cx * (IP_B_BYTES / 4), &p.w_hi, &full[s], kb * IP_BK, n0 + cx * (IP_BN / 4), mask_w);
+                    tma_load_2d_mc(st + 2 * IP_A_BYTES + IP_B_BYTES + cx * (IP_B_BYTES / 4), &p.w_lo, &full[s], kb * IP_BK, n0 + cx * (IP_BN / 4), mask_w);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(IP_BM, IP_BN);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % IP_STAGES;
-                const uint32_t ph = (kb / IP_STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            const uint16_t mask_rel = mask_a | mask_w;     // every CTA that writes into my stages
+            uint32_t it = 0, tile = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters, ++tile) {
+                const uint32_t acc = tile & 1;
+                mbar_wait(&tmem_empty[acc], ((tile >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(stage_base + s * IP_STAGE_BYTES);
-                const uint32_t a_lo = a_hi + IP_A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * IP_A_BYTES;
-                const uint32_t b_lo = b_hi + IP_B_BYTES;
-                const int ksteps = min(IP_BK, p.k_real - kb * IP_BK + 15) / 16;   // skip all-padding K16 steps
-                for (int ks = 0; ks < ksteps && ks < IP_BK / 16; ++ks) {
-                    const uint32_t off = ks * 32;   // 16 fp16 = 32 bytes inside the 128-byte swizzle row
-                    const uint64_t da_hi = make_smem_desc(a_hi + off, 16, 1024, LAYOUT_SW128);
-                    const uint64_t da_lo = make_smem_desc(a_lo + off, 16, 1024, LAYOUT_SW128);
-                    const uint64_t db_hi = make_smem_desc(b_hi + off, 16, 1024, LAYOUT_SW128);
-                    const uint64_t db_lo = make_smem_desc(b_lo + off, 16, 1024, LAYOUT_SW128);
-                    mma_f16_ss(tmem_base, da_hi, db_hi, idesc, (kb | ks) != 0);
-                    mma_f16_ss(tmem_base, da_lo, db_hi, idesc, 1);
-                    mma_f16_ss(tmem_base, da_hi, db_lo, idesc, 1);
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % IP_STAGES;
+                    mbar_wait_cluster(&full[s], (it / IP_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(stage_base + s * IP_STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + IP_A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * IP_A_BYTES;
+                    const uint32_t b_lo = b_hi + IP_B_BYTES;
+                    const int ksteps = min(IP_BK, p.k_real - kb * IP_BK) / 16;   // skip all-padding K16 steps
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t off = ks * 32;   // 16 fp16 = 32 bytes inside the 128-byte swizzle row
+                        const uint64_t da_hi = make_smem_desc(a_hi + off, 16, 1024, LAYOUT_SW128);
+                        const uint64_t da_lo = make_smem_desc(a_lo + off, 16, 1024, LAYOUT_SW128);
+                        const uint64_t db_hi = make_smem_desc(b_hi + off, 16, 1024, LAYOUT_SW128);
+                        const uint64_t db_lo = make_smem_desc(b_lo + off, 16, 1024, LAYOUT_SW128);
+                        mma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
+                        mma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1);
+                        mma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1);
+                    }
+                    mma_commit_mc(&empty[s], mask_rel);    // frees this stage in every CTA that fills it
                 }
-                mma_commit(&empty[s]);          // frees the smem stage when these MMAs retire
+                mma_commit(&tmem_full[acc]);               // accumulator complete
             }
-            mma_commit(tmem_full);              // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
         const int q = warp & 3;
         const int row = q * 32 + lane;          // tile row = time index t0 + row
         const int et = threadIdx.x - 64;        // 0..127
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int dir = n0 / TC_G, nl0 = n0 % TC_G;
-        for (int c = 0; c < IP_BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-            tmem_ld_wait();
-            unsigned char *ob = out_base + (c & 1) * IP_OUT_BYTES;
-            if (c >= 2 && et == 0) tma_store_wait_read<1>();     // the store that last used this buffer has read it
-            named_barrier(1, 128);
-            const float *bias = p.bias + n0 + c * 32;
+        uint32_t tile = 0, chunk = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++tile) {
+            const int m_tile = (item / (IP_N_TILES / IP_CN)) * IP_CM + cx;
+            const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * IP_BM;
+            const int n0 = ((item % (IP_N_TILES / IP_CN)) * IP_CN + cy) * IP_BN;
+            const int dir = n0 / TC_G, nl0 = n0 % TC_G;
+            const uint32_t acc = tile & 1;
+            mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
+            tc_fence_after();
+            for (int c = 0; c < IP_BN / 32; ++c, ++chunk) {
+                uint32_t v[32];
+                tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c * 32, v);
+                tmem_ld_wait();
+                if (c == IP_BN / 32 - 1) {                  // accumulator drained: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                unsigned char *ob = out_base + (chunk & 1) * IP_OUT_BYTES;
+                if (chunk >= 2 && et == 0) tma_store_wait_read<1>();     // the store that last used this buffer has read it
+                named_barrier(1, 128);
+                const float *bias = p.bias + n0 + c * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o;
-                o.x = __uint_as_float(v[4 * j + 0]) + __ldg(bias + 4 * j + 0);
-                o.y = __uint_as_float(v[4 * j + 1]) + __ldg(bias + 4 * j + 1);
-                o.z = __uint_as_float(v[4 * j + 2]) + __ldg(bias + 4 * j + 2);
-                o.w = __uint_as_float(v[4 * j + 3]) + __ldg(bias + 4 * j + 3);
-                *reinterpret_cast<float4 *>(ob + row * 128 + ((j ^ (row & 7)) << 4)) = o;   // 128B swizzle
-            }
-            fence_proxy_async_smem();
-            named_barrier(1, 128);
-            if (et == 0) {
-                tma_store_4d(&p.out, ob, nl0 + c * 32, b, t0, dir);
-                tma_store_commit();
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bj = __ldg(reinterpret_cast<const float4 *>(bias) + j);
+                    float4 o;
+                    o.x = __uint_as_float(v[4 * j + 0]) + bj.x;
+                    o.y = __uint_as_float(v[4 * j + 1]) + bj.y;
+                    o.z = __uint_as_float(v[4 * j + 2]) + bj.z;
+                    o.w = __uint_as_float(v[4 * j + 3]) + bj.w;
+                    *reinterpret_cast<float4 *>(ob + row * 128 + ((j ^ (row & 7)) << 4)) = o;   // 128B swizzle
+                }
+                fence_proxy_async_smem();
+                named_barrier(1, 128);
+                if (et == 0) {
+                    tma_store_4d(&p.out, ob, nl0 + c * 32, b, t0, dir);
+                    tma_store_commit();
+                }
             }
         }
         if (et == 0) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync();     // nobody leaves while peers may still multicast into / arrive on this CTA
     if (warp == 1) tmem_dealloc<IP_TMEM_COLS>(tmem_base);
 }
 
@@ -317,14 +366,14 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     {
         const uint64_t dims[3] = {(uint64_t)(layer == 0 ? Kp : kreal), (uint64_t)T, (uint64_t)B};
         const uint64_t strides[2] = {(uint64_t)pitch_elems * 2, (uint64_t)T * pitch_elems * 2};
-        const uint32_t box[3] = {IP_BK, IP_BM, 1};
+        const uint32_t box[3] = {IP_BK, IP_BM / IP_CN, 1};
         if (int rc = make_tmap(&prm.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
         if (int rc = make_tmap(&prm.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
     {
         const uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)TC_NG};
         const uint64_t strides[1] = {(uint64_t)Kp * 2};
-        const uint32_t box[2] = {IP_BK, IP_BN};
+        const uint32_t box[2] = {IP_BK, IP_BN / IP_CM};
         const __half *hi = m->tc_wih[layer], *lo = hi + (size_t)TC_NG * Kp;
         if (int rc = make_tmap(&prm.w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
         if (int rc = make_tmap(&prm.w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
@@ -338,12 +387,33 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     prm.bias = m->tc_bias[layer];
     prm.k_real = kreal;
     prm.t_tiles = (int)((T + IP_BM - 1) / IP_BM);
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(tc_inproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IP_SMEM_BYTES); });
-    dim3 grid((unsigned)(B * prm.t_tiles), TC_NG / IP_BN);
-    ProfScope prof("tc_inproj", st);
-    tc_inproj_kernel<<<grid, 192, IP_SMEM_BYTES, st>>>(prm);
-    HSSB_LAUNCH_OK("tc_inproj_kernel");
+    prm.m_groups = (int)((B * prm.t_tiles + IP_CM - 1) / IP_CM);
+
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = IP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = IP_SMEM_BYTES;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_clusters = 0;
+    if (!max_clusters) {
+        cudaError_t e = cudaFuncSetAttribute(tc_inproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IP_SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_inproj_kernel)");
+        cfg.gridDim = dim3(IP_CL * 16);
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, tc_inproj_kernel, &cfg);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_inproj_kernel)");
+        if (n < 1) return fail(HSSB_E_DEVICE, "device cannot host an input-projection cluster");
+        max_clusters = n;
+    }
+    const int n_items = prm.m_groups * (IP_N_TILES / IP_CN);
+    cfg.gridDim = dim3((unsigned)(IP_CL * std::min(max_clusters, n_items)));
+    ProfScope prof(layer == 0 ? "tc_inproj_l0" : "tc_inproj_l1", st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_inproj_kernel, prm);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_inproj_kernel)");
     return 0;
 }
 
