@@ -446,17 +446,22 @@ constexpr int RC_U = 30;            // real units per CTA
 constexpr int RC_KP = 256;          // padded K (8 ranks x 32 slots)
 constexpr int RC_XW = 4 * RC_U;     // xproj floats per (t, b) owned by one CTA (120)
 
-template <int NB, int S>
+// PAIR: the two CTAs of a TPC issue one tcgen05.mma.cta_group::2 (M = 256 gate rows, N = NB columns) whose B
+// operand is split between them (NB/2 columns each), so each CTA receives only half of the all-gather.
+template <int NB, int S, bool PAIR>
 struct RcCfg {
-    static constexpr int HBUF_BYTES = NB * RC_KP * 2 * 2;       // one B-operand buffer: hi+lo planes (NB KB)
-    static constexpr int SLICE_BYTES = NB * 32 * 2 * 2;         // one rank's image: [plane][4 chunks][NB][8] fp16
-    static constexpr int PER_SUB = 2 * HBUF_BYTES + 2 * SLICE_BYTES;
+    static constexpr int NBH = PAIR ? NB / 2 : NB;              // batch columns of the B operand held by one CTA
+    static constexpr int SLICE_BYTES = NBH * 32 * 2 * 2;        // one rank's slot: [plane][4 chunks][NBH][8] fp16
+    static constexpr int HBUF_BYTES = RC_CL * SLICE_BYTES;      // one B-operand buffer (hi+lo planes)
+    static constexpr int IMG_BYTES = NB * 32 * 2 * 2;           // this CTA's h_t of all NB columns ([half] x slot layout)
+    static constexpr int PER_SUB = 2 * HBUF_BYTES + 2 * IMG_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = S * PER_SUB + BAR_BYTES + 1024;
     static constexpr int THREADS = 32 * S + 128 * S;         // S MMA-issuer warps + S epilogue groups of 4 warps
     static_assert(NB % 16 == 0 && NB <= 64, "NB must be 16, 32, 48 or 64");
     static_assert(S * NB <= 256, "accumulators must fit in the TMEM columns left of the weights");
-    static_assert(3 * S * 8 <= BAR_BYTES - 8, "barrier area too small");
+    static_assert(5 * S * 8 <= BAR_BYTES - 8, "barrier area too small");
+    static_assert(!PAIR || NB % 32 == 0, "pair mode splits NB in two halves of a multiple of 16 columns");
 };
 
 struct RecurParams {
@@ -509,18 +514,20 @@ __device__ __forceinline__ void quad_transpose(float (&r)[4], int j)
     if (o2) { r[0] = s0; r[1] = s1; } else { r[2] = s0; r[3] = s1; }
 }
 
-template <int NB, int S>
-__global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(const __grid_constant__ RecurParams p)
+template <int NB, int S, bool PAIR>
+__global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_kernel(const __grid_constant__ RecurParams p)
 {
-    using C = RcCfg<NB, S>;
+    using C = RcCfg<NB, S, PAIR>;
+    constexpr int NBH = C::NBH;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * C::HBUF_BYTES; };
-    auto image = [&](int s, int par) { return smem + s * C::PER_SUB + 2 * C::HBUF_BYTES + par * C::SLICE_BYTES; };
+    auto image = [&](int s, int par) { return smem + s * C::PER_SUB + 2 * C::HBUF_BYTES + par * C::IMG_BYTES; };
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S * C::PER_SUB);
-    uint64_t *h_full = bars;                 // [S][2]
-    uint64_t *d_full = bars + 2 * S;         // [S]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S);
+    uint64_t *h_full = bars;                 // [S][2]  my B-operand buffer is complete
+    uint64_t *d_full = bars + 2 * S;         // [S]     accumulator complete
+    uint64_t *peer_full = bars + 3 * S;      // [S][2]  (pair leader) the odd CTA's buffer is complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 * S);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -531,10 +538,14 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
     auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * NB; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&h_full[2 * s], 1); mbar_init(&h_full[2 * s + 1], 1); mbar_init(&d_full[s], 1); }
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&h_full[2 * s], 1); mbar_init(&h_full[2 * s + 1], 1); mbar_init(&d_full[s], 1);
+            mbar_init(&peer_full[2 * s], 1); mbar_init(&peer_full[2 * s + 1], 1);
+        }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    if (PAIR) cluster_sync();                // both CTAs of a pair are resident before the paired TMEM allocation
+    if (warp == 0) { if (PAIR) tmem_alloc2<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
     // zero the buffers (padding slots u = 30, 31 of every image must be finite zeros forever)
     for (int i = threadIdx.x; i < S * C::PER_SUB / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
@@ -549,26 +560,43 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
         named_barrier(S + 1, 32 * S + 128);      // weights are in TMEM (loaded by epilogue group 0)
         tc_fence_after();
         if (sub_b0(s) < B && elect_one()) {
-            constexpr uint32_t idesc = make_idesc_f16(128, NB);
-            const uint32_t d_tmem = tmem_base + 256 + s * NB;
-            for (long long t = 0; t < T; ++t) {
-                const int par = (int)(t & 1);
-                mbar_wait_cluster(&h_full[2 * s + par], (uint32_t)((t >> 1) & 1));
-                tc_fence_after();
-                HSSB_TRACE(TR_MMA_HFULL, t, s);
-                const uint32_t hb = smem_u32(hbuf(s, par));
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t blk = hb + (j >> 1) * (NB * 128) + (j & 1) * (NB * 32);
-                    const uint64_t b_hi = make_smem_desc(blk, NB * 16, 128, LAYOUT_NONE);
-                    const uint64_t b_lo = make_smem_desc(blk + NB * 64, NB * 16, 128, LAYOUT_NONE);
-                    const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
-                    mma_f16_ts(d_tmem, a_hi, b_hi, idesc, j != 0);
-                    mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                    mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
+            if (PAIR && (rank & 1)) {
+                // odd CTA of a pair: tell the leader when my half of the B operand has landed
+                for (long long t = 0; t < T; ++t) {
+                    const int par = (int)(t & 1);
+                    mbar_wait_cluster(&h_full[2 * s + par], (uint32_t)((t >> 1) & 1));
+                    mbar_arrive_remote(&peer_full[2 * s + par], rank ^ 1u);
                 }
-                mma_commit(&d_full[s]);
-                HSSB_TRACE(TR_MMA_ISSUED, t, s);
+            } else {
+                constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, NB);
+                const uint32_t d_tmem = tmem_base + 256 + s * NB;
+                const uint16_t pair_mask = (uint16_t)(3u << (rank & ~1u));
+                for (long long t = 0; t < T; ++t) {
+                    const int par = (int)(t & 1);
+                    mbar_wait_cluster(&h_full[2 * s + par], (uint32_t)((t >> 1) & 1));
+                    if (PAIR) mbar_wait_cluster(&peer_full[2 * s + par], (uint32_t)((t >> 1) & 1));
+                    tc_fence_after();
+                    HSSB_TRACE(TR_MMA_HFULL, t, s);
+                    const uint32_t hb = smem_u32(hbuf(s, par));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t blk = hb + (j >> 1) * (NBH * 128) + (j & 1) * (NBH * 32);
+                        const uint64_t b_hi = make_smem_desc(blk, NBH * 16, 128, LAYOUT_NONE);
+                        const uint64_t b_lo = make_smem_desc(blk + NBH * 64, NBH * 16, 128, LAYOUT_NONE);
+                        const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
+                        if (PAIR) {
+                            mma_f16_ts2(d_tmem, a_hi, b_hi, idesc, j != 0);
+                            mma_f16_ts2(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_f16_ts2(d_tmem, a_hi, b_lo, idesc, 1);
+                        } else {
+                            mma_f16_ts(d_tmem, a_hi, b_hi, idesc, j != 0);
+                            mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
+                    }
+                    if (PAIR) mma_commit2_mc(&d_full[s], pair_mask); else mma_commit(&d_full[s]);
+                    HSSB_TRACE(TR_MMA_ISSUED, t, s);
+                }
             }
         }
     } else {
@@ -669,14 +697,16 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
                 }
                 // h_t of (unit u, columns 4i + j) -> fp16 hi/lo image [plane][k-chunk q][b][8 units]
                 if (t + 1 < T) {
-                    __half *img_hi = reinterpret_cast<__half *>(image(s, (int)(t & 1))) + q * (NB * 8) + j * 8 + (lane >> 2);
-                    __half *img_lo = img_hi + NB * 32;
+                    // (pair mode: columns [0, NB/2) form the half sent to the even CTAs, the rest goes to the odd ones)
+                    __half *img_hi = reinterpret_cast<__half *>(image(s, (int)(t & 1))) + q * (NBH * 8) + j * 8 + (lane >> 2);
+                    __half *img_lo = img_hi + NBH * 32;
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         __half hh, hl;
                         split_f16(hv[i], hh, hl);
-                        img_hi[i * 32] = hh;
-                        img_lo[i * 32] = hl;
+                        const int off = (4 * i >= NBH) ? (NBH * 64 + (4 * i - NBH) * 8) : 4 * i * 8;   // [half][plane][chunk][col][8]
+                        img_hi[off] = hh;
+                        img_lo[off] = hl;
                     }
                     fence_proxy_async_smem();
                     named_barrier(1 + s, 128);
@@ -688,7 +718,8 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
                         if (lane == 0) mbar_arrive_expect_tx(&h_full[2 * s + par], C::HBUF_BYTES);
                         __syncwarp();
                         if (lane < RC_CL)
-                            bulk_copy_to_cta(hbuf(s, par) + rank * C::SLICE_BYTES, image(s, (int)(t & 1)), C::SLICE_BYTES, &h_full[2 * s + par], lane);
+                            bulk_copy_to_cta(hbuf(s, par) + rank * C::SLICE_BYTES, image(s, (int)(t & 1)) + (PAIR ? (lane & 1) * C::SLICE_BYTES : 0),
+                                             C::SLICE_BYTES, &h_full[2 * s + par], lane);
                     }
                     if (leader && lane == 0) HSSB_TRACE(TR_EPI_COPIES, t, s);
                 }
@@ -728,7 +759,7 @@ __global__ void __launch_bounds__(RcCfg<NB, S>::THREADS, 1) tc_recurrent_kernel(
     tc_fence_before();
     __syncthreads();
     cluster_sync();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
+    if (warp == 0) { if (PAIR) tmem_dealloc2<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }
 
 // torch W_hh[960][240] -> planes [dir][rank][plane][128 rows 4*u+q][256 k' = 32 r' + u']
@@ -750,10 +781,10 @@ __global__ void pack_whh_kernel(const float *__restrict__ w, int dir, __half *__
 static unsigned long long *g_trace_buf = nullptr;
 static int g_trace_steps = 0;
 
-template <int NB, int S>
+template <int NB, int S, bool PAIR>
 static cudaLaunchConfig_t recurrent_config(int clusters, cudaStream_t st, cudaLaunchAttribute *attr)
 {
-    using C = RcCfg<NB, S>;
+    using C = RcCfg<NB, S, PAIR>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * RC_CL));
     cfg.blockDim = dim3(C::THREADS);
@@ -767,18 +798,18 @@ static cudaLaunchConfig_t recurrent_config(int clusters, cudaStream_t st, cudaLa
 }
 
 // How many 8-CTA clusters of this geometry are co-resident on the current device (cached per geometry).
-template <int NB, int S>
+template <int NB, int S, bool PAIR>
 static int max_resident_clusters(int *out)
 {
-    using C = RcCfg<NB, S>;
+    using C = RcCfg<NB, S, PAIR>;
     static int cached = 0;
     if (!cached) {
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_kernel<NB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_kernel<NB, S, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_kernel)");
         cudaLaunchAttribute attr[1];
-        cudaLaunchConfig_t cfg = recurrent_config<NB, S>(16, nullptr, attr);
+        cudaLaunchConfig_t cfg = recurrent_config<NB, S, PAIR>(16, nullptr, attr);
         int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_kernel<NB, S>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_kernel<NB, S, PAIR>, &cfg);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         cached = n;
@@ -787,14 +818,14 @@ static int max_resident_clusters(int *out)
     return 0;
 }
 
-template <int NB, int S>
+template <int NB, int S, bool PAIR>
 static int launch_recurrent(const RecurParams &prm_in, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
 {
     RecurParams prm = prm_in;
     prm.trace = g_trace_buf;
     prm.trace_steps = g_trace_steps;
     int max_clusters = 0;
-    if (int rc = max_resident_clusters<NB, S>(&max_clusters)) return rc;
+    if (int rc = max_resident_clusters<NB, S, PAIR>(&max_clusters)) return rc;
     // one cluster per (direction, group): never launch more groups than are co-resident, a second wave
     // of clusters would double the latency of the whole launch
     const int per = NB * S;
@@ -805,9 +836,9 @@ static int launch_recurrent(const RecurParams &prm_in, int64_t rem, int *cols_do
     prm.stagger_ns = 800;
     if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
     cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg = recurrent_config<NB, S>(2 * groups, st, attr);
+    cudaLaunchConfig_t cfg = recurrent_config<NB, S, PAIR>(2 * groups, st, attr);
     ProfScope prof("tc_recurrent", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_kernel<NB, S>, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_kernel<NB, S, PAIR>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_kernel)");
     return 0;
 }
@@ -825,32 +856,39 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
     // run as successive launches over blocks of batch columns
     // Geometry: as few batch columns per cluster as the co-resident clusters allow (the DSMEM all-gather
     // volume per CTA and step is 1 KB per column), S sub-tiles of NB columns each.
-    // HSSB_RC_GEOM="NB,S" forces one geometry (experiments).
-    int force_nb = 0, force_s = 0;
-    if (const char *e = getenv("HSSB_RC_GEOM")) sscanf(e, "%d,%d", &force_nb, &force_s);
+    // HSSB_RC_GEOM="NB,S[,pair]" forces one geometry (experiments).
+    int force_nb = 0, force_s = 0, force_pair = -1;
+    if (const char *e = getenv("HSSB_RC_GEOM")) sscanf(e, "%d,%d,%d", &force_nb, &force_s, &force_pair);
     int max_clusters = 0;
-    if (int rc = max_resident_clusters<32, 3>(&max_clusters)) return rc;
+    if (int rc = max_resident_clusters<32, 3, false>(&max_clusters)) return rc;
     const int max_groups = max_clusters / 2;
     for (int64_t base = 0; base < B;) {
         const int64_t rem = B - base;
         prm.b_base = (int)base;
         const int64_t per_group = (rem + max_groups - 1) / max_groups;
-        int nb, s;
-        if (force_nb) { nb = force_nb; s = force_s; }
-        else if (per_group <= 16) { nb = 16; s = 1; }
-        else if (per_group <= 32) { nb = 16; s = 2; }
-        else if (per_group <= 48) { nb = 16; s = 3; }
-        else if (per_group <= 64) { nb = 32; s = 2; }
-        else { nb = 32; s = 3; }
+        int nb, s, pair;
+        if (force_nb) { nb = force_nb; s = force_s; pair = force_pair < 0 ? (nb % 32 == 0) : force_pair; }
+        else if (per_group <= 16) { nb = 16; s = 1; pair = 0; }
+        else if (per_group <= 32) { nb = 16; s = 2; pair = 0; }
+        else if (per_group <= 48) { nb = 16; s = 3; pair = 0; }
+        else if (per_group <= 64) { nb = 32; s = 2; pair = 0; }
+        else { nb = 32; s = 3; pair = 0; }
+        // (the CTA-pair variants -- cta_group::2, half the all-gather volume -- are validated but measured slower on
+        //  B200: at N = 32 the paired MMA is issue-overhead bound, ~30 cycles each against ~18 for cta_group::1)
         int rc, done = 0;
-        if (nb == 16 && s == 1) rc = launch_recurrent<16, 1>(prm, rem, &done, xproj, st);
-        else if (nb == 16 && s == 2) rc = launch_recurrent<16, 2>(prm, rem, &done, xproj, st);
-        else if (nb == 16 && s == 3) rc = launch_recurrent<16, 3>(prm, rem, &done, xproj, st);
-        else if (nb == 32 && s == 1) rc = launch_recurrent<32, 1>(prm, rem, &done, xproj, st);
-        else if (nb == 32 && s == 2) rc = launch_recurrent<32, 2>(prm, rem, &done, xproj, st);
-        else if (nb == 32 && s == 3) rc = launch_recurrent<32, 3>(prm, rem, &done, xproj, st);
-        else if (nb == 48 && s == 2) rc = launch_recurrent<48, 2>(prm, rem, &done, xproj, st);
-        else return fail(HSSB_E_MODE, "HSSB_RC_GEOM=%d,%d unsupported", nb, s);
+        const int key = nb * 100 + s * 10 + pair;
+        switch (key) {
+        case 1610: rc = launch_recurrent<16, 1, false>(prm, rem, &done, xproj, st); break;
+        case 1620: rc = launch_recurrent<16, 2, false>(prm, rem, &done, xproj, st); break;
+        case 1630: rc = launch_recurrent<16, 3, false>(prm, rem, &done, xproj, st); break;
+        case 3220: rc = launch_recurrent<32, 2, false>(prm, rem, &done, xproj, st); break;
+        case 3230: rc = launch_recurrent<32, 3, false>(prm, rem, &done, xproj, st); break;
+        case 3211: rc = launch_recurrent<32, 1, true>(prm, rem, &done, xproj, st); break;
+        case 3221: rc = launch_recurrent<32, 2, true>(prm, rem, &done, xproj, st); break;
+        case 3231: rc = launch_recurrent<32, 3, true>(prm, rem, &done, xproj, st); break;
+        case 3241: rc = launch_recurrent<32, 4, true>(prm, rem, &done, xproj, st); break;
+        default: return fail(HSSB_E_MODE, "HSSB_RC_GEOM=%d,%d,%d unsupported", nb, s, pair);
+        }
         if (rc) return rc;
         base += done;
     }
@@ -910,7 +948,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
 extern "C" int hssb_debug_max_clusters(void)
 {
     int n = 0;
-    if (hssb::max_resident_clusters<32, 3>(&n)) return -1;
+    if (hssb::max_resident_clusters<32, 3, false>(&n)) return -1;
     return n;
 }
 
