@@ -110,17 +110,18 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 // cluster work on 4 consecutive m-tiles x 2 consecutive n-tiles and share their loads by TMA multicast:
 // the A stage (128 rows) is fetched in two halves by the two CTAs of a column and multicast to both, the
 // W stage (192 rows) in four quarters by the four CTAs of a row -> (128/2 + 192/4) rows per CTA and stage.
-//   warp 0   : TMA producer (2-stage ring of 80 KB stages, BK = 64, SW128)
+//   warp 0   : TMA producer (4-stage ring of 40 KB stages, BK = 32, SW64: the refill of a stage waits for the
+//              slowest of the 5 CTAs that read it, so depth matters more than stage size)
 //   warp 1   : tcgen05.mma issuer; accumulators double-buffered in TMEM (2 x 192 columns) so that the
 //              epilogue of tile i overlaps the main loop of tile i+1; smem stages are released to all
 //              CTAs that write into this one with a multicast tcgen05.commit
 //   warps 2-5: epilogue TMEM -> registers (+bias) -> swizzled smem -> TMA store
 // ------------------------------------------------------------------------------------------------
-constexpr int IP_BM = 128, IP_BN = 192, IP_BK = 64, IP_STAGES = 2;
+constexpr int IP_BM = 128, IP_BN = 192, IP_BK = 32, IP_STAGES = 4;   // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
 constexpr int IP_CM = 4, IP_CN = 2, IP_CL = IP_CM * IP_CN;   // cluster shape
-constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (16 KB)
-constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (24 KB)
-constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 80 KB
+constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (8 KB)
+constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (12 KB)
+constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 40 KB
 constexpr int IP_OUT_BYTES = IP_BM * 32 * 4;             // epilogue staging tile 128 x 32 fp32 (16 KB)
 constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + 2 * IP_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 192 columns (at 0 and 256)
@@ -128,8 +129,8 @@ constexpr int IP_N_TILES = TC_NG / IP_BN;                // 10
 static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
 
 struct InprojParams {
-    CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (64, 64, 1), SW128   (half of the A stage)
-    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (64, 48), SW128  (quarter of the W stage)
+    CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (32, 64, 1), SW64   (half of the A stage)
+    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 48), SW64  (quarter of the W stage)
     CUtensorMap out;          // [g'(960), b, t, dir] fp32, box (32,1,128,1), SW128
     const float *bias;        // [1920]
     int k_real;               // true K rounded up to 16 (48 / 480)
@@ -212,11 +213,11 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
                     const uint32_t b_lo = b_hi + IP_B_BYTES;
                     const int ksteps = min(IP_BK, p.k_real - kb * IP_BK) / 16;   // skip all-padding K16 steps
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t off = ks * 32;   // 16 fp16 = 32 bytes inside the 128-byte swizzle row
-                        const uint64_t da_hi = make_smem_desc(a_hi + off, 16, 1024, LAYOUT_SW128);
-                        const uint64_t da_lo = make_smem_desc(a_lo + off, 16, 1024, LAYOUT_SW128);
-                        const uint64_t db_hi = make_smem_desc(b_hi + off, 16, 1024, LAYOUT_SW128);
-                        const uint64_t db_lo = make_smem_desc(b_lo + off, 16, 1024, LAYOUT_SW128);
+                        const uint32_t off = ks * 32;   // 16 fp16 = 32 bytes inside the 64-byte swizzle row
+                        const uint64_t da_hi = make_smem_desc(a_hi + off, 16, 512, LAYOUT_SW64);
+                        const uint64_t da_lo = make_smem_desc(a_lo + off, 16, 512, LAYOUT_SW64);
+                        const uint64_t db_hi = make_smem_desc(b_hi + off, 16, 512, LAYOUT_SW64);
+                        const uint64_t db_lo = make_smem_desc(b_lo + off, 16, 512, LAYOUT_SW64);
                         mma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
                         mma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1);
                         mma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1);
@@ -367,16 +368,16 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
         const uint64_t dims[3] = {(uint64_t)(layer == 0 ? Kp : kreal), (uint64_t)T, (uint64_t)B};
         const uint64_t strides[2] = {(uint64_t)pitch_elems * 2, (uint64_t)T * pitch_elems * 2};
         const uint32_t box[3] = {IP_BK, IP_BM / IP_CN, 1};
-        if (int rc = make_tmap(&prm.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-        if (int rc = make_tmap(&prm.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        if (int rc = make_tmap(&prm.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+        if (int rc = make_tmap(&prm.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
     {
         const uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)TC_NG};
         const uint64_t strides[1] = {(uint64_t)Kp * 2};
         const uint32_t box[2] = {IP_BK, IP_BN / IP_CM};
         const __half *hi = m->tc_wih[layer], *lo = hi + (size_t)TC_NG * Kp;
-        if (int rc = make_tmap(&prm.w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-        if (int rc = make_tmap(&prm.w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        if (int rc = make_tmap(&prm.w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+        if (int rc = make_tmap(&prm.w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
     {
         const uint64_t dims[4] = {(uint64_t)TC_G, (uint64_t)B, (uint64_t)T, 2};
