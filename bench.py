@@ -239,13 +239,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    wall = [time.perf_counter()]
     for _ in range(args.steps):
         labels, cm = step(x_host.to(dev, non_blocking=True))
         labels_host.copy_(labels, non_blocking=True)
         cm_host = cm.cpu()
+        wall.append(time.perf_counter())
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    if os.environ.get("HSSB_BENCH_DEBUG"):
+        print("e2e wall per step (ms):", [round(1e3 * (b - a), 3) for a, b in zip(wall, wall[1:])], "events total", ms_e2e, file=sys.stderr)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:

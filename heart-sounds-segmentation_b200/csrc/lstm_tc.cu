@@ -27,11 +27,18 @@ using namespace ptx;
 constexpr int TC_H = 240;
 constexpr int TC_G = 960;          // gate rows per direction
 constexpr int TC_NG = 2 * TC_G;    // both directions
+// "slot layout" of the hidden state handed from one layer to the next: column = dir*256 + rank*32 + slot
+// (rank = recurrence CTA 0..7, slot = unit within the rank 0..29; slots 30, 31 are zero).  Every CTA's 8-unit
+// k-chunk is then a 16-byte aligned, non-overlapping run, which is what lets the recurrence write its outputs
+// with TMA stores straight from the shared-memory image.
+constexpr int TC_OP = 512;
+constexpr size_t TC_GATHER_BYTES = (size_t)16 * 8 * 3 * 2 * 4096;   // L2 scratch of the multicast all-gather: [cluster][rank][S][parity][4 KB]
 
 // ------------------------------------------------------------------------------------------------
 // host: tensor maps
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_whh_kernel(const float *__restrict__ w, int dir, __half *__restrict__ dst);   // defined with K5
+__global__ void pack_whh_kernel(const float *__restrict__ w, int dir, int frag, __half *__restrict__ dst);   // defined with K5
+__global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict__ dst);
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -84,15 +91,19 @@ __global__ void split_planes_kernel(const float *__restrict__ x, long long M, in
 }
 
 // torch W_ih[960][Kin] (rows q*240 + unit) -> planes [dir*960 + g'][Kp]; bias[dir*960 + g'] = b_ih + b_hh
+// slots != 0: the K index is in slot layout (column = dir*256 + rank*32 + slot) and maps to torch column dir*240 + rank*30 + slot
 __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__restrict__ b_ih, const float *__restrict__ b_hh, int Kin,
-                                int Kp, int dir, __half *__restrict__ hi, __half *__restrict__ lo, float *__restrict__ bias)
+                                int Kp, int dir, int slots, __half *__restrict__ hi, __half *__restrict__ lo, float *__restrict__ bias)
 {
     const int gp = blockIdx.x;                     // g' = r*120 + 4*u + q
     const int r = gp / 120, u = (gp % 120) / 4, q = gp % 4;
     const int row = q * TC_H + 30 * r + u;
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
         __half h = __float2half_rn(0.f), l = h;
-        if (k < Kin) split_f16(w[(size_t)row * Kin + k], h, l);
+        if (slots) {
+            const int slot = k & 31;
+            if (slot < 30) split_f16(w[(size_t)row * Kin + (k >> 8) * TC_H + ((k >> 5) & 7) * 30 + slot], h, l);
+        } else if (k < Kin) split_f16(w[(size_t)row * Kin + k], h, l);
         hi[((size_t)dir * TC_G + gp) * Kp + k] = h;
         lo[((size_t)dir * TC_G + gp) * Kp + k] = l;
     }
@@ -297,7 +308,7 @@ __global__ void unpermute_xproj_kernel(const float *__restrict__ src, long long 
 // host side
 // ------------------------------------------------------------------------------------------------
 static int kp_of_layer(int layer, int F) { return layer == 0 ? 64 : 512; }
-static int kreal_of_layer(int layer, int F) { return layer == 0 ? ((F + 15) / 16) * 16 : 2 * TC_H; }
+static int kreal_of_layer(int layer, int F) { return layer == 0 ? ((F + 15) / 16) * 16 : TC_OP; }
 
 size_t tc_pack_bytes(int F, int H)
 {
@@ -306,8 +317,9 @@ size_t tc_pack_bytes(int F, int H)
     for (int l = 0; l < 2; ++l) {
         n += align_up(sizeof(__half) * 2 * TC_NG * kp_of_layer(l, F), 256);   // wih hi+lo
         n += align_up(sizeof(float) * TC_NG, 256);                             // bias
-        n += align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 256, 256);            // whh planes [dir][rank][plane][128][256]
+        n += 2 * align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 256, 256);        // whh planes [dir][rank][plane][128][256], two row orders
     }
+    n += align_up(sizeof(float) * 4 * TC_OP, 256);                             // linear weights in slot layout
     return n;
 }
 
@@ -332,6 +344,8 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
         off += align_up(sizeof(float) * TC_NG, 256);
         m->tc_whh[l] = reinterpret_cast<__half *>(base + off);
         off += align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 256, 256);
+        m->tc_whh_frag[l] = reinterpret_cast<__half *>(base + off);
+        off += align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 256, 256);
         __half *hi = m->tc_wih[l], *lo = hi + (size_t)TC_NG * Kp;
         for (int d = 0; d < 2 && !rc; ++d) {
             float *w = tmp, *bi = tmp + (size_t)TC_G * kin[l], *bh = bi + TC_G;
@@ -341,14 +355,25 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
                 rc = cuda_fail(e, "cudaMemcpyAsync(tc_pack)");
                 break;
             }
-            pack_wih_kernel<<<TC_G, 128, 0, st>>>(w, bi, bh, kin[l], Kp, d, hi, lo, m->tc_bias[l]);
+            pack_wih_kernel<<<TC_G, 128, 0, st>>>(w, bi, bh, kin[l], Kp, d, l, hi, lo, m->tc_bias[l]);
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "pack_wih_kernel"); break; }
             if ((e = cudaMemcpyAsync(w, p->w_hh[l][d], sizeof(float) * TC_G * TC_H, cudaMemcpyDefault, st)) != cudaSuccess) {
                 rc = cuda_fail(e, "cudaMemcpyAsync(tc_pack w_hh)");
                 break;
             }
-            pack_whh_kernel<<<8 * 128, 128, 0, st>>>(w, d, m->tc_whh[l]);
+            pack_whh_kernel<<<8 * 128, 128, 0, st>>>(w, d, 0, m->tc_whh[l]);
+            pack_whh_kernel<<<8 * 128, 128, 0, st>>>(w, d, 1, m->tc_whh_frag[l]);
             if ((e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e, "pack_whh_kernel");
+        }
+    }
+    if (!rc) {
+        m->tc_lin_w = reinterpret_cast<float *>(base + off);
+        off += align_up(sizeof(float) * 4 * TC_OP, 256);
+        cudaError_t e2 = cudaMemcpyAsync(tmp, p->lin_w, sizeof(float) * 4 * 2 * TC_H, cudaMemcpyDefault, st);
+        if (e2 != cudaSuccess) rc = cuda_fail(e2, "cudaMemcpyAsync(tc_pack lin_w)");
+        else {
+            pack_linw_kernel<<<4, TC_OP, 0, st>>>(tmp, m->tc_lin_w);
+            if ((e2 = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e2, "pack_linw_kernel");
         }
     }
     cudaFreeAsync(tmp, st);
@@ -478,6 +503,9 @@ struct RecurParams {
     int stagger_ns;             // initial phase offset between the sub-tiles of a cluster
     unsigned long long *trace;  // diagnostic (hssb_debug_trace): clock64 stamps of cluster 0 / rank 0, or nullptr
     int trace_steps;
+    // pair kernel: TMA stores of relu(h) into the slot-layout outputs [B][T][512] (fp16 hi, lo planes or one fp32 tensor)
+    alignas(64) CUtensorMap out_map[2];
+    unsigned char *gather;      // multicast kernel: L2 scratch [cluster][rank][S][2][4 KB] of the all-gather
 };
 
 // trace events (per step, per sub-tile): see scripts/trace_recurrent.py
@@ -608,7 +636,7 @@ __global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_k
         const int u = row >> 2, j = lane & 3;    // unit 0..31 (30, 31 padding), gate / column residue
         const bool unit_ok = u < RC_U;
         const long long b0 = sub_b0(s);
-        const int hcol = dir * TC_H + (int)rank * RC_U + u;      // column in the [.., 480] outputs
+        const int hcol = dir * (TC_OP / 2) + (int)rank * 32 + u;    // column in the [.., 512] slot-layout outputs
         const bool leader = (warp == S + 4 * s);
 
         if (s == 0) {
@@ -656,9 +684,9 @@ __global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_k
             };
             load_x();
             // outputs of (unit u, column 4i + j): element offset of step tt = o_base + i*o_stride + tt*480
-            const size_t o_stride = (size_t)4 * T * (2 * TC_H);
-            size_t o_next = ((size_t)(b0 + j) * T + (dir ? T - 1 : 0)) * (2 * TC_H) + hcol;
-            const long long o_step = (dir ? -1 : 1) * (2 * TC_H);
+            const size_t o_stride = (size_t)4 * T * TC_OP;
+            size_t o_next = ((size_t)(b0 + j) * T + (dir ? T - 1 : 0)) * TC_OP + hcol;
+            const long long o_step = (dir ? -1 : 1) * TC_OP;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * NB;
             if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster
 #pragma unroll
@@ -726,7 +754,7 @@ __global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_k
                 }
                 // ---- off the critical path: this step's outputs to global memory ----
                 if (t >= 0) {
-                    if (unit_ok) {
+                    {                                   // padding slots 30, 31 are written too (zeros)
                         size_t o = o_next;
                         if (p.out_f32) {
 #pragma unroll
@@ -763,11 +791,654 @@ __global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_k
     if (warp == 0) { if (PAIR) tmem_dealloc2<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }
 
-// torch W_hh[960][240] -> planes [dir][rank][plane][128 rows 4*u+q][256 k' = 32 r' + u']
-__global__ void pack_whh_kernel(const float *__restrict__ w, int dir, __half *__restrict__ dst)
+// ------------------------------------------------------------------------------------------------
+// K5p: recurrence for large batches -- CTA pairs (cta_group::2), 64 batch columns per MMA.
+//
+// What bounds the kernel above is the per-step chain (MMA -> TMEM load -> activations -> all-gather) and, at 96
+// columns per cluster, the all-gather itself: every CTA pushes 1 KB per column to 7 peers through DSMEM
+// (~17 B/cycle/SM measured, scripts/microbench/ub_cluster.cu), about twice the tensor time of the same columns.
+// Here the two CTAs of a TPC issue ONE tcgen05.mma.cta_group::2 (M = 256 gate rows, N = 64 columns; 33 cycles,
+// the same as a cta_group::1 MMA of that N) whose B operand is split between them: the even CTA holds columns
+// [0, 32) of h_{t-1}, the odd CTA columns [32, 64), so every CTA receives -- and sends -- half as much.
+//   * TMEM lanes in "fragment order" (lane = 32*(u/8) + 8*gate + u%8): two tcgen05.ld.16x256b.x4 hand thread
+//     (ul = lane/4, cp = lane%4) the four gates of unit 8q+ul for the 8 columns 8k + 2cp + {0,1} -- no shuffles,
+//     and the matching xproj values are 8 coalesced 16-byte loads (xproj keeps the 4*u + gate order of K4).
+//   * 8 epilogue warps per sub-tile = 4 TMEM lane quadrants x 2 column halves; the warps of half `hf` produce
+//     exactly the part of the image that goes to the CTAs of parity `hf` (4 bulk copies of 4 KB per half).
+//   * every B buffer has one mbarrier per SOURCE PAIR, so the MMA issuer starts on the K range of a pair as soon
+//     as that pair's slices landed (the group holding this pair's own slices first: its arrival also proves that
+//     all 16 epilogue warps of the pair have read the previous accumulator).  The odd CTA relays its arrivals to
+//     the even (issuing) CTA.
+//   * activations with 8 instead of 10 MUFU ops per (unit, column): the reciprocals of i.g and o.tanh(c) are
+//     shared, i*g = (1 - e_g) / ((1 + e_i)(1 + e_g)) with e_x = exp(-x) (exp(-2x) for g and c).
+//   * outputs (relu(h) of the step) leave through a per-warp shared-memory tile and one TMA tensor store per
+//     plane (box 8 units x 32 columns of the slot-layout [B][T][512] tensors; ragged batches are clipped by the
+//     TMA unit) instead of 16 scattered 2-byte global stores per thread.
+// Layout of one B buffer: [source rank 8][k-chunk 4][plane 2][column 32][8 units] fp16 (K-major core matrices:
+// LBO = 1 KB between k-chunks, SBO = 128 B between 8-column groups).
+// ------------------------------------------------------------------------------------------------
+constexpr int RP_NB = 64;                          // columns of one sub-tile (pair MMA N)
+constexpr int RP_NBH = 32;                         // columns held (and produced per epilogue warp) per CTA half
+constexpr int RP_G = 4;                            // arrival groups per buffer (= source pairs)
+constexpr int RP_PIECE = RP_NBH * 8 * 2 * 2;       // [plane][32 cols][8 units] fp16 = 1 KB: one epilogue warp's output
+constexpr int RP_SLICE = 4 * RP_PIECE;             // one source rank: 4 k-chunks
+constexpr int RP_HBUF = RC_CL * RP_SLICE;          // 32 KB
+
+template <int S>
+struct RpCfg {
+    static constexpr int PER_SUB = 2 * RP_HBUF + 4 * RP_SLICE;       // 2 B buffers + images [parity][half]
+    static constexpr int OUT_BYTES = S * 8 * 1024;                   // per epilogue warp: relu(h) tile for the TMA store
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + BAR_BYTES + 1024;
+    static constexpr int THREADS = 32 * S + 256 * S;                 // S issuer / relay warps + S x 8 epilogue warps
+    static_assert(S * RP_NB <= 256, "accumulators must fit in the TMEM columns left of the weights");
+    static_assert((4 * S * RP_G + S) * 8 + 8 <= BAR_BYTES, "barrier area too small");
+};
+
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_b16(uint32_t addr, __half v)
+{
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(v)) : "memory");
+}
+__device__ __forceinline__ void sts_b32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+template <int S>
+__global__ void __launch_bounds__(RpCfg<S>::THREADS, 1) tc_recurrent_pair_kernel(const __grid_constant__ RecurParams p)
+{
+    using C = RpCfg<S>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * RP_HBUF; };
+    auto image = [&](int s, int par, int hf) { return smem + s * C::PER_SUB + 2 * RP_HBUF + (par * 2 + hf) * RP_SLICE; };
+    unsigned char *out_tiles = smem + S * C::PER_SUB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_tiles + C::OUT_BYTES);
+    uint64_t *own_full = bars;                       // [S][2][G]  slices of source pair g have landed in my buffer
+    uint64_t *peer_full = bars + 2 * S * RP_G;       // [S][2][G]  (even CTA) ... and in the odd CTA's buffer
+    uint64_t *d_full = bars + 4 * S * RP_G;          // [S]        accumulator complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + S);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x / RC_CL;
+    const int dir = cid & 1;
+    const int group = cid >> 1;
+    const long long T = p.T, B = p.B;
+    auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * RP_NB; };
+    unsigned long long *const tr_buf = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+#define RP_TRACE(ev, step, sub)                                                                                       \
+    do {                                                                                                              \
+        if (tr_buf && (step) >= 0 && (step) < p.trace_steps) tr_buf[(((step) * 4 + (sub)) * TR_EVENTS) + (ev)] = clock64(); \
+    } while (0)
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4 * S * RP_G + S; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+        prefetch_tmap(&p.out_map[0]);
+        if (!p.out_f32) prefetch_tmap(&p.out_map[1]);
+    }
+    cluster_sync();                          // both CTAs of a pair are resident before the paired TMEM allocation
+    if (warp == 0) tmem_alloc2<512>(tmem_slot);
+    for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync();                          // every CTA's barriers are initialised before any remote copy can target them
+
+    if (warp < S) {
+        // ================= MMA issuer (even CTA) / arrival relay (odd CTA) of sub-tile s = warp =================
+        const int s = warp;
+        named_barrier(9, 32 * S + 128);          // weights are in TMEM
+        tc_fence_after();
+        if (sub_b0(s) < B && elect_one()) {
+            const int g0 = (int)(rank >> 1);
+            for (int i = 0; i < 2 * RP_G; ++i) mbar_arrive_expect_tx(&own_full[s * 2 * RP_G + i], 2 * RP_SLICE);
+            if (rank & 1) {
+                for (long long t = 0; t < T; ++t) {
+                    const int par = (int)(t & 1);
+                    const uint32_t ph = (uint32_t)((t >> 1) & 1);
+#pragma unroll
+                    for (int gi = 0; gi < RP_G; ++gi) {
+                        const int bi = (s * 2 + par) * RP_G + ((g0 + gi) & (RP_G - 1));
+                        mbar_wait_cluster(&own_full[bi], ph);
+                        mbar_arrive_remote(&peer_full[bi], rank ^ 1u);
+                        if (t + 2 < T) mbar_arrive_expect_tx(&own_full[bi], 2 * RP_SLICE);
+                    }
+                }
+            } else {
+                constexpr uint32_t idesc = make_idesc_f16(256, RP_NB);
+                const uint32_t d_tmem = tmem_base + 256 + s * RP_NB;
+                const uint16_t pair_mask = (uint16_t)(3u << rank);
+                for (long long t = 0; t < T; ++t) {
+                    const int par = (int)(t & 1);
+                    const uint32_t ph = (uint32_t)((t >> 1) & 1);
+                    const uint32_t hb = smem_u32(hbuf(s, par));
+#pragma unroll
+                    for (int gi = 0; gi < RP_G; ++gi) {
+                        const int g = (g0 + gi) & (RP_G - 1);
+                        const int bi = (s * 2 + par) * RP_G + g;
+                        mbar_wait_cluster(&own_full[bi], ph);
+                        mbar_wait_cluster(&peer_full[bi], ph);
+                        if (t + 2 < T) mbar_arrive_expect_tx(&own_full[bi], 2 * RP_SLICE);
+                        tc_fence_after();
+                        if (gi == 0) RP_TRACE(TR_MMA_HFULL, t, s);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = 4 * g + jj;                      // K16 step: source rank j >> 1, k-chunks 2(j&1), 2(j&1)+1
+                            const uint32_t blk = hb + (j >> 1) * RP_SLICE + (j & 1) * (2 * RP_PIECE);
+                            const uint64_t b_hi = make_smem_desc(blk, RP_PIECE, 128, LAYOUT_NONE);
+                            const uint64_t b_lo = make_smem_desc(blk + RP_PIECE / 2, RP_PIECE, 128, LAYOUT_NONE);
+                            const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
+                            mma_f16_ts2(d_tmem, a_hi, b_hi, idesc, (gi | jj) != 0);
+                            mma_f16_ts2(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_f16_ts2(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
+                    }
+                    mma_commit2_mc(&d_full[s], pair_mask);
+                    RP_TRACE(TR_MMA_ISSUED, t, s);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warp: sub-tile s, column half hf, TMEM lane quadrant q =================
+        const int k = (warp - S) >> 2;
+        const int s = k >> 1, hf = k & 1;
+        const int q = warp & 3;
+        const int ul = lane >> 2, cp = lane & 3;     // unit within the k-chunk q; column pair
+        const int u = 8 * q + ul;                    // unit 0..31 of this CTA (30, 31 padding)
+        const bool unit_ok = u < RC_U;
+        const long long b0 = sub_b0(s) + hf * RP_NBH;
+        const bool tracer = (hf == 0 && q == 0 && lane == 0);
+        unsigned char *out_tile = out_tiles + (warp - S) * 1024;
+
+        if (k == 0) {
+            // one-time: W_hh slice -> TMEM.  This thread owns lane 32q + lane; column c holds k' = 2c, 2c+1.
+            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * RC_KP;
+#pragma unroll 1
+            for (int plane = 0; plane < 2; ++plane) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
+#pragma unroll 4
+                for (int c8 = 0; c8 < 16; ++c8) {
+                    const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
+                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            named_barrier(9, 32 * S + 128);
+        }
+
+        if (sub_b0(s) < B) {
+            constexpr int NI = RP_NBH / 4;              // 8 (unit, column) cells per thread: columns 8*(i/2) + 2*cp + (i&1)
+            constexpr float LOG2E = 1.4426950408889634f;
+            constexpr float EMAX = 60.0f;               // exponent clamp: (1 + 2^60)^2 is finite, sigmoid(-41) = 0 in fp32 anyway
+            const long long left = B - b0;
+            const int ncols = (int)(left < 0 ? 0 : (left < RP_NBH ? left : RP_NBH));    // valid columns of this half (may be 0)
+            auto col_of = [&](int i) { return 8 * (i >> 1) + 2 * cp + (i & 1); };
+            // xproj of (unit u, column c): 4 consecutive floats i, f, g, o at xp + c*960 (16-byte aligned)
+            const int ux = unit_ok ? u : RC_U - 1;
+            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * B * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
+            const long long xstep = (dir ? -1 : 1) * B * TC_G;
+            float4 xnext[NI];
+            float c_state[NI];
+            // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
+            // wait of the warp (spill reloads, TMA issue, ...) would otherwise sit behind these HBM loads.
+            auto load_x = [&]() {
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const int c = col_of(i);
+                    xnext[i] = (c < ncols) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                xp_next += xstep;
+            };
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * RP_NB + hf * RP_NBH;
+            const uint32_t my_group = rank >> 1;          // my slices complete barrier `my_group` of every destination
+            const int out_c0 = dir * (TC_OP / 2) + (int)rank * 32 + 8 * q;      // first column of this warp's 8 units
+            const size_t state_o = ((size_t)dir * B + b0) * TC_H + rank * RC_U + u;      // + column * TC_H
+            // h_t of (unit u, 8 columns) -> this warp's piece [plane][col][8 units] of the fp16 hi/lo image, then
+            // (after the 4 warps of this half have written theirs) 4 bulk copies of the 4 KB half-image
+            auto publish = [&](const float (&hv)[NI], int t) {
+                const uint32_t img = smem_u32(image(s, (int)(t & 1), hf)) + q * RP_PIECE + ul * 2;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    __half hh, hl;
+                    split_f16(hv[i], hh, hl);
+                    sts_b16(img + col_of(i) * 16, hh);
+                    sts_b16(img + RP_NBH * 16 + col_of(i) * 16, hl);
+                }
+                fence_proxy_async_smem();
+                named_barrier(1 + k, 128);
+                if (tracer) RP_TRACE(TR_EPI_IMAGE, t, s);
+                if (q == 0 && elect_one()) {
+                    const int par = (int)((t + 1) & 1);
+                    uint64_t *bar = &own_full[(s * 2 + par) * RP_G + my_group];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)
+                        bulk_copy_to_cta(hbuf(s, par) + rank * RP_SLICE, image(s, (int)(t & 1), hf), RP_SLICE, bar, (uint32_t)(2 * d + hf));
+                }
+                if (tracer) RP_TRACE(TR_EPI_COPIES, t, s);
+            };
+            {
+                float h_init[NI];
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const bool ok = unit_ok && col_of(i) < ncols;
+                    h_init[i] = ok ? __ldg(p.h0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
+                    c_state[i] = ok ? __ldg(p.c0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
+                }
+                if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster
+                publish(h_init, -1);
+            }
+            load_x();
+            const int Ti = (int)T;
+            int t_idx = dir ? Ti - 1 : 0;
+            for (int t = 0; t < Ti; ++t) {
+                mbar_wait(&d_full[s], (uint32_t)(t & 1));
+                tc_fence_after();
+                if (tracer) RP_TRACE(TR_EPI_DFULL, t, s);
+                float hv[NI];
+                {
+                    // two passes of 16 columns keep the register peak (xproj prefetch + accumulators + exponentials) under 96
+                    float ei[NI], ef[NI], eg[NI], eo[NI];
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        uint32_t a[8], b[8];    // a: gates i (lane ul), f (lane ul+8);  b: gates g, o;  [4k + 2*gate + c] = column 16*pass + 8k + 2cp + c
+                        tmem_ld_16x256b_x2(taddr + 16 * pass, a);
+                        tmem_ld_16x256b_x2(taddr + (16u << 16) + 16 * pass, b);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            const int i = 4 * pass + ii, r = 4 * (ii >> 1) + (ii & 1);
+                            ei[i] = ex2_approx(fminf((__uint_as_float(a[r]) + xnext[i].x) * -LOG2E, EMAX));
+                            ef[i] = ex2_approx(fminf((__uint_as_float(a[r + 2]) + xnext[i].y) * -LOG2E, EMAX));
+                            eg[i] = ex2_approx(fminf((__uint_as_float(b[r]) + xnext[i].z) * (-2.0f * LOG2E), EMAX));
+                            eo[i] = ex2_approx(fminf((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E, EMAX));
+                        }
+                    }
+                    tc_fence_before();
+                    if (tracer) RP_TRACE(TR_EPI_ACT, t, s);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const float ig = (1.0f - eg[i]) * rcp_approx((1.0f + ei[i]) * (1.0f + eg[i]));      // sigmoid(i) tanh(g)
+                        const float c = fmaf(rcp_approx(1.0f + ef[i]), c_state[i], ig);
+                        c_state[i] = c;
+                        const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EMAX));
+                        const float h = (1.0f - ec) * rcp_approx((1.0f + eo[i]) * (1.0f + ec));             // sigmoid(o) tanh(c)
+                        hv[i] = unit_ok ? h : 0.0f;
+                    }
+                    if (tracer) RP_TRACE(TR_EPI_CELL, t, s);
+                }
+                if (t + 1 < Ti) publish(hv, t);
+                // ---- off the critical path: relu(h_t) -> global memory by TMA from this warp's tile ----
+                if (elect_one()) tma_store_wait_read<0>();        // the previous step's store has read the tile
+                __syncwarp();
+                const uint32_t tile = smem_u32(out_tile);
+                if (p.out_f32) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) sts_b32(tile + col_of(i) * 32 + ul * 4, fmaxf(hv[i], 0.f));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        __half hh, hl;
+                        split_f16(fmaxf(hv[i], 0.f), hh, hl);
+                        sts_b16(tile + col_of(i) * 16 + ul * 2, hh);
+                        sts_b16(tile + 512 + col_of(i) * 16 + ul * 2, hl);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (ncols > 0 && elect_one()) {
+                    tma_store_3d(&p.out_map[0], out_tile, out_c0, t_idx, (int)b0);
+                    if (!p.out_f32) tma_store_3d(&p.out_map[1], out_tile + 512, out_c0, t_idx, (int)b0);
+                    tma_store_commit();
+                }
+                t_idx += dir ? -1 : 1;
+                if (t + 1 < Ti) {
+                    load_x();
+                } else if (unit_ok) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+                        if (col_of(i) < ncols) {
+                            p.hn[state_o + (size_t)col_of(i) * TC_H] = hv[i];
+                            p.cn[state_o + (size_t)col_of(i) * TC_H] = c_state[i];
+                        }
+                }
+            }
+            if (elect_one()) tma_store_wait<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 0) tmem_dealloc2<512>(tmem_base);
+#undef RP_TRACE
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5m: recurrence with the all-gather through L2 (bulk store + TMA multicast) -- the large-batch kernel.
+//
+// Measured on B200 (scripts/microbench/ub_cluster.cu): a CTA can push ~17 B/cycle into DSMEM, so the 8-way
+// all-gather of the kernels above costs 5 750 cycles per step at 96 columns per cluster -- twice the tensor time.
+// The same exchange through L2 -- every CTA bulk-stores its 4 KB image once and then issues ONE multicast bulk
+// load that delivers it to all 8 CTAs of the cluster -- moves 50-60 B/cycle into every SM and takes ~1 100
+// cycles end to end, with two bulk operations per sub-tile and step instead of eight.
+//   * one CTA per 30 units as before (cta_group::1, M = 128, N = 32, W_hh hi/lo resident in TMEM), S = 1..3
+//     independent sub-tiles of 32 batch columns interleaved per cluster;
+//   * TMEM lanes in fragment order, xproj as 16-byte loads issued at the END of a step, outputs by TMA store:
+//     see the pair kernel above (same epilogue);
+//   * every B buffer has one mbarrier per pair of source ranks; the MMA issuer starts on a pair's K range as
+//     soon as its two slices landed (own pair first: its arrival proves that the four epilogue warps have
+//     read the previous accumulator);
+//   * the image is single-buffered: the issuing thread waits for its bulk store (cp.async.bulk.wait_group)
+//     before it issues the multicast load, and nobody rewrites the image before the next accumulator, which
+//     depends on that load; the L2 scratch slot is double-buffered by step parity.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+struct RmCfg {
+    static constexpr int PER_SUB = 2 * RP_HBUF + RP_SLICE;           // 2 B buffers + one image
+    static constexpr int OUT_BYTES = S * 4 * 1024;                   // per epilogue warp: relu(h) tile for the TMA store
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + BAR_BYTES + 1024;
+    static constexpr int THREADS = 32 * S + 128 * S;                 // S issuer warps + S x 4 epilogue warps
+    static_assert(S * RP_NBH <= 256, "accumulators must fit in the TMEM columns left of the weights");
+    static_assert((2 * S * RP_G + S) * 8 + 8 <= BAR_BYTES, "barrier area too small");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void bulk_store_global(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+// global -> the same smem offset in every CTA of `mask`, completing `bytes` on each one's mbarrier
+__device__ __forceinline__ void bulk_load_multicast(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
+template <int S>
+__global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
+{
+    using C = RmCfg<S>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * RP_HBUF; };
+    auto image = [&](int s) { return smem + s * C::PER_SUB + 2 * RP_HBUF; };
+    unsigned char *out_tiles = smem + S * C::PER_SUB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_tiles + C::OUT_BYTES);
+    uint64_t *h_full = bars;                         // [S][2][G]  slices of source pair g have landed in my buffer
+    uint64_t *d_full = bars + 2 * S * RP_G;          // [S]        accumulator complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + S);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x / RC_CL;
+    const int dir = cid & 1;
+    const int group = cid >> 1;
+    const long long T = p.T, B = p.B;
+    auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * RP_NBH; };
+    unsigned long long *const tr_buf = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+#define RM_TRACE(ev, step, sub)                                                                                       \
+    do {                                                                                                              \
+        if (tr_buf && (step) >= 0 && (step) < p.trace_steps) tr_buf[(((step) * 4 + (sub)) * TR_EVENTS) + (ev)] = clock64(); \
+    } while (0)
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * S * RP_G + S; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+        prefetch_tmap(&p.out_map[0]);
+        if (!p.out_f32) prefetch_tmap(&p.out_map[1]);
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync();                          // every CTA's barriers are initialised before any multicast can target them
+
+    if (warp < S) {
+        // ================= MMA issuer of sub-tile s = warp (one elected thread) =================
+        const int s = warp;
+        named_barrier(9, 32 * S + 128);          // weights are in TMEM
+        tc_fence_after();
+        if (sub_b0(s) < B && elect_one()) {
+            const int g0 = (int)(rank >> 1);
+            for (int i = 0; i < 2 * RP_G; ++i) mbar_arrive_expect_tx(&h_full[s * 2 * RP_G + i], 2 * RP_SLICE);
+            constexpr uint32_t idesc = make_idesc_f16(128, RP_NBH);
+            const uint32_t d_tmem = tmem_base + 256 + s * RP_NBH;
+            const int Ti = (int)T;
+            for (int t = 0; t < Ti; ++t) {
+                const int par = t & 1;
+                const uint32_t ph = (uint32_t)((t >> 1) & 1);
+                const uint32_t hb = smem_u32(hbuf(s, par));
+#pragma unroll
+                for (int gi = 0; gi < RP_G; ++gi) {
+                    const int g = (g0 + gi) & (RP_G - 1);
+                    uint64_t *bar = &h_full[(s * 2 + par) * RP_G + g];
+                    mbar_wait_cluster(bar, ph);
+                    if (t + 2 < Ti) mbar_arrive_expect_tx(bar, 2 * RP_SLICE);
+                    tc_fence_after();
+                    if (gi == 0) RM_TRACE(TR_MMA_HFULL, t, s);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * g + jj;                      // K16 step: source rank j >> 1, k-chunks 2(j&1), 2(j&1)+1
+                        const uint32_t blk = hb + (j >> 1) * RP_SLICE + (j & 1) * (2 * RP_PIECE);
+                        const uint64_t b_hi = make_smem_desc(blk, RP_PIECE, 128, LAYOUT_NONE);
+                        const uint64_t b_lo = make_smem_desc(blk + RP_PIECE / 2, RP_PIECE, 128, LAYOUT_NONE);
+                        const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
+                        mma_f16_ts(d_tmem, a_hi, b_hi, idesc, (gi | jj) != 0);
+                        mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                        mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                    }
+                }
+                mma_commit(&d_full[s]);
+                RM_TRACE(TR_MMA_ISSUED, t, s);
+            }
+        }
+    } else {
+        // ================= epilogue warp: sub-tile s, TMEM lane quadrant q =================
+        const int s = (warp - S) >> 2;
+        const int q = warp & 3;
+        const int ul = lane >> 2, cp = lane & 3;     // unit within the k-chunk q; column pair
+        const int u = 8 * q + ul;                    // unit 0..31 of this CTA (30, 31 padding)
+        const bool unit_ok = u < RC_U;
+        const long long b0 = sub_b0(s);
+        const bool tracer = (q == 0 && lane == 0);
+        unsigned char *out_tile = out_tiles + (warp - S) * 1024;
+
+        if (s == 0) {
+            // one-time: W_hh slice -> TMEM.  This thread owns lane 32q + lane; column c holds k' = 2c, 2c+1.
+            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * RC_KP;
+#pragma unroll 1
+            for (int plane = 0; plane < 2; ++plane) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
+#pragma unroll 4
+                for (int c8 = 0; c8 < 16; ++c8) {
+                    const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
+                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            named_barrier(9, 32 * S + 128);
+        }
+
+        if (b0 < B) {
+            constexpr int NI = RP_NBH / 4;              // 8 (unit, column) cells per thread: columns 8*(i/2) + 2*cp + (i&1)
+            constexpr float LOG2E = 1.4426950408889634f;
+            constexpr float EMAX = 60.0f;               // exponent clamp: (1 + 2^60)^2 is finite, sigmoid(-41) = 0 in fp32 anyway
+            const long long left = B - b0;
+            const int ncols = (int)(left < RP_NBH ? left : RP_NBH);
+            auto col_of = [&](int i) { return 8 * (i >> 1) + 2 * cp + (i & 1); };
+            const int ux = unit_ok ? u : RC_U - 1;
+            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * B * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
+            const long long xstep = (dir ? -1 : 1) * B * TC_G;
+            float4 xnext[NI];
+            float c_state[NI];
+            // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
+            // wait of the warp (TMA issue, spill reloads, ...) would otherwise sit behind these HBM loads.
+            auto load_x = [&]() {
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const int c = col_of(i);
+                    xnext[i] = (c < ncols) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                xp_next += xstep;
+            };
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * RP_NBH;
+            const int out_c0 = dir * (TC_OP / 2) + (int)rank * 32 + 8 * q;      // first column of this warp's 8 units
+            const size_t state_o = ((size_t)dir * B + b0) * TC_H + rank * RC_U + u;      // + column * TC_H
+            unsigned char *gslot = p.gather + ((((size_t)cid * RC_CL + rank) * S + s) * 2) * RP_SLICE;     // [parity][4 KB]
+            // h_t -> this warp's piece [plane][col][8 units] of the fp16 hi/lo image; then one thread stores the 4 KB image
+            // to its L2 slot and multicasts it into slot `rank` of every CTA's B buffer for step t + 1
+            auto publish = [&](const float (&hv)[NI], int t) {
+                const uint32_t img = smem_u32(image(s)) + q * RP_PIECE + ul * 2;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    __half hh, hl;
+                    split_f16(hv[i], hh, hl);
+                    sts_b16(img + col_of(i) * 16, hh);
+                    sts_b16(img + RP_NBH * 16 + col_of(i) * 16, hl);
+                }
+                fence_proxy_async_smem();
+                named_barrier(1 + s, 128);
+                if (tracer) RM_TRACE(TR_EPI_IMAGE, t, s);
+                if (q == 0 && elect_one()) {
+                    const int par = (t + 1) & 1;
+                    unsigned char *g = gslot + par * RP_SLICE;
+                    bulk_store_global(g, image(s), RP_SLICE);
+                    tma_store_commit();
+                    tma_store_wait<0>();
+                    bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE, g, RP_SLICE, &h_full[(s * 2 + par) * RP_G + (rank >> 1)], (uint16_t)0xFF);
+                }
+                if (tracer) RM_TRACE(TR_EPI_COPIES, t, s);
+            };
+            {
+                float h_init[NI];
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const bool ok = unit_ok && col_of(i) < ncols;
+                    h_init[i] = ok ? __ldg(p.h0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
+                    c_state[i] = ok ? __ldg(p.c0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
+                }
+                if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster
+                publish(h_init, -1);
+            }
+            load_x();
+            const int Ti = (int)T;
+            int t_idx = dir ? Ti - 1 : 0;
+            for (int t = 0; t < Ti; ++t) {
+                mbar_wait(&d_full[s], (uint32_t)(t & 1));
+                tc_fence_after();
+                if (tracer) RM_TRACE(TR_EPI_DFULL, t, s);
+                float hv[NI];
+                {
+                    uint32_t a[16], b[16];      // a: gates i (lane ul), f (lane ul+8);  b: gates g, o;  [4k + 2*gate + c] = column 8k + 2cp + c
+                    tmem_ld_16x256b_x4(taddr, a);
+                    tmem_ld_16x256b_x4(taddr + (16u << 16), b);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    float ei[NI], ef[NI], eg[NI], eo[NI];
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const int r = 4 * (i >> 1) + (i & 1);
+                        ei[i] = ex2_approx(fminf((__uint_as_float(a[r]) + xnext[i].x) * -LOG2E, EMAX));
+                        ef[i] = ex2_approx(fminf((__uint_as_float(a[r + 2]) + xnext[i].y) * -LOG2E, EMAX));
+                        eg[i] = ex2_approx(fminf((__uint_as_float(b[r]) + xnext[i].z) * (-2.0f * LOG2E), EMAX));
+                        eo[i] = ex2_approx(fminf((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E, EMAX));
+                    }
+                    if (tracer) RM_TRACE(TR_EPI_ACT, t, s);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const float ig = (1.0f - eg[i]) * rcp_approx((1.0f + ei[i]) * (1.0f + eg[i]));      // sigmoid(i) tanh(g)
+                        const float c = fmaf(rcp_approx(1.0f + ef[i]), c_state[i], ig);
+                        c_state[i] = c;
+                        const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EMAX));
+                        const float h = (1.0f - ec) * rcp_approx((1.0f + eo[i]) * (1.0f + ec));             // sigmoid(o) tanh(c)
+                        hv[i] = unit_ok ? h : 0.0f;
+                    }
+                    if (tracer) RM_TRACE(TR_EPI_CELL, t, s);
+                }
+                if (t + 1 < Ti) publish(hv, t);
+                // ---- off the critical path: relu(h_t) -> global memory by TMA from this warp's tile ----
+                if (elect_one()) tma_store_wait_read<0>();        // the previous step's store has read the tile
+                __syncwarp();
+                const uint32_t tile = smem_u32(out_tile);
+                if (p.out_f32) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) sts_b32(tile + col_of(i) * 32 + ul * 4, fmaxf(hv[i], 0.f));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        __half hh, hl;
+                        split_f16(fmaxf(hv[i], 0.f), hh, hl);
+                        sts_b16(tile + col_of(i) * 16 + ul * 2, hh);
+                        sts_b16(tile + 512 + col_of(i) * 16 + ul * 2, hl);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_3d(&p.out_map[0], out_tile, out_c0, t_idx, (int)b0);
+                    if (!p.out_f32) tma_store_3d(&p.out_map[1], out_tile + 512, out_c0, t_idx, (int)b0);
+                    tma_store_commit();
+                }
+                t_idx += dir ? -1 : 1;
+                if (t + 1 < Ti) {
+                    load_x();
+                } else if (unit_ok) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+                        if (col_of(i) < ncols) {
+                            p.hn[state_o + (size_t)col_of(i) * TC_H] = hv[i];
+                            p.cn[state_o + (size_t)col_of(i) * TC_H] = c_state[i];
+                        }
+                }
+            }
+            if (elect_one()) tma_store_wait<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+#undef RM_TRACE
+}
+
+// torch W_hh[960][240] -> planes [dir][rank][plane][128 rows][256 k' = 32 r' + u'];  row (TMEM lane) order:
+//   frag == 0: lane = 4*u + gate                          (tc_recurrent_kernel: 32x32b loads + quad shuffles)
+//   frag == 1: lane = 32*(u/8) + 8*gate + u%8             (tc_recurrent_pair_kernel: 16x256b fragment loads)
+__global__ void pack_whh_kernel(const float *__restrict__ w, int dir, int frag, __half *__restrict__ dst)
 {
     const int rank = blockIdx.x / 128, row = blockIdx.x % 128;
-    const int u = row / 4, q = row % 4;              // TMEM lane = 4*unit + gate
+    const int u = frag ? (row / 32) * 8 + row % 8 : row / 4;
+    const int q = frag ? (row % 32) / 8 : row % 4;
     __half *hi = dst + ((((size_t)dir * RC_CL + rank) * 2 + 0) * 128 + row) * RC_KP;
     __half *lo = dst + ((((size_t)dir * RC_CL + rank) * 2 + 1) * 128 + row) * RC_KP;
     for (int kp = threadIdx.x; kp < RC_KP; kp += blockDim.x) {
@@ -777,6 +1448,13 @@ __global__ void pack_whh_kernel(const float *__restrict__ w, int dir, __half *__
         hi[kp] = h;
         lo[kp] = l;
     }
+}
+
+// linear.weight[4][480] -> slot layout [4][512]
+__global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict__ dst)
+{
+    const int c = blockIdx.x, k = threadIdx.x, slot = k & 31;
+    dst[c * TC_OP + k] = slot < 30 ? w[c * 2 * TC_H + (k >> 8) * TC_H + ((k >> 5) & 7) * 30 + slot] : 0.f;
 }
 
 static unsigned long long *g_trace_buf = nullptr;
@@ -844,15 +1522,110 @@ static int launch_recurrent(const RecurParams &prm_in, int64_t rem, int *cols_do
     return 0;
 }
 
+template <int S>
+static int launch_recurrent_pair(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
+{
+    using C = RpCfg<S>;
+    RecurParams prm = prm_in;
+    prm.whh = whh_frag;
+    prm.trace = g_trace_buf;
+    prm.trace_steps = g_trace_steps;
+    static int max_clusters = 0;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (!max_clusters) {
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_pair_kernel)");
+        cfg.gridDim = dim3(16 * RC_CL);
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_pair_kernel<S>, &cfg);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_pair_kernel)");
+        if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
+        max_clusters = n;
+    }
+    const int per = RP_NB * S;
+    const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);
+    *cols_done = groups * per;
+    prm.xproj = xproj;
+    prm.groups = groups;
+    prm.stagger_ns = 1500;
+    if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
+    cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
+    ProfScope prof("tc_recurrent", st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_pair_kernel<S>, prm);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_pair_kernel)");
+    return 0;
+}
+
+template <int S>
+static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
+{
+    using C = RmCfg<S>;
+    RecurParams prm = prm_in;
+    prm.whh = whh_frag;
+    prm.trace = g_trace_buf;
+    prm.trace_steps = g_trace_steps;
+    static int max_clusters = 0;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (!max_clusters) {
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_mc_kernel)");
+        cfg.gridDim = dim3(16 * RC_CL);
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S>, &cfg);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_mc_kernel)");
+        if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
+        max_clusters = std::min(n, 16);
+    }
+    const int per = RP_NBH * S;
+    const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);
+    *cols_done = groups * per;
+    prm.xproj = xproj;
+    prm.groups = groups;
+    prm.stagger_ns = 600;
+    if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
+    cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
+    ProfScope prof("tc_recurrent", st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S>, prm);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
+    return 0;
+}
+
 // One layer's recurrence for batch columns [0, B): picks the sub-tile geometry from B.
 static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const float *h0, const float *c0, float *hn, float *cn,
-                        __half *out_hi, __half *out_lo, float *out_f32, int64_t B, int64_t T, cudaStream_t st)
+                        __half *out_hi, __half *out_lo, float *out_f32, unsigned char *gather, int64_t B, int64_t T, cudaStream_t st)
 {
     RecurParams prm = {};
+    prm.gather = gather;
     prm.whh = m->tc_whh[layer];
     prm.h0 = h0; prm.c0 = c0; prm.hn = hn; prm.cn = cn;
     prm.out_hi = out_hi; prm.out_lo = out_lo; prm.out_f32 = out_f32;
     prm.B = B; prm.T = T;
+    {
+        const bool f32 = out_f32 != nullptr;
+        const uint64_t es = f32 ? 4 : 2;
+        const uint64_t dims[3] = {(uint64_t)TC_OP, (uint64_t)T, (uint64_t)B};
+        const uint64_t strides[2] = {(uint64_t)TC_OP * es, (uint64_t)T * TC_OP * es};
+        const uint32_t box[3] = {8, 1, RP_NBH};
+        const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        if (int rc = make_tmap(&prm.out_map[0], dt, 3, f32 ? (const void *)out_f32 : (const void *)out_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        if (int rc = make_tmap(&prm.out_map[1], dt, 3, f32 ? (const void *)out_f32 : (const void *)out_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    }
     // at most 8 groups per direction are co-resident (16 clusters of 8 CTAs on 148 SMs); larger batches
     // run as successive launches over blocks of batch columns
     // Geometry: as few batch columns per cluster as the co-resident clusters allow (the DSMEM all-gather
@@ -888,6 +1661,11 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         case 3221: rc = launch_recurrent<32, 2, true>(prm, rem, &done, xproj, st); break;
         case 3231: rc = launch_recurrent<32, 3, true>(prm, rem, &done, xproj, st); break;
         case 3241: rc = launch_recurrent<32, 4, true>(prm, rem, &done, xproj, st); break;
+        case 3212: rc = launch_recurrent_mc<1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3222: rc = launch_recurrent_mc<2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3232: rc = launch_recurrent_mc<3>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 6411: rc = launch_recurrent_pair<1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 6421: rc = launch_recurrent_pair<2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
         default: return fail(HSSB_E_MODE, "HSSB_RC_GEOM=%d,%d,%d unsupported", nb, s, pair);
         }
         if (rc) return rc;
@@ -897,7 +1675,7 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
 }
 
 namespace {
-struct TcWs { size_t xhi, xlo, xproj, o1hi, o1lo, out2, hn, cn, total; };
+struct TcWs { size_t xhi, xlo, xproj, o1hi, o1lo, out2, hn, cn, gather, total; };
 TcWs tc_ws_layout(int64_t B, int64_t T)
 {
     const size_t M = (size_t)B * T;
@@ -906,11 +1684,12 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
     w.xhi = off;   off += align_up(sizeof(__half) * M * 64, 1024);
     w.xlo = off;   off += align_up(sizeof(__half) * M * 64, 1024);
     w.xproj = off; off += align_up(sizeof(float) * 2 * M * TC_G, 1024);
-    w.o1hi = off;  off += align_up(sizeof(__half) * M * 2 * TC_H, 1024);
-    w.o1lo = off;  off += align_up(sizeof(__half) * M * 2 * TC_H, 1024);
-    w.out2 = off;  off += align_up(sizeof(float) * M * 2 * TC_H, 1024);
+    w.o1hi = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
+    w.o1lo = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
+    w.out2 = off;  off += align_up(sizeof(float) * M * TC_OP, 1024);
     w.hn = off;    off += align_up(sizeof(float) * 2 * B * TC_H, 1024);
     w.cn = off;    off += align_up(sizeof(float) * 2 * B * TC_H, 1024);
+    w.gather = off; off += TC_GATHER_BYTES;
     w.total = off;
     return w;
 }
@@ -929,6 +1708,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     __half *o1hi = reinterpret_cast<__half *>(base + w.o1hi), *o1lo = reinterpret_cast<__half *>(base + w.o1lo);
     float *out2 = reinterpret_cast<float *>(base + w.out2);
     float *hn = reinterpret_cast<float *>(base + w.hn), *cn = reinterpret_cast<float *>(base + w.cn);
+    unsigned char *gather = reinterpret_cast<unsigned char *>(base + w.gather);
     const int64_t M = B * T;
     {
         ProfScope prof("split_planes", st);
@@ -936,10 +1716,10 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         HSSB_LAUNCH_OK("split_planes_kernel");
     }
     if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st)) return rc;
-    if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, B, T, st)) return rc;
-    if (int rc = tc_inproj(m, 1, o1hi, o1lo, 2 * TC_H, B, T, xproj, st)) return rc;
-    if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, B, T, st)) return rc;
-    return head_forward(out2, M, 2 * TC_H, m->lin_w, m->lin_b, logp, labels, st);
+    if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st)) return rc;
+    if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st)) return rc;
+    if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, st)) return rc;
+    return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st);
 }
 
 }  // namespace hssb

@@ -18,7 +18,9 @@ struct hssb_model {
     bool tc_ready;
     __half *tc_wih[2];        // layer l: [2 planes hi/lo][2 dirs][1024 g'][KinP]   KinP = 64 (l=0) / 512 (l=1)
     __half *tc_whh[2];        // layer l: [2 planes][2 dirs][1024 g'][256]  (k index = rank*32+u order, padded)
-    float *tc_bias[2];        // layer l: [2 dirs][1024]
+    __half *tc_whh_frag[2];   // the same W_hh planes with the TMEM lanes in fragment order (see pack_whh_kernel)
+    float *tc_bias[2];        // layer l: [2 dirs][960]
+    float *tc_lin_w;          // [4][512] linear weights in slot layout
     void *all;                // single allocation backing everything above
     size_t all_bytes;
 };

@@ -41,6 +41,8 @@ for s in range(4):
         continue
     base = tr[:, s, 0]
     period = np.diff(base)[8:]
+    if period.size == 0:
+        continue
     print(f"sub-tile {s}: step period mean {period.mean():.0f} cyc (min {period.min():.0f}, max {period.max():.0f})")
     for e, name in enumerate(EV):
         d = (tr[8:, s, e] - base[8:])

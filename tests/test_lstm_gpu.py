@@ -93,6 +93,18 @@ def test_odd_batch_and_short_sequences(lib):
     assert m(torch.zeros(2, 0, 44)).shape == (2, 0, 4)
 
 
+@pytest.mark.parametrize("geom", ["16,3,0", "32,3,0", "32,2,1", "64,2,1", "64,1,1", "32,1,2", "32,2,2", "32,3,2"])
+@pytest.mark.parametrize("B,T", [(130, 40), (97, 23)])
+def test_recurrence_geometries(lib, geom, B, T, monkeypatch):
+    """Every sub-tile geometry of the tcgen05 recurrence (single CTA / CTA pair, ragged last group) against torch-CPU."""
+    monkeypatch.setenv("HSSB_RC_GEOM", geom)
+    m = make_model(7, 44, B, 240)
+    x = torch.randn(B, T, 44, generator=torch.Generator().manual_seed(B + T))
+    params, h0, c0 = lo.reference_params(7, 44, B, 240)
+    logp, labels = m.forward_with_labels(x.cuda())
+    check(logp.cpu(), labels.cpu(), lo.forward_torch(params, h0, c0, x))
+
+
 def test_state_dict_reload_repacks_weights(lib):
     m = make_model(3, 44, 2, 240)
     x = torch.randn(2, 20, 44)
