@@ -74,7 +74,10 @@ stft_hop1_kernel(const float *__restrict__ x, long long N, const float *__restri
 // K2
 // ------------------------------------------------------------------------------------------------
 constexpr int RT = 128;        // time columns (= threads) per CTA of the reassignment kernel
-constexpr int RU = 5;          // bins loaded ahead per thread (memory-level parallelism)
+#ifndef HSSB_RU
+#define HSSB_RU 8
+#endif
+constexpr int RU = HSSB_RU;    // bins loaded ahead per thread (memory-level parallelism)
 
 __device__ __forceinline__ Moments shfl_xor_moments(Moments m, int lane_mask)
 {
@@ -126,20 +129,24 @@ if_reassign_kernel(const float2 *__restrict__ Sg, const float2 *__restrict__ Sdg
 
     if (partials == nullptr) return;
 
-    // per-thread two-pass moments of this column's Kout values, then Chan merges (fixed tree order)
+    // per-thread two-pass moments of this column's Kout values (fp32: 22 values, two-pass), then Chan merges in
+    // double (fixed tree order)
     Moments m[2];
     if (active) {
-        double sx = 0.0, sy = 0.0;
+        float sx = 0.f, sy = 0.f;
         for (int r = 0; r < Kout; ++r) { const float2 v = acc[r * RT + tid]; sx += v.x; sy += v.y; }
-        const double mx = sx / Kout, my = sy / Kout;
-        double qx = 0.0, qy = 0.0;
+        const float mx = sx / (float)Kout, my = sy / (float)Kout;
+        float qx = 0.f, qy = 0.f, ex = 0.f, ey = 0.f;
         for (int r = 0; r < Kout; ++r) {
             const float2 v = acc[r * RT + tid];
-            qx += (v.x - mx) * (v.x - mx);
-            qy += (v.y - my) * (v.y - my);
+            const float dx = v.x - mx, dy = v.y - my;
+            qx = fmaf(dx, dx, qx); ex += dx;
+            qy = fmaf(dy, dy, qy); ey += dy;
         }
-        m[0] = Moments{(double)Kout, mx, qx};
-        m[1] = Moments{(double)Kout, my, qy};
+        // corrected two-pass: the residual sums ex, ey absorb the rounding of the fp32 means
+        const double cx = (double)ex / Kout, cy = (double)ey / Kout;
+        m[0] = Moments{(double)Kout, (double)mx + cx, (double)qx - cx * cx * Kout};
+        m[1] = Moments{(double)Kout, (double)my + cy, (double)qy - cy * cy * Kout};
     } else {
         m[0] = m[1] = Moments{0.0, 0.0, 0.0};
     }

@@ -94,28 +94,39 @@ HSSB_HD void stft_phase3(int k, int c, const float2 *buf, float2 &sg, float2 &sd
 // ---------------------------------------------------------------------------------------------
 HSSB_HD int wrap_row(float r, int nfft)
 {
-    // r is integer valued.  |r| < 2^30: exact int conversion; beyond that (S_g ~ 0, garbage IF)
-    // reduce in floating point first.
-    if (fabsf(r) >= 1073741824.0f) r = fmodf(r, (float)nfft);
-    return ((int)r) & (nfft - 1);
+    // r is integer valued.  Below 2^31 the int conversion is exact; from 2^31 on every float is a multiple of 256,
+    // i.e. of nfft (128 or 256): row 0.  Branch free (the IF of a bin with S_g ~ 0 is garbage, but it must not trap).
+    return (fabsf(r) < 2147483648.0f) ? (((int)r) & (nfft - 1)) : 0;
+}
+
+// MATLAB round(): half away from zero.  x - trunc(x) is exact, so this is too.
+HSSB_HD float round_half_away(float x)
+{
+    const float t = truncf(x);
+    return (fabsf(x - t) >= 0.5f) ? t + copysignf(1.0f, x) : t;
 }
 
 HSSB_HD void reassign_one(int k, float2 a, float2 d, int nfft, float bins_per_hz, int k_lo, int k_hi,
                           float2 *acc, int astride)
 {
     const float den = a.x * a.x + a.y * a.y;
-    float fc = -((d.y * a.x - d.x * a.y) / den);
+    const float num = d.x * a.y - d.y * a.x;            // -imag(Sdg * conj(Sg))
+#ifdef __CUDA_ARCH__
+    float fc = __fdividef(num, den);                    // MUFU.RCP + FMUL: 2 ulp, no slow-path call
+#else
+    float fc = num / den;
+#endif
     if (!(fabsf(fc) <= 3.0e38f)) fc = 0.0f;   // NaN or Inf -> 0
     const float off = fc * bins_per_hz;
     const float sgn = (k & 1) ? -1.0f : 1.0f;
     const float vx = sgn * a.x, vy = sgn * a.y;
-    const int row = wrap_row(roundf((float)k + off), nfft);
+    const int row = wrap_row(round_half_away((float)k + off), nfft);
     if (row >= k_lo && row <= k_hi) {
         float2 *p = acc + (row - k_lo) * astride;
         p->x += vx; p->y += vy;
     }
     if (k > 0 && k < nfft / 2) {
-        const int rowm = wrap_row(roundf((float)(nfft - k) - off), nfft);
+        const int rowm = wrap_row(round_half_away((float)(nfft - k) - off), nfft);
         if (rowm >= k_lo && rowm <= k_hi) {
             float2 *p = acc + (rowm - k_lo) * astride;
             p->x += vx; p->y -= vy;
@@ -133,8 +144,13 @@ HSSB_HD Moments merge_moments(Moments a, Moments b)
     const double delta = b.mean - a.mean;
     Moments r;
     r.n = n;
-    r.mean = a.mean + delta * (b.n / n);
-    r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / n);
+    if (a.n == b.n) {          // the common case inside a full tile: no division (x * 0.5 is exact)
+        r.mean = a.mean + delta * 0.5;
+        r.m2 = a.m2 + b.m2 + delta * delta * (a.n * 0.5);
+    } else {
+        r.mean = a.mean + delta * (b.n / n);
+        r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / n);
+    }
     return r;
 }
 

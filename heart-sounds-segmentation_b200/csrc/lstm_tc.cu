@@ -133,8 +133,10 @@ constexpr int IP_CM = 4, IP_CN = 2, IP_CL = IP_CM * IP_CN;   // cluster shape
 constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (8 KB)
 constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (12 KB)
 constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 40 KB
-constexpr int IP_OUT_BYTES = IP_BM * 32 * 4;             // epilogue staging tile 128 x 32 fp32 (16 KB)
-constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + 2 * IP_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue staging tile of one warp: 32 rows x 32 fp32 (4 KB)
+constexpr int IP_OUT_RING = 3;                           // tiles per warp
+constexpr int IP_OUT_BYTES = 4 * IP_OUT_RING * IP_OUT_TILE;
+constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + IP_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 192 columns (at 0 and 256)
 constexpr int IP_N_TILES = TC_NG / IP_BN;                // 10
 static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
@@ -142,9 +144,10 @@ static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
 struct InprojParams {
     CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (32, 64, 1), SW64   (half of the A stage)
     CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 48), SW64  (quarter of the W stage)
-    CUtensorMap out;          // [g'(960), b, t, dir] fp32, box (32,1,128,1), SW128
+    CUtensorMap out;          // [g'(960), b, t, dir] fp32, box (32,1,32,1), SW128
     const float *bias;        // [1920]
-    int k_real;               // true K rounded up to 16 (48 / 480)
+    int k_real;               // true K rounded up to 16 (48 / 512)
+    int T;
     int t_tiles;              // ceil(T/128)
     int m_groups;             // ceil(B * t_tiles / 4)
 };
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char *stage_base = smem;
     unsigned char *out_base = smem + IP_STAGES * IP_STAGE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + 2 * IP_OUT_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + IP_OUT_BYTES);
     uint64_t *full = bars, *empty = bars + IP_STAGES, *tmem_full = bars + 2 * IP_STAGES, *tmem_empty = bars + 2 * IP_STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * IP_STAGES + 4);
 
@@ -240,9 +243,10 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+        // Every warp drains its own 32 rows: TMEM -> registers (+bias) -> its private ring of swizzled 4 KB smem tiles ->
+        // one TMA store per 32 x 32 tile.  No block-level barrier anywhere in the epilogue.
         const int q = warp & 3;
-        const int row = q * 32 + lane;          // tile row = time index t0 + row
-        const int et = threadIdx.x - 64;        // 0..127
+        unsigned char *ring = out_base + q * (IP_OUT_RING * IP_OUT_TILE);
         uint32_t tile = 0, chunk = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters, ++tile) {
             const int m_tile = (item / (IP_N_TILES / IP_CN)) * IP_CM + cx;
@@ -261,9 +265,11 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                unsigned char *ob = out_base + (chunk & 1) * IP_OUT_BYTES;
-                if (chunk >= 2 && et == 0) tma_store_wait_read<1>();     // the store that last used this buffer has read it
-                named_barrier(1, 128);
+                unsigned char *ob = ring + (chunk % IP_OUT_RING) * IP_OUT_TILE;
+                if (chunk >= IP_OUT_RING) {                 // the store that last used this tile has read it
+                    if (lane == 0) tma_store_wait_read<IP_OUT_RING - 1>();
+                    __syncwarp();
+                }
                 const float *bias = p.bias + n0 + c * 32;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -273,17 +279,17 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
                     o.y = __uint_as_float(v[4 * j + 1]) + bj.y;
                     o.z = __uint_as_float(v[4 * j + 2]) + bj.z;
                     o.w = __uint_as_float(v[4 * j + 3]) + bj.w;
-                    *reinterpret_cast<float4 *>(ob + row * 128 + ((j ^ (row & 7)) << 4)) = o;   // 128B swizzle
+                    *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;   // 128B swizzle
                 }
                 fence_proxy_async_smem();
-                named_barrier(1, 128);
-                if (et == 0) {
-                    tma_store_4d(&p.out, ob, nl0 + c * 32, b, t0, dir);
+                __syncwarp();
+                if (lane == 0) {
+                    if (t0 + q * 32 < p.T) tma_store_4d(&p.out, ob, nl0 + c * 32, b, t0 + q * 32, dir);
                     tma_store_commit();
                 }
             }
         }
-        if (et == 0) tma_store_wait<0>();
+        if (lane == 0) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -407,11 +413,12 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     {
         const uint64_t dims[4] = {(uint64_t)TC_G, (uint64_t)B, (uint64_t)T, 2};
         const uint64_t strides[3] = {(uint64_t)TC_G * 4, (uint64_t)B * TC_G * 4, (uint64_t)T * B * TC_G * 4};
-        const uint32_t box[4] = {32, 1, IP_BM, 1};
+        const uint32_t box[4] = {32, 1, 32, 1};
         if (int rc = make_tmap(&prm.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xproj, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
     prm.bias = m->tc_bias[layer];
     prm.k_real = kreal;
+    prm.T = (int)T;
     prm.t_tiles = (int)((T + IP_BM - 1) / IP_BM);
     prm.m_groups = (int)((B * prm.t_tiles + IP_CM - 1) / IP_CM);
 
@@ -1642,11 +1649,9 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         const int64_t per_group = (rem + max_groups - 1) / max_groups;
         int nb, s, pair;
         if (force_nb) { nb = force_nb; s = force_s; pair = force_pair < 0 ? (nb % 32 == 0) : force_pair; }
-        else if (per_group <= 16) { nb = 16; s = 1; pair = 0; }
-        else if (per_group <= 32) { nb = 16; s = 2; pair = 0; }
-        else if (per_group <= 48) { nb = 16; s = 3; pair = 0; }
-        else if (per_group <= 64) { nb = 32; s = 2; pair = 0; }
-        else { nb = 32; s = 3; pair = 0; }
+        else if (per_group <= 32) { nb = 32; s = 1; pair = 2; }     // pair = 2: the L2-multicast kernel (K5m), fastest at every batch
+        else if (per_group <= 64) { nb = 32; s = 2; pair = 2; }     // size measured (scripts/sweep_recurrent.py)
+        else { nb = 32; s = 3; pair = 2; }
         // (the CTA-pair variants -- cta_group::2, half the all-gather volume -- are validated but measured slower on
         //  B200: at N = 32 the paired MMA is issue-overhead bound, ~30 cycles each against ~18 for cta_group::1)
         int rc, done = 0;
