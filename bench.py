@@ -48,6 +48,23 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "tensor_tflops_burst": 1590.0, "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
+TRAFFIC_FILE = "r01c_traffic.json"
+
+
+def traffic_source():
+    return os.path.join("profiles", TRAFFIC_FILE)
+
+
+def load_traffic() -> dict:
+    path = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
+    if not os.path.exists(path):
+        return {}
+    try:
+        return json.load(open(path))["kernels"]
+    except (ValueError, KeyError):
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -275,10 +292,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 entry.update({"bound": "tensor", "achieved": tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tensor_tflops"],
                               "note": "useful FLOPs (1x) over all launches of this kernel in a step"})
             per_kernel[name] = entry
+        # ncu evidence committed under profiles/ (scripts/gpu_profiles.sh + scripts/ncu_traffic.py): DRAM bytes per launch and
+        # tensor-pipe activity of every kernel of this workload; only attached when the workload is the profiled one
+        traffic = load_traffic() if (B == WINDOWS_PER_GPU) else {}
+        for name, entry in per_kernel.items():
+            t = traffic.get(name)
+            if t:
+                entry["traffic"] = t["dram_bytes_per_launch"]
+                if t["tensor_pipe_active_pct"] > 0:
+                    entry["ncu_tensor_pipe_active_pct"] = t["tensor_pipe_active_pct"]
         dominant = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
         d = per_kernel[dominant]
         roofline = {"kernel": dominant, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": d.get("peak"), "unit": d.get("unit"),
-                    "frac": d.get("frac"), "traffic": None, "share_of_step": d["ms_per_step"] / (ms / args.steps), "peak_source": peaks["source"]}
+                    "frac": d.get("frac"), "traffic": d.get("traffic"), "share_of_step": d["ms_per_step"] / (ms / args.steps),
+                    "peak_source": peaks["source"],
+                    "note": "achieved = useful fp32-equivalent FLOPs (1x) of the W_hh contraction / launch time; the kernel issues 3 fp16 MMAs "
+                            "per product on 8-CTA clusters (96 of 148 SMs at 512 windows), ncu sm__pipe_tensor_cycles_active in "
+                            "ncu_tensor_pipe_active_pct" if dominant == "tc_recurrent" else None,
+                    "ncu_tensor_pipe_active_pct": d.get("ncu_tensor_pipe_active_pct"), "traffic_source": traffic_source() if d.get("traffic") else None}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(50)

@@ -136,7 +136,8 @@ constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 40 KB
 constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue staging tile of one warp: 32 rows x 32 fp32 (4 KB)
 constexpr int IP_OUT_RING = 3;                           // tiles per warp
 constexpr int IP_OUT_BYTES = 4 * IP_OUT_RING * IP_OUT_TILE;
-constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + IP_OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int IP_BIAS_BYTES = TC_NG * 4;                 // all 1920 folded biases, staged once per CTA
+constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + IP_OUT_BYTES + IP_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 192 columns (at 0 and 256)
 constexpr int IP_N_TILES = TC_NG / IP_BN;                // 10
 static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char *stage_base = smem;
     unsigned char *out_base = smem + IP_STAGES * IP_STAGE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + IP_OUT_BYTES);
+    float *bias_s = reinterpret_cast<float *>(out_base + IP_OUT_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + IP_OUT_BYTES + IP_BIAS_BYTES);
     uint64_t *full = bars, *empty = bars + IP_STAGES, *tmem_full = bars + 2 * IP_STAGES, *tmem_empty = bars + 2 * IP_STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * IP_STAGES + 4);
 
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<IP_TMEM_COLS>(tmem_slot);
+    for (int i = threadIdx.x; i < TC_NG; i += 192) bias_s[i] = __ldg(p.bias + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -270,10 +273,10 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
                     if (lane == 0) tma_store_wait_read<IP_OUT_RING - 1>();
                     __syncwarp();
                 }
-                const float *bias = p.bias + n0 + c * 32;
+                const float4 *bias = reinterpret_cast<const float4 *>(bias_s + n0 + c * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 bj = __ldg(reinterpret_cast<const float4 *>(bias) + j);
+                    const float4 bj = bias[j];                 // shared-memory broadcast
                     float4 o;
                     o.x = __uint_as_float(v[4 * j + 0]) + bj.x;
                     o.y = __uint_as_float(v[4 * j + 1]) + bj.y;
