@@ -128,16 +128,24 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 //              CTAs that write into this one with a multicast tcgen05.commit
 //   warps 2-5: epilogue TMEM -> registers (+bias) -> swizzled smem -> TMA store
 // ------------------------------------------------------------------------------------------------
-constexpr int IP_BM = 128, IP_BN = 192, IP_BK = 32, IP_STAGES = 4;   // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
+constexpr int IP_BM = 128, IP_BN = 192, IP_BK = 32;   // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
 constexpr int IP_CM = 4, IP_CN = 2, IP_CL = IP_CM * IP_CN;   // cluster shape
 constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (8 KB)
 constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (12 KB)
 constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 40 KB
 constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue staging tile of one warp: 32 rows x 32 fp32 (4 KB)
 constexpr int IP_OUT_RING = 3;                           // tiles per warp
-constexpr int IP_OUT_BYTES = 4 * IP_OUT_RING * IP_OUT_TILE;
 constexpr int IP_BIAS_BYTES = TC_NG * 4;                 // all 1920 folded biases, staged once per CTA
-constexpr int IP_SMEM_BYTES = IP_STAGES * IP_STAGE_BYTES + IP_OUT_BYTES + IP_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// STAGES / EPI_WARPS: layer 2's projection (K = 512) is main-loop bound: 4 smem stages, 4 epilogue warps.  Layer 1's (K = 48)
+// is epilogue bound -- one warp per SMSP cannot hide the TMEM-load / shared-memory latencies of the drain: 3 stages, 8 warps.
+template <int STAGES, int EPI_WARPS>
+struct IpCfg {
+    static constexpr int OUT_BYTES = EPI_WARPS * IP_OUT_RING * IP_OUT_TILE;
+    static constexpr int SMEM_BYTES = STAGES * IP_STAGE_BYTES + OUT_BYTES + IP_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two warps per TMEM lane quadrant");
+};
 constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 192 columns (at 0 and 256)
 constexpr int IP_N_TILES = TC_NG / IP_BN;                // 10
 static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
@@ -153,8 +161,11 @@ struct InprojParams {
     int m_groups;             // ceil(B * t_tiles / 4)
 };
 
-__global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant__ InprojParams p)
+template <int IP_STAGES, int EPI_WARPS>
+__global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_inproj_kernel(const __grid_constant__ InprojParams p)
 {
+    using C = IpCfg<IP_STAGES, EPI_WARPS>;
+    constexpr int IP_OUT_BYTES = C::OUT_BYTES;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char *stage_base = smem;
@@ -176,11 +187,11 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.a_hi); prefetch_tmap(&p.a_lo); prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo); prefetch_tmap(&p.out);
         for (int s = 0; s < IP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], IP_CM + IP_CN - 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<IP_TMEM_COLS>(tmem_slot);
-    for (int i = threadIdx.x; i < TC_NG; i += 192) bias_s[i] = __ldg(p.bias + i);
+    for (int i = threadIdx.x; i < TC_NG; i += C::THREADS) bias_s[i] = __ldg(p.bias + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -249,7 +260,9 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
         // Every warp drains its own 32 rows: TMEM -> registers (+bias) -> its private ring of swizzled 4 KB smem tiles ->
         // one TMA store per 32 x 32 tile.  No block-level barrier anywhere in the epilogue.
         const int q = warp & 3;
-        unsigned char *ring = out_base + q * (IP_OUT_RING * IP_OUT_TILE);
+        const int half = (warp - 2) >> 2;       // with 8 epilogue warps: the two warps of a quadrant take alternate 32-column chunks
+        constexpr int CSTEP = EPI_WARPS / 4;
+        unsigned char *ring = out_base + (warp - 2) * (IP_OUT_RING * IP_OUT_TILE);
         uint32_t tile = 0, chunk = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters, ++tile) {
             const int m_tile = (item / (IP_N_TILES / IP_CN)) * IP_CM + cx;
@@ -259,11 +272,11 @@ __global__ void __launch_bounds__(192, 1) tc_inproj_kernel(const __grid_constant
             const uint32_t acc = tile & 1;
             mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
             tc_fence_after();
-            for (int c = 0; c < IP_BN / 32; ++c, ++chunk) {
+            for (int c = half; c < IP_BN / 32; c += CSTEP, ++chunk) {
                 uint32_t v[32];
                 tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c * 32, v);
                 tmem_ld_wait();
-                if (c == IP_BN / 32 - 1) {                  // accumulator drained: hand it back to the MMA warp
+                if (c + CSTEP >= IP_BN / 32) {              // my part of the accumulator is drained: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -391,6 +404,37 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
     return 0;
 }
 
+template <int STAGES, int EPI_WARPS>
+static int launch_inproj(const InprojParams &prm, int n_items, const char *name, cudaStream_t st)
+{
+    using C = IpCfg<STAGES, EPI_WARPS>;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = IP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_clusters = 0;
+    if (!max_clusters) {
+        cudaError_t e = cudaFuncSetAttribute(tc_inproj_kernel<STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_inproj_kernel)");
+        cfg.gridDim = dim3(IP_CL * 16);
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, tc_inproj_kernel<STAGES, EPI_WARPS>, &cfg);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_inproj_kernel)");
+        if (n < 1) return fail(HSSB_E_DEVICE, "device cannot host an input-projection cluster");
+        max_clusters = n;
+    }
+    cfg.gridDim = dim3((unsigned)(IP_CL * std::min(max_clusters, n_items)));
+    ProfScope prof(name, st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_inproj_kernel<STAGES, EPI_WARPS>, prm);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_inproj_kernel)");
+    return 0;
+}
+
 // One layer's input projection on the tensor cores.  a_hi/a_lo: [B*T][pitch] fp16 planes.
 int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *a_lo, int pitch_elems, int64_t B, int64_t T,
               float *xproj /*[2][T][B][960]*/, cudaStream_t st)
@@ -425,32 +469,9 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     prm.t_tiles = (int)((T + IP_BM - 1) / IP_BM);
     prm.m_groups = (int)((B * prm.t_tiles + IP_CM - 1) / IP_CM);
 
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = IP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = IP_SMEM_BYTES;
-    cfg.stream = st;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    static int max_clusters = 0;
-    if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(tc_inproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IP_SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_inproj_kernel)");
-        cfg.gridDim = dim3(IP_CL * 16);
-        int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_inproj_kernel, &cfg);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_inproj_kernel)");
-        if (n < 1) return fail(HSSB_E_DEVICE, "device cannot host an input-projection cluster");
-        max_clusters = n;
-    }
     const int n_items = prm.m_groups * (IP_N_TILES / IP_CN);
-    cfg.gridDim = dim3((unsigned)(IP_CL * std::min(max_clusters, n_items)));
-    ProfScope prof(layer == 0 ? "tc_inproj_l0" : "tc_inproj_l1", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_inproj_kernel, prm);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_inproj_kernel)");
-    return 0;
+    if (layer == 0) return launch_inproj<3, 8>(prm, n_items, "tc_inproj_l0", st);
+    return launch_inproj<4, 4>(prm, n_items, "tc_inproj_l1", st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1190,7 +1211,7 @@ __device__ __forceinline__ void bulk_load_multicast(void *sdst, const void *gsrc
                  : "memory");
 }
 
-template <int S>
+template <int S, bool WARP_PUBLISH>
 __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
 {
     using C = RmCfg<S>;
@@ -1337,15 +1358,29 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
                     sts_b16(img + RP_NBH * 16 + col_of(i) * 16, hl);
                 }
                 fence_proxy_async_smem();
-                named_barrier(1 + s, 128);
-                if (tracer) RM_TRACE(TR_EPI_IMAGE, t, s);
-                if (q == 0 && elect_one()) {
-                    const int par = (t + 1) & 1;
-                    unsigned char *g = gslot + par * RP_SLICE;
-                    bulk_store_global(g, image(s), RP_SLICE);
-                    tma_store_commit();
-                    tma_store_wait<0>();
-                    bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE, g, RP_SLICE, &h_full[(s * 2 + par) * RP_G + (rank >> 1)], (uint16_t)0xFF);
+                const int par = (t + 1) & 1;
+                uint64_t *bar = &h_full[(s * 2 + par) * RP_G + (rank >> 1)];
+                if (WARP_PUBLISH) {
+                    // every warp publishes its own 1 KB piece: no block barrier, the exchange starts with the first warp done
+                    __syncwarp();
+                    if (tracer) RM_TRACE(TR_EPI_IMAGE, t, s);
+                    if (elect_one()) {
+                        unsigned char *g = gslot + par * RP_SLICE + q * RP_PIECE;
+                        bulk_store_global(g, image(s) + q * RP_PIECE, RP_PIECE);
+                        tma_store_commit();
+                        tma_store_wait<0>();
+                        bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + q * RP_PIECE, g, RP_PIECE, bar, (uint16_t)0xFF);
+                    }
+                } else {
+                    named_barrier(1 + s, 128);
+                    if (tracer) RM_TRACE(TR_EPI_IMAGE, t, s);
+                    if (q == 0 && elect_one()) {
+                        unsigned char *g = gslot + par * RP_SLICE;
+                        bulk_store_global(g, image(s), RP_SLICE);
+                        tma_store_commit();
+                        tma_store_wait<0>();
+                        bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE, g, RP_SLICE, bar, (uint16_t)0xFF);
+                    }
                 }
                 if (tracer) RM_TRACE(TR_EPI_COPIES, t, s);
             };
@@ -1378,10 +1413,12 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         const int r = 4 * (i >> 1) + (i & 1);
-                        ei[i] = ex2_approx(fminf((__uint_as_float(a[r]) + xnext[i].x) * -LOG2E, EMAX));
-                        ef[i] = ex2_approx(fminf((__uint_as_float(a[r + 2]) + xnext[i].y) * -LOG2E, EMAX));
+                        // e_i, e_f, e_o may overflow to +inf (1/inf = 0 is the right limit); e_g and e_c are clamped because
+                        // (1 - e) * 0 must not become inf * 0
+                        ei[i] = ex2_approx((__uint_as_float(a[r]) + xnext[i].x) * -LOG2E);
+                        ef[i] = ex2_approx((__uint_as_float(a[r + 2]) + xnext[i].y) * -LOG2E);
                         eg[i] = ex2_approx(fminf((__uint_as_float(b[r]) + xnext[i].z) * (-2.0f * LOG2E), EMAX));
-                        eo[i] = ex2_approx(fminf((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E, EMAX));
+                        eo[i] = ex2_approx((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E);
                     }
                     if (tracer) RM_TRACE(TR_EPI_ACT, t, s);
 #pragma unroll
@@ -1574,7 +1611,7 @@ static int launch_recurrent_pair(const RecurParams &prm_in, const __half *whh_fr
     return 0;
 }
 
-template <int S>
+template <int S, bool WARP_PUBLISH>
 static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
 {
     using C = RmCfg<S>;
@@ -1593,11 +1630,11 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_mc_kernel)");
         cfg.gridDim = dim3(16 * RC_CL);
         int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH>, &cfg);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_mc_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         max_clusters = std::min(n, 16);
@@ -1611,7 +1648,7 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
     cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
     ProfScope prof("tc_recurrent", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S>, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
     return 0;
 }
@@ -1652,9 +1689,9 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         const int64_t per_group = (rem + max_groups - 1) / max_groups;
         int nb, s, pair;
         if (force_nb) { nb = force_nb; s = force_s; pair = force_pair < 0 ? (nb % 32 == 0) : force_pair; }
-        else if (per_group <= 32) { nb = 32; s = 1; pair = 2; }     // pair = 2: the L2-multicast kernel (K5m), fastest at every batch
-        else if (per_group <= 64) { nb = 32; s = 2; pair = 2; }     // size measured (scripts/sweep_recurrent.py)
-        else { nb = 32; s = 3; pair = 2; }
+        else if (per_group <= 32) { nb = 32; s = 1; pair = 3; }     // pair = 2 / 3: the L2-multicast kernel (K5m) with per-sub-tile /
+        else if (per_group <= 64) { nb = 32; s = 2; pair = 3; }     // per-warp publishing; fastest at every batch size measured
+        else { nb = 32; s = 3; pair = 3; }                          // (scripts/sweep_recurrent.py)
         // (the CTA-pair variants -- cta_group::2, half the all-gather volume -- are validated but measured slower on
         //  B200: at N = 32 the paired MMA is issue-overhead bound, ~30 cycles each against ~18 for cta_group::1)
         int rc, done = 0;
@@ -1669,9 +1706,12 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         case 3221: rc = launch_recurrent<32, 2, true>(prm, rem, &done, xproj, st); break;
         case 3231: rc = launch_recurrent<32, 3, true>(prm, rem, &done, xproj, st); break;
         case 3241: rc = launch_recurrent<32, 4, true>(prm, rem, &done, xproj, st); break;
-        case 3212: rc = launch_recurrent_mc<1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3222: rc = launch_recurrent_mc<2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3232: rc = launch_recurrent_mc<3>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3212: rc = launch_recurrent_mc<1, false>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3222: rc = launch_recurrent_mc<2, false>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3232: rc = launch_recurrent_mc<3, false>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3213: rc = launch_recurrent_mc<1, true>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3223: rc = launch_recurrent_mc<2, true>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3233: rc = launch_recurrent_mc<3, true>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
         case 6411: rc = launch_recurrent_pair<1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
         case 6421: rc = launch_recurrent_pair<2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
         default: return fail(HSSB_E_MODE, "HSSB_RC_GEOM=%d,%d,%d unsupported", nb, s, pair);
