@@ -133,10 +133,10 @@ constexpr int IP_CM = 4, IP_CN = 2, IP_CL = IP_CM * IP_CN;   // cluster shape
 constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (8 KB)
 constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (12 KB)
 constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 40 KB
-constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue staging tile of one warp: 32 rows x 32 fp32 (4 KB)
-constexpr int IP_OUT_RING = 3;                           // tiles per warp
+constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue transposition tile of one warp: 32 rows x 32 fp32 (4 KB)
+constexpr int IP_OUT_RING = 1;                           // tiles per warp
 constexpr int IP_BIAS_BYTES = TC_NG * 4;                 // all 1920 folded biases, staged once per CTA
-// STAGES / EPI_WARPS: layer 2's projection (K = 512) is main-loop bound: 4 smem stages, 4 epilogue warps.  Layer 1's (K = 48)
+// STAGES / EPI_WARPS: layer 2's projection (K = 512) is main-loop bound: 5 smem stages, 4 epilogue warps.  Layer 1's (K = 48)
 // is epilogue bound -- one warp per SMSP cannot hide the TMEM-load / shared-memory latencies of the drain: 3 stages, 8 warps.
 template <int STAGES, int EPI_WARPS>
 struct IpCfg {
@@ -153,8 +153,9 @@ static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
 struct InprojParams {
     CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (32, 64, 1), SW64   (half of the A stage)
     CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 48), SW64  (quarter of the W stage)
-    CUtensorMap out;          // [g'(960), b, t, dir] fp32, box (32,1,32,1), SW128
+    float *out;               // xproj [dir][t][b][960] fp32
     const float *bias;        // [1920]
+    long long B;
     int k_real;               // true K rounded up to 16 (48 / 512)
     int T;
     int t_tiles;              // ceil(T/128)
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
     const int n_items = p.m_groups * (IP_N_TILES / IP_CN);
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&p.a_hi); prefetch_tmap(&p.a_lo); prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo); prefetch_tmap(&p.out);
+        prefetch_tmap(&p.a_hi); prefetch_tmap(&p.a_lo); prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
         for (int s = 0; s < IP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], IP_CM + IP_CN - 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
         fence_barrier_init();
@@ -281,11 +282,10 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                unsigned char *ob = ring + (chunk % IP_OUT_RING) * IP_OUT_TILE;
-                if (chunk >= IP_OUT_RING) {                 // the store that last used this tile has read it
-                    if (lane == 0) tma_store_wait_read<IP_OUT_RING - 1>();
-                    __syncwarp();
-                }
+                // registers (one row of 32 columns per thread) -> swizzled smem tile -> 16-byte global stores in which 8 consecutive
+                // lanes cover one 128-byte row segment: every store instruction writes four full lines.  (TMA stores of these
+                // 128-byte rows topped out at ~12 B/cycle/SM, half of what the HBM write stream of layer 1's projection needs.)
+                unsigned char *ob = ring;
                 const float4 *bias = reinterpret_cast<const float4 *>(bias_s + n0 + c * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -295,17 +295,22 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
                     o.y = __uint_as_float(v[4 * j + 1]) + bj.y;
                     o.z = __uint_as_float(v[4 * j + 2]) + bj.z;
                     o.w = __uint_as_float(v[4 * j + 3]) + bj.w;
-                    *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;   // 128B swizzle
+                    *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;   // 128B xor swizzle: conflict free both ways
                 }
-                fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    if (t0 + q * 32 < p.T) tma_store_4d(&p.out, ob, nl0 + c * 32, b, t0 + q * 32, dir);
-                    tma_store_commit();
+                {
+                    const int rsub = lane >> 3, c16 = lane & 7;
+                    float *gout = p.out + (((size_t)dir * p.T + t0 + q * 32) * p.B + b) * TC_G + nl0 + c * 32 + c16 * 4;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int row = 4 * j + rsub;
+                        const float4 o = *reinterpret_cast<const float4 *>(ob + row * 128 + ((c16 ^ (row & 7)) << 4));
+                        if (b < p.B && t0 + q * 32 + row < p.T) __stcs(reinterpret_cast<float4 *>(gout + (size_t)row * p.B * TC_G), o);   // padding tiles of the last m-group
+                    }
                 }
+                __syncwarp();
             }
         }
-        if (lane == 0) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -457,12 +462,8 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
         if (int rc = make_tmap(&prm.w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
         if (int rc = make_tmap(&prm.w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
-    {
-        const uint64_t dims[4] = {(uint64_t)TC_G, (uint64_t)B, (uint64_t)T, 2};
-        const uint64_t strides[3] = {(uint64_t)TC_G * 4, (uint64_t)B * TC_G * 4, (uint64_t)T * B * TC_G * 4};
-        const uint32_t box[4] = {32, 1, 32, 1};
-        if (int rc = make_tmap(&prm.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xproj, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    }
+    prm.out = xproj;
+    prm.B = B;
     prm.bias = m->tc_bias[layer];
     prm.k_real = kreal;
     prm.T = (int)T;
@@ -471,7 +472,7 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
 
     const int n_items = prm.m_groups * (IP_N_TILES / IP_CN);
     if (layer == 0) return launch_inproj<3, 8>(prm, n_items, "tc_inproj_l0", st);
-    return launch_inproj<4, 4>(prm, n_items, "tc_inproj_l1", st);
+    return launch_inproj<5, 4>(prm, n_items, "tc_inproj_l1", st);
 }
 
 // ------------------------------------------------------------------------------------------------
