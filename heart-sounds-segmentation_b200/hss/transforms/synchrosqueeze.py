@@ -74,6 +74,17 @@ class FSST:
             raise ValueError(f"FSST expects a 1-D signal or [N, 1], got shape {tuple(x.shape)}")
         return self.batch(x.unsqueeze(0))[0]
 
+    def frames(self, x: torch.Tensor, stride: int, n: int) -> torch.Tensor:
+        """Transform every ``n``-sample frame (one every ``stride`` samples) of a whole recording in one call.
+
+        Same frames as reference ``hss/utils/preprocess.py:39-56`` and same per-frame result as calling the
+        transform on each of them (every frame is zero-padded and z-scored on its own, reference
+        ``hss/datasets/heart_sounds.py:160-169``): ``[L, ...]`` stacked along a new first dimension.
+        """
+        from ..utils.preprocess import frame_batch
+
+        return self.batch(frame_batch(x, stride, n))
+
     def batch(self, x: torch.Tensor) -> torch.Tensor:
         """``x[B, N]`` -> raw ``[B, Kt, N]`` complex64 | abs ``[B, N, Kt]`` | stack ``[B, N, 2*Kt]`` float32."""
         if x.dim() != 2:

@@ -200,3 +200,32 @@ def test_host_entry_point_matches_device_path(lib):
     feats = np.zeros((B, N, 44), dtype=np.float32)
     _lib.check(lib.hssb_fsst_host(x.ctypes.data, B, N, FS, W.ctypes.data, dg.ctypes.data, 128, 4, 25, 2, feats.ctypes.data), "host")
     assert np.array_equal(feats, FSST(1000, window=W, truncate_freq=BAND, stack=True).batch(torch.from_numpy(x)).numpy())
+
+
+def test_frames_of_a_recording_equal_per_frame_calls(lib):
+    """FSST.frames: one call over the strided frames of a recording == the per-frame loop of the reference dataset."""
+    from hss.transforms import FSST
+    from hss.utils.preprocess import frame_signal
+
+    x = torch.from_numpy(fo.synth_pcg_batch(1, 9000, seed=5)[0])
+    f = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True)
+    out = f.frames(x.cuda(), 1000, 2000)
+    frames, _ = frame_signal(x, torch.zeros(x.shape[0], dtype=torch.int64), 1000, 2000)
+    assert out.shape == (len(frames), 2000, 44) and len(frames) == 7
+    for i, fr in enumerate(frames):
+        assert torch.equal(out[i].cpu(), f(fr))          # CPU-in -> CPU-out per-item path, same kernels
+
+
+def test_config5_long_windows_at_2khz(lib):
+    """BASELINE config 5 geometry at reduced size: 2 kHz windows, band (50, 400) Hz -> rows 4..25 -> 44 features, long N."""
+    from hss.transforms import FSST
+
+    fs, N, B = 2000.0, 30000, 3
+    x = torch.from_numpy(fo.synth_pcg_batch(B, N, fs=fs, seed=11))
+    w = fo.reference_window()
+    f = FSST(fs, window=w, truncate_freq=(50, 400), stack=True)
+    out = f.batch(x.cuda()).cpu().numpy()
+    assert out.shape == (B, N, 44)
+    for b in range(B):
+        ref = fo.fsst_features(x[b].numpy(), fs, w, stack=True, truncate_freq=(50, 400))
+        assert np.abs(out[b] - ref).max() < 5e-4

@@ -97,3 +97,26 @@ def test_metrics_from_counts():
     assert torch.allclose(m["precision_per_class"], torch.tensor([8 / 9, 9 / 11, 1.0, 10 / 15], dtype=torch.float64))
     assert abs(m["micro_accuracy"] - 32 / 40) < 1e-12
     assert metrics_from_counts(torch.zeros(4, 4))["f1"] == 0.0
+
+
+def test_frame_signal_matches_reference_contract():
+    """hss.utils.preprocess: L = floor((T - n) / stride) frames, truncated single frame otherwise (reference preprocess.py:39-56)."""
+    import math
+
+    import torch
+    from hss.utils.preprocess import frame_batch, frame_signal
+
+    for T, stride, n in ((35000, 1000, 2000), (4001, 1000, 2000), (2000, 1000, 2000), (1500, 1000, 2000), (9999, 333, 512)):
+        x = torch.arange(T, dtype=torch.float32)
+        y = (torch.arange(T) % 4).to(torch.int64)
+        frames, labels = frame_signal(x, y, stride, n)
+        L = math.floor((T - n) / stride)
+        if L <= 0:
+            assert len(frames) == 1 and frames[0].shape == (min(T, n), 1) and torch.equal(frames[0][:, 0], x[:n])
+            assert frame_batch(x, stride, n).shape == (1, min(T, n))
+            continue
+        assert len(frames) == len(labels) == L
+        for i, (f, l) in enumerate(zip(frames, labels)):
+            assert f.shape == (n, 1) and torch.equal(f[:, 0], x[i * stride:i * stride + n]) and torch.equal(l[:, 0], y[i * stride:i * stride + n])
+        fb = frame_batch(x, stride, n)
+        assert fb.shape == (L, n) and torch.equal(fb, torch.stack([f[:, 0] for f in frames]))
