@@ -537,7 +537,9 @@ struct RecurParams {
     int trace_steps;
     // pair kernel: TMA stores of relu(h) into the slot-layout outputs [B][T][512] (fp16 hi, lo planes or one fp32 tensor)
     alignas(64) CUtensorMap out_map[2];
+    alignas(64) CUtensorMap out_map16[2];   // the same with boxes of 16 batch columns (two epilogue warps per quadrant)
     unsigned char *gather;      // multicast kernel: L2 scratch [cluster][rank][S][2][4 KB] of the all-gather
+    int debug;                  // HSSB_RC_DEBUG knock-out switches for timing experiments (results are wrong when set)
 };
 
 // trace events (per step, per sub-tile): see scripts/trace_recurrent.py
@@ -1187,13 +1189,16 @@ __global__ void __launch_bounds__(RpCfg<S>::THREADS, 1) tc_recurrent_pair_kernel
 //     before it issues the multicast load, and nobody rewrites the image before the next accumulator, which
 //     depends on that load; the L2 scratch slot is double-buffered by step parity.
 // ------------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int EW>
 struct RmCfg {
+    static constexpr int NW = RP_NBH / EW;                           // batch columns per epilogue warp
     static constexpr int PER_SUB = 2 * RP_HBUF + RP_SLICE;           // 2 B buffers + one image
-    static constexpr int OUT_BYTES = S * 4 * 1024;                   // per epilogue warp: relu(h) tile for the TMA store
+    static constexpr int TILE_BYTES = 1024 / EW;                     // per epilogue warp: relu(h) tile for the TMA store
+    static constexpr int OUT_BYTES = S * 4 * EW * TILE_BYTES;
     static constexpr int BAR_BYTES = 512;
     static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + BAR_BYTES + 1024;
-    static constexpr int THREADS = 32 * S + 128 * S;                 // S issuer warps + S x 4 epilogue warps
+    static constexpr int THREADS = 32 * S + 128 * S * EW;            // S issuer warps + S x 4 x EW epilogue warps
+    static_assert(EW == 1 || EW == 2, "one or two epilogue warps per TMEM lane quadrant and sub-tile");
     static_assert(S * RP_NBH <= 256, "accumulators must fit in the TMEM columns left of the weights");
     static_assert((2 * S * RP_G + S) * 8 + 8 <= BAR_BYTES, "barrier area too small");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -1212,10 +1217,11 @@ __device__ __forceinline__ void bulk_load_multicast(void *sdst, const void *gsrc
                  : "memory");
 }
 
-template <int S, bool WARP_PUBLISH>
-__global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
+template <int S, bool WARP_PUBLISH, int EW>
+__global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
 {
-    using C = RmCfg<S>;
+    using C = RmCfg<S, EW>;
+    static_assert(EW == 1 || WARP_PUBLISH, "two warps per quadrant publish per warp");
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * RP_HBUF; };
@@ -1242,8 +1248,9 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * S * RP_G + S; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
-        prefetch_tmap(&p.out_map[0]);
-        if (!p.out_f32) prefetch_tmap(&p.out_map[1]);
+        const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;
+        prefetch_tmap(&om[0]);
+        if (!p.out_f32) prefetch_tmap(&om[1]);
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -1284,6 +1291,7 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
                         const uint64_t b_lo = make_smem_desc(blk + RP_PIECE / 2, RP_PIECE, 128, LAYOUT_NONE);
                         const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
                         mma_f16_ts(d_tmem, a_hi, b_hi, idesc, (gi | jj) != 0);
+                        if (p.debug & 8) continue;                     // (timing experiment: one MMA per K16 step)
                         mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
                         mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
                     }
@@ -1294,16 +1302,18 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
         }
     } else {
         // ================= epilogue warp: sub-tile s, TMEM lane quadrant q =================
-        const int s = (warp - S) >> 2;
+        const int s = (warp - S) / (4 * EW);
+        const int half = ((warp - S) >> 2) % EW;     // which NW-column part of the sub-tile this warp drains
+        const int cbase = half * C::NW;
         const int q = warp & 3;
         const int ul = lane >> 2, cp = lane & 3;     // unit within the k-chunk q; column pair
         const int u = 8 * q + ul;                    // unit 0..31 of this CTA (30, 31 padding)
         const bool unit_ok = u < RC_U;
         const long long b0 = sub_b0(s);
-        const bool tracer = (q == 0 && lane == 0);
-        unsigned char *out_tile = out_tiles + (warp - S) * 1024;
+        const bool tracer = (q == 0 && lane == 0 && half == 0);
+        unsigned char *out_tile = out_tiles + (warp - S) * C::TILE_BYTES;
 
-        if (s == 0) {
+        if (s == 0 && half == 0) {
             // one-time: W_hh slice -> TMEM.  This thread owns lane 32q + lane; column c holds k' = 2c, 2c+1.
             const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * RC_KP;
 #pragma unroll 1
@@ -1322,12 +1332,13 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
         }
 
         if (b0 < B) {
-            constexpr int NI = RP_NBH / 4;              // 8 (unit, column) cells per thread: columns 8*(i/2) + 2*cp + (i&1)
+            constexpr int NW = C::NW;
+            constexpr int NI = NW / 4;                  // (unit, column) cells per thread: columns cbase + 8*(i/2) + 2*cp + (i&1)
             constexpr float LOG2E = 1.4426950408889634f;
             constexpr float EMAX = 60.0f;               // exponent clamp: (1 + 2^60)^2 is finite, sigmoid(-41) = 0 in fp32 anyway
             const long long left = B - b0;
             const int ncols = (int)(left < RP_NBH ? left : RP_NBH);
-            auto col_of = [&](int i) { return 8 * (i >> 1) + 2 * cp + (i & 1); };
+            auto col_of = [&](int i) { return cbase + 8 * (i >> 1) + 2 * cp + (i & 1); };
             const int ux = unit_ok ? u : RC_U - 1;
             const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * B * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
             const long long xstep = (dir ? -1 : 1) * B * TC_G;
@@ -1339,11 +1350,11 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
                     const int c = col_of(i);
-                    xnext[i] = (c < ncols) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xnext[i] = (c < ncols && !(p.debug & 1)) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 xp_next += xstep;
             };
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * RP_NBH;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * RP_NBH + cbase;
             const int out_c0 = dir * (TC_OP / 2) + (int)rank * 32 + 8 * q;      // first column of this warp's 8 units
             const size_t state_o = ((size_t)dir * B + b0) * TC_H + rank * RC_U + u;      // + column * TC_H
             unsigned char *gslot = p.gather + ((((size_t)cid * RC_CL + rank) * S + s) * 2) * RP_SLICE;     // [parity][4 KB]
@@ -1362,15 +1373,27 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
                 const int par = (t + 1) & 1;
                 uint64_t *bar = &h_full[(s * 2 + par) * RP_G + (rank >> 1)];
                 if (WARP_PUBLISH) {
-                    // every warp publishes its own 1 KB piece: no block barrier, the exchange starts with the first warp done
+                    // every warp publishes its own piece: no block barrier, the exchange starts with the first warp done
                     __syncwarp();
                     if (tracer) RM_TRACE(TR_EPI_IMAGE, t, s);
                     if (elect_one()) {
-                        unsigned char *g = gslot + par * RP_SLICE + q * RP_PIECE;
-                        bulk_store_global(g, image(s) + q * RP_PIECE, RP_PIECE);
-                        tma_store_commit();
-                        tma_store_wait<0>();
-                        bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + q * RP_PIECE, g, RP_PIECE, bar, (uint16_t)0xFF);
+                        if (EW == 1) {
+                            unsigned char *g = gslot + par * RP_SLICE + q * RP_PIECE;
+                            bulk_store_global(g, image(s) + q * RP_PIECE, RP_PIECE);
+                            tma_store_commit();
+                            tma_store_wait<0>();
+                            bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + q * RP_PIECE, g, RP_PIECE, bar, (uint16_t)0xFF);
+                        } else {
+                            // my NW columns are one run of NW*16 bytes in each plane of the piece
+                            const int o0 = q * RP_PIECE + cbase * 16, o1 = o0 + RP_PIECE / 2;
+                            unsigned char *g = gslot + par * RP_SLICE;
+                            bulk_store_global(g + o0, image(s) + o0, NW * 16);
+                            bulk_store_global(g + o1, image(s) + o1, NW * 16);
+                            tma_store_commit();
+                            tma_store_wait<0>();
+                            bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + o0, g + o0, NW * 16, bar, (uint16_t)0xFF);
+                            bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + o1, g + o1, NW * 16, bar, (uint16_t)0xFF);
+                        }
                     }
                 } else {
                     named_barrier(1 + s, 128);
@@ -1405,9 +1428,14 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
                 if (tracer) RM_TRACE(TR_EPI_DFULL, t, s);
                 float hv[NI];
                 {
-                    uint32_t a[16], b[16];      // a: gates i (lane ul), f (lane ul+8);  b: gates g, o;  [4k + 2*gate + c] = column 8k + 2cp + c
-                    tmem_ld_16x256b_x4(taddr, a);
-                    tmem_ld_16x256b_x4(taddr + (16u << 16), b);
+                    uint32_t a[2 * NI], b[2 * NI];      // a: gates i (lane ul), f (lane ul+8);  b: gates g, o;  [4k + 2*gate + c] = column cbase + 8k + 2cp + c
+                    if (EW == 1) {
+                        tmem_ld_16x256b_x4(taddr, *reinterpret_cast<uint32_t(*)[16]>(&a[0]));
+                        tmem_ld_16x256b_x4(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[16]>(&b[0]));
+                    } else {
+                        tmem_ld_16x256b_x2(taddr, *reinterpret_cast<uint32_t(*)[8]>(&a[0]));
+                        tmem_ld_16x256b_x2(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[8]>(&b[0]));
+                    }
                     tmem_ld_wait();
                     tc_fence_before();
                     float ei[NI], ef[NI], eg[NI], eo[NI];
@@ -1422,6 +1450,10 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
                         eo[i] = ex2_approx((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E);
                     }
                     if (tracer) RM_TRACE(TR_EPI_ACT, t, s);
+                    if (p.debug & 4) {                                  // (timing experiment: no cell math)
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) hv[i] = unit_ok ? 0.25f * (ei[i] + ef[i]) * 1e-3f + 1e-3f * (eg[i] + eo[i]) : 0.0f;
+                    } else
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         const float ig = (1.0f - eg[i]) * rcp_approx((1.0f + ei[i]) * (1.0f + eg[i]));      // sigmoid(i) tanh(g)
@@ -1440,21 +1472,22 @@ __global__ void __launch_bounds__(RmCfg<S>::THREADS, 1) tc_recurrent_mc_kernel(c
                 const uint32_t tile = smem_u32(out_tile);
                 if (p.out_f32) {
 #pragma unroll
-                    for (int i = 0; i < NI; ++i) sts_b32(tile + col_of(i) * 32 + ul * 4, fmaxf(hv[i], 0.f));
+                    for (int i = 0; i < NI; ++i) sts_b32(tile + (col_of(i) - cbase) * 32 + ul * 4, fmaxf(hv[i], 0.f));
                 } else {
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         __half hh, hl;
                         split_f16(fmaxf(hv[i], 0.f), hh, hl);
-                        sts_b16(tile + col_of(i) * 16 + ul * 2, hh);
-                        sts_b16(tile + 512 + col_of(i) * 16 + ul * 2, hl);
+                        sts_b16(tile + (col_of(i) - cbase) * 16 + ul * 2, hh);
+                        sts_b16(tile + NW * 16 + (col_of(i) - cbase) * 16 + ul * 2, hl);
                     }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (elect_one()) {
-                    tma_store_3d(&p.out_map[0], out_tile, out_c0, t_idx, (int)b0);
-                    if (!p.out_f32) tma_store_3d(&p.out_map[1], out_tile + 512, out_c0, t_idx, (int)b0);
+                if (!(p.debug & 2) && elect_one()) {
+                    const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;       // box of 32 / 16 batch columns
+                    tma_store_3d(&om[0], out_tile, out_c0, t_idx, (int)b0 + cbase);
+                    if (!p.out_f32) tma_store_3d(&om[1], out_tile + NW * 16, out_c0, t_idx, (int)b0 + cbase);
                     tma_store_commit();
                 }
                 t_idx += dir ? -1 : 1;
@@ -1612,10 +1645,10 @@ static int launch_recurrent_pair(const RecurParams &prm_in, const __half *whh_fr
     return 0;
 }
 
-template <int S, bool WARP_PUBLISH>
+template <int S, bool WARP_PUBLISH, int EW>
 static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
 {
-    using C = RmCfg<S>;
+    using C = RmCfg<S, EW>;
     RecurParams prm = prm_in;
     prm.whh = whh_frag;
     prm.trace = g_trace_buf;
@@ -1631,11 +1664,11 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_mc_kernel)");
         cfg.gridDim = dim3(16 * RC_CL);
         int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW>, &cfg);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_mc_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         max_clusters = std::min(n, 16);
@@ -1647,9 +1680,10 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     prm.groups = groups;
     prm.stagger_ns = 600;
     if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
+    if (const char *e = getenv("HSSB_RC_DEBUG")) prm.debug = atoi(e);
     cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
     ProfScope prof("tc_recurrent", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH>, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
     return 0;
 }
@@ -1673,6 +1707,9 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
         if (int rc = make_tmap(&prm.out_map[0], dt, 3, f32 ? (const void *)out_f32 : (const void *)out_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
         if (int rc = make_tmap(&prm.out_map[1], dt, 3, f32 ? (const void *)out_f32 : (const void *)out_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        const uint32_t box16[3] = {8, 1, RP_NBH / 2};
+        if (int rc = make_tmap(&prm.out_map16[0], dt, 3, f32 ? (const void *)out_f32 : (const void *)out_hi, dims, strides, box16, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        if (int rc = make_tmap(&prm.out_map16[1], dt, 3, f32 ? (const void *)out_f32 : (const void *)out_lo, dims, strides, box16, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     }
     // at most 8 groups per direction are co-resident (16 clusters of 8 CTAs on 148 SMs); larger batches
     // run as successive launches over blocks of batch columns
@@ -1690,9 +1727,11 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         const int64_t per_group = (rem + max_groups - 1) / max_groups;
         int nb, s, pair;
         if (force_nb) { nb = force_nb; s = force_s; pair = force_pair < 0 ? (nb % 32 == 0) : force_pair; }
-        else if (per_group <= 32) { nb = 32; s = 1; pair = 3; }     // pair = 2 / 3: the L2-multicast kernel (K5m) with per-sub-tile /
-        else if (per_group <= 64) { nb = 32; s = 2; pair = 3; }     // per-warp publishing; fastest at every batch size measured
-        else { nb = 32; s = 3; pair = 3; }                          // (scripts/sweep_recurrent.py)
+        // the L2-multicast kernel (K5m) is the fastest at every batch size measured (scripts/sweep_recurrent.py); variants
+        // pair = 2: one publisher per sub-tile, 3: per-warp publishing, 4: per-warp + two epilogue warps per TMEM quadrant
+        else if (per_group <= 32) { nb = 32; s = 1; pair = 4; }
+        else if (per_group <= 64) { nb = 32; s = 2; pair = 4; }
+        else { nb = 32; s = 3; pair = 3; }
         // (the CTA-pair variants -- cta_group::2, half the all-gather volume -- are validated but measured slower on
         //  B200: at N = 32 the paired MMA is issue-overhead bound, ~30 cycles each against ~18 for cta_group::1)
         int rc, done = 0;
@@ -1707,12 +1746,15 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         case 3221: rc = launch_recurrent<32, 2, true>(prm, rem, &done, xproj, st); break;
         case 3231: rc = launch_recurrent<32, 3, true>(prm, rem, &done, xproj, st); break;
         case 3241: rc = launch_recurrent<32, 4, true>(prm, rem, &done, xproj, st); break;
-        case 3212: rc = launch_recurrent_mc<1, false>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3222: rc = launch_recurrent_mc<2, false>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3232: rc = launch_recurrent_mc<3, false>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3213: rc = launch_recurrent_mc<1, true>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3223: rc = launch_recurrent_mc<2, true>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3233: rc = launch_recurrent_mc<3, true>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3212: rc = launch_recurrent_mc<1, false, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3222: rc = launch_recurrent_mc<2, false, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3232: rc = launch_recurrent_mc<3, false, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3213: rc = launch_recurrent_mc<1, true, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3223: rc = launch_recurrent_mc<2, true, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3233: rc = launch_recurrent_mc<3, true, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3214: rc = launch_recurrent_mc<1, true, 2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3224: rc = launch_recurrent_mc<2, true, 2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
+        case 3234: rc = launch_recurrent_mc<3, true, 2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
         case 6411: rc = launch_recurrent_pair<1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
         case 6421: rc = launch_recurrent_pair<2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
         default: return fail(HSSB_E_MODE, "HSSB_RC_GEOM=%d,%d,%d unsupported", nb, s, pair);

@@ -93,7 +93,7 @@ def test_odd_batch_and_short_sequences(lib):
     assert m(torch.zeros(2, 0, 44)).shape == (2, 0, 4)
 
 
-@pytest.mark.parametrize("geom", ["16,3,0", "32,3,0", "32,2,1", "64,2,1", "64,1,1", "32,1,2", "32,2,2", "32,3,2", "32,1,3", "32,3,3"])
+@pytest.mark.parametrize("geom", ["16,3,0", "32,3,0", "32,2,1", "64,2,1", "64,1,1", "32,1,2", "32,2,2", "32,3,2", "32,1,3", "32,3,3", "32,1,4", "32,2,4", "32,3,4"])
 @pytest.mark.parametrize("B,T", [(130, 40), (97, 23)])
 def test_recurrence_geometries(lib, geom, B, T, monkeypatch):
     """Every sub-tile geometry of the tcgen05 recurrence (single CTA / CTA pair, ragged last group) against torch-CPU."""
