@@ -156,6 +156,7 @@ struct InprojParams {
     float *out;               // xproj [dir][t][b][960] fp32
     const float *bias;        // [1920]
     long long B;
+    int debug;                // HSSB_IP_DEBUG bit 0: skip the global stores (timing experiment; results are wrong when set)
     int k_real;               // true K rounded up to 16 (48 / 512)
     int T;
     int t_tiles;              // ceil(T/128)
@@ -257,14 +258,19 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-        // Every warp drains its own 32 rows: TMEM -> registers (+bias) -> its private ring of swizzled 4 KB smem tiles ->
-        // one TMA store per 32 x 32 tile.  No block-level barrier anywhere in the epilogue.
+        // ===== epilogue: warps 2.., TMEM lane quadrant = warp % 4; with 8 warps the two warps of a quadrant take alternate chunks =====
+        // A warp first pulls ALL of its 32-column chunks of the accumulator into registers and hands the accumulator back to the
+        // MMA warp at once (the stores below are slow -- 1.5 ms of layer 2's projection -- and must not hold TMEM), then per chunk:
+        // registers (one row of 32 columns per thread, + bias) -> xor-swizzled smem tile -> 16-byte global stores in which 8
+        // consecutive lanes cover one 128-byte row segment (every store instruction writes four full lines).
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;       // with 8 epilogue warps: the two warps of a quadrant take alternate 32-column chunks
+        const int half = (warp - 2) >> 2;
         constexpr int CSTEP = EPI_WARPS / 4;
-        unsigned char *ring = out_base + (warp - 2) * (IP_OUT_RING * IP_OUT_TILE);
-        uint32_t tile = 0, chunk = 0;
+        constexpr int NCH = (IP_BN / 32) / CSTEP;           // chunks per warp: 6 (4 warps) or 3 (8 warps)
+        constexpr int NPASS = (NCH > 3) ? 2 : 1;            // registers hold 3 chunks at a time
+        constexpr int PCH = NCH / NPASS;
+        unsigned char *ob = out_base + (warp - 2) * IP_OUT_TILE;
+        uint32_t tile = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters, ++tile) {
             const int m_tile = (item / (IP_N_TILES / IP_CN)) * IP_CM + cx;
             const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * IP_BM;
@@ -273,42 +279,44 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
             const uint32_t acc = tile & 1;
             mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
             tc_fence_after();
-            for (int c = half; c < IP_BN / 32; c += CSTEP, ++chunk) {
-                uint32_t v[32];
-                tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c * 32, v);
+#pragma unroll
+            for (int pass = 0; pass < NPASS; ++pass) {
+                uint32_t v[PCH][32];
+#pragma unroll
+                for (int i = 0; i < PCH; ++i)
+                    tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (half + (pass * PCH + i) * CSTEP) * 32, v[i]);
                 tmem_ld_wait();
-                if (c + CSTEP >= IP_BN / 32) {              // my part of the accumulator is drained: hand it back to the MMA warp
+                if (pass == NPASS - 1) {                    // my part of the accumulator is in registers: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                // registers (one row of 32 columns per thread) -> swizzled smem tile -> 16-byte global stores in which 8 consecutive
-                // lanes cover one 128-byte row segment: every store instruction writes four full lines.  (TMA stores of these
-                // 128-byte rows topped out at ~12 B/cycle/SM, half of what the HBM write stream of layer 1's projection needs.)
-                unsigned char *ob = ring;
-                const float4 *bias = reinterpret_cast<const float4 *>(bias_s + n0 + c * 32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bj = bias[j];                 // shared-memory broadcast
-                    float4 o;
-                    o.x = __uint_as_float(v[4 * j + 0]) + bj.x;
-                    o.y = __uint_as_float(v[4 * j + 1]) + bj.y;
-                    o.z = __uint_as_float(v[4 * j + 2]) + bj.z;
-                    o.w = __uint_as_float(v[4 * j + 3]) + bj.w;
-                    *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;   // 128B xor swizzle: conflict free both ways
-                }
-                __syncwarp();
-                {
+                for (int i = 0; i < PCH; ++i) {
+                    const int c = half + (pass * PCH + i) * CSTEP;
+                    const float4 *bias = reinterpret_cast<const float4 *>(bias_s + n0 + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bj = bias[j];                 // shared-memory broadcast
+                        float4 o;
+                        o.x = __uint_as_float(v[i][4 * j + 0]) + bj.x;
+                        o.y = __uint_as_float(v[i][4 * j + 1]) + bj.y;
+                        o.z = __uint_as_float(v[i][4 * j + 2]) + bj.z;
+                        o.w = __uint_as_float(v[i][4 * j + 3]) + bj.w;
+                        *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;   // 128B xor swizzle: conflict free both ways
+                    }
+                    __syncwarp();
                     const int rsub = lane >> 3, c16 = lane & 7;
                     float *gout = p.out + (((size_t)dir * p.T + t0 + q * 32) * p.B + b) * TC_G + nl0 + c * 32 + c16 * 4;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int row = 4 * j + rsub;
                         const float4 o = *reinterpret_cast<const float4 *>(ob + row * 128 + ((c16 ^ (row & 7)) << 4));
-                        if (b < p.B && t0 + q * 32 + row < p.T) __stcs(reinterpret_cast<float4 *>(gout + (size_t)row * p.B * TC_G), o);   // padding tiles of the last m-group
+                        if (b < p.B && t0 + q * 32 + row < p.T && !(p.debug & 1))                    // (b >= B: padding tiles of the last m-group)
+                            __stcs(reinterpret_cast<float4 *>(gout + (size_t)row * p.B * TC_G), o);
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     }
@@ -464,6 +472,8 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     }
     prm.out = xproj;
     prm.B = B;
+    prm.debug = 0;
+    if (const char *e = getenv("HSSB_IP_DEBUG")) prm.debug = atoi(e);
     prm.bias = m->tc_bias[layer];
     prm.k_real = kreal;
     prm.T = (int)T;
@@ -472,6 +482,10 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
 
     const int n_items = prm.m_groups * (IP_N_TILES / IP_CN);
     if (layer == 0) return launch_inproj<3, 8>(prm, n_items, "tc_inproj_l0", st);
+    if (const char *e = getenv("HSSB_IP_L1")) {
+        if (atoi(e) == 48) return launch_inproj<4, 8>(prm, n_items, "tc_inproj_l1", st);
+        if (atoi(e) == 44) return launch_inproj<4, 4>(prm, n_items, "tc_inproj_l1", st);
+    }
     return launch_inproj<5, 4>(prm, n_items, "tc_inproj_l1", st);
 }
 
