@@ -288,7 +288,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 gbs = BYTES_PER_SAMPLE[name] * units / (per_launch_ms * 1e-3) / 1e9
                 entry.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]})
             elif name in FLOP_PER_SAMPLE:
-                tf = FLOP_PER_SAMPLE[name] * units / (tot / args.steps * 1e-3) / 1e12
+                flop = FLOP_PER_SAMPLE[name]
+                if name == "tc_recurrent" and "tc_inproj_l0" not in prof:
+                    flop += FLOP_PER_SAMPLE["tc_inproj_l0"]        # layer 1's input projection is fused into the recurrence kernel
+                tf = flop * units / (tot / args.steps * 1e-3) / 1e12
                 entry.update({"bound": "tensor", "achieved": tf, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["tensor_tflops"],
                               "note": "useful FLOPs (1x) over all launches of this kernel in a step"})
             per_kernel[name] = entry

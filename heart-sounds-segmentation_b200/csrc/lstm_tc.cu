@@ -39,6 +39,8 @@ constexpr size_t TC_GATHER_BYTES = (size_t)16 * 8 * 3 * 2 * 4096;   // L2 scratc
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_whh_kernel(const float *__restrict__ w, int dir, int frag, __half *__restrict__ dst);   // defined with K5
 __global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict__ dst);
+__global__ void pack_wih0_frag_kernel(const float *__restrict__ w, const float *__restrict__ b_ih, const float *__restrict__ b_hh, int F,
+                                      int dir, __half *__restrict__ dst, float *__restrict__ bias);
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -355,6 +357,8 @@ size_t tc_pack_bytes(int F, int H)
         n += 2 * align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 256, 256);        // whh planes [dir][rank][plane][128][256], two row orders
     }
     n += align_up(sizeof(float) * 4 * TC_OP, 256);                             // linear weights in slot layout
+    n += align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 64, 256);                 // layer-1 W_ih slices for the fused projection
+    n += align_up(sizeof(float) * 2 * 8 * 128, 256);                           // ... and their folded biases
     return n;
 }
 
@@ -371,6 +375,10 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&tmp), sizeof(float) * tmp_floats, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tc_pack)");
     int rc = 0;
+    m->tc_wih0_frag = reinterpret_cast<__half *>(base + off);
+    off += align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 64, 256);
+    m->tc_bias0_frag = reinterpret_cast<float *>(base + off);
+    off += align_up(sizeof(float) * 2 * 8 * 128, 256);
     for (int l = 0; l < 2 && !rc; ++l) {
         const int Kp = kp_of_layer(l, m->F);
         m->tc_wih[l] = reinterpret_cast<__half *>(base + off);
@@ -391,6 +399,7 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
                 break;
             }
             pack_wih_kernel<<<TC_G, 128, 0, st>>>(w, bi, bh, kin[l], Kp, d, l, hi, lo, m->tc_bias[l]);
+            if (l == 0) pack_wih0_frag_kernel<<<8 * 128, 64, 0, st>>>(w, bi, bh, kin[0], d, m->tc_wih0_frag, m->tc_bias0_frag);
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "pack_wih_kernel"); break; }
             if ((e = cudaMemcpyAsync(w, p->w_hh[l][d], sizeof(float) * TC_G * TC_H, cudaMemcpyDefault, st)) != cudaSuccess) {
                 rc = cuda_fail(e, "cudaMemcpyAsync(tc_pack w_hh)");
@@ -552,8 +561,14 @@ struct RecurParams {
     // pair kernel: TMA stores of relu(h) into the slot-layout outputs [B][T][512] (fp16 hi, lo planes or one fp32 tensor)
     alignas(64) CUtensorMap out_map[2];
     alignas(64) CUtensorMap out_map16[2];   // the same with boxes of 16 batch columns (two epilogue warps per quadrant)
+    // fused layer-1 input projection (multicast kernel): x planes [chunk][b][t][8] fp16 (hi, lo), W_ih slices
+    // [dir][rank][plane][128 rows in fragment order][64] fp16 and b_ih + b_hh [dir][rank][128] in the same row order
+    alignas(64) CUtensorMap x_map[2];
+    const __half *wih0;
+    const float *bias0;
     unsigned char *gather;      // multicast kernel: L2 scratch [cluster][rank][S][2][4 KB] of the all-gather
     int debug;                  // HSSB_RC_DEBUG knock-out switches for timing experiments (results are wrong when set)
+    int layer;
 };
 
 // trace events (per step, per sub-tile): see scripts/trace_recurrent.py
@@ -1203,20 +1218,36 @@ __global__ void __launch_bounds__(RpCfg<S>::THREADS, 1) tc_recurrent_pair_kernel
 //     before it issues the multicast load, and nobody rewrites the image before the next accumulator, which
 //     depends on that load; the L2 scratch slot is double-buffered by step parity.
 // ------------------------------------------------------------------------------------------------
-template <int S, int EW>
+constexpr int RX_KSTEPS = 3;                       // fused layer-1 input projection: K16 steps of the x operand (input_size <= 48)
+constexpr int RX_CHUNKS = 2 * RX_KSTEPS;           // 8-feature k-chunks
+constexpr int RX_PLANE = RX_CHUNKS * RP_NBH * 16;  // [chunk][32 cols][8 features] fp16 = 3 KB
+constexpr int RX_TMEM = 256 + 96;                  // TMEM column of the W_ih slice (hi plane; lo plane 8*RX_KSTEPS columns further)
+
+template <int S, int EW, bool FUSE_X = false>
 struct RmCfg {
     static constexpr int NW = RP_NBH / EW;                           // batch columns per epilogue warp
     static constexpr int PER_SUB = 2 * RP_HBUF + RP_SLICE;           // 2 B buffers + one image
     static constexpr int TILE_BYTES = 1024 / EW;                     // per epilogue warp: relu(h) tile for the TMA store
-    static constexpr int OUT_BYTES = S * 4 * EW * TILE_BYTES;
+    // fused: the relu(h) tile of a warp reuses its piece of the image (free again once the bulk store of the publish has
+    // completed), which makes room for the x operand buffers
+    static constexpr int OUT_BYTES = FUSE_X ? 0 : S * 4 * EW * TILE_BYTES;
+    static constexpr int X_BYTES = FUSE_X ? S * 2 * RX_PLANE : 0;
     static constexpr int BAR_BYTES = 512;
-    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + X_BYTES + BAR_BYTES + 1024;
     static constexpr int THREADS = 32 * S + 128 * S * EW;            // S issuer warps + S x 4 x EW epilogue warps
     static_assert(EW == 1 || EW == 2, "one or two epilogue warps per TMEM lane quadrant and sub-tile");
-    static_assert(S * RP_NBH <= 256, "accumulators must fit in the TMEM columns left of the weights");
-    static_assert((2 * S * RP_G + S) * 8 + 8 <= BAR_BYTES, "barrier area too small");
+    static_assert(S * RP_NBH <= 96, "accumulators sit in TMEM columns [256, 352)");
+    static_assert((2 * S * RP_G + 4 * S) * 8 + 8 <= BAR_BYTES, "barrier area too small");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
+
+__device__ __forceinline__ void tma_load_4d_nomc(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
 __device__ __forceinline__ void bulk_store_global(void *gdst, const void *ssrc, uint32_t bytes)
 {
@@ -1231,20 +1262,25 @@ __device__ __forceinline__ void bulk_load_multicast(void *sdst, const void *gsrc
                  : "memory");
 }
 
-template <int S, bool WARP_PUBLISH, int EW>
-__global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
+template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X>
+__global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
 {
-    using C = RmCfg<S, EW>;
+    using C = RmCfg<S, EW, FUSE_X>;
     static_assert(EW == 1 || WARP_PUBLISH, "two warps per quadrant publish per warp");
+    static_assert(!FUSE_X || WARP_PUBLISH, "the fused kernel reuses each warp's image piece as its output tile");
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * RP_HBUF; };
     auto image = [&](int s) { return smem + s * C::PER_SUB + 2 * RP_HBUF; };
     unsigned char *out_tiles = smem + S * C::PER_SUB;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(out_tiles + C::OUT_BYTES);
+    unsigned char *xbufs = out_tiles + C::OUT_BYTES;             // fused: [S][plane][chunk][32 cols][8 features] fp16
+    uint64_t *bars = reinterpret_cast<uint64_t *>(xbufs + C::X_BYTES);
     uint64_t *h_full = bars;                         // [S][2][G]  slices of source pair g have landed in my buffer
     uint64_t *d_full = bars + 2 * S * RP_G;          // [S]        accumulator complete
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + S);
+    uint64_t *d_empty = d_full + S;                  // [S]        (fused) every epilogue warp has read the accumulator
+    uint64_t *x_full = d_full + 2 * S;               // [S]        (fused) x_t operand landed
+    uint64_t *x_empty = d_full + 3 * S;              // [S]        (fused) the MMAs reading the x operand are complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + 4 * S);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -1260,14 +1296,16 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
     } while (0)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * S * RP_G + S; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 2 * S * RP_G + 4 * S; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < S; ++i) mbar_init(&d_empty[i], 4 * EW);
         fence_barrier_init();
+        if (FUSE_X) { prefetch_tmap(&p.x_map[0]); prefetch_tmap(&p.x_map[1]); }
         const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;
         prefetch_tmap(&om[0]);
         if (!p.out_f32) prefetch_tmap(&om[1]);
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
-    for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES + C::X_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1285,10 +1323,35 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
             constexpr uint32_t idesc = make_idesc_f16(128, RP_NBH);
             const uint32_t d_tmem = tmem_base + 256 + s * RP_NBH;
             const int Ti = (int)T;
+            unsigned char *xb = xbufs + s * 2 * RX_PLANE;
+            auto load_x_operand = [&](int t) {           // x_t of this sub-tile's 32 columns: both fp16 planes, [chunk][col][8]
+                const int t_idx = dir ? Ti - 1 - t : t;
+                mbar_arrive_expect_tx(&x_full[s], 2 * RX_PLANE);
+                tma_load_4d_nomc(xb, &p.x_map[0], &x_full[s], 0, t_idx, (int)sub_b0(s), 0);
+                tma_load_4d_nomc(xb + RX_PLANE, &p.x_map[1], &x_full[s], 0, t_idx, (int)sub_b0(s), 0);
+            };
+            if (FUSE_X) load_x_operand(0);
             for (int t = 0; t < Ti; ++t) {
                 const int par = t & 1;
                 const uint32_t ph = (uint32_t)((t >> 1) & 1);
                 const uint32_t hb = smem_u32(hbuf(s, par));
+                if (FUSE_X) {
+                    // W_ih . x_t first: it does not depend on h_{t-1}, only on the epilogue having read the previous accumulator
+                    if (t > 0) mbar_wait(&d_empty[s], (uint32_t)((t - 1) & 1));
+                    mbar_wait(&x_full[s], (uint32_t)(t & 1));
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < RX_KSTEPS; ++j) {
+                        const uint32_t blk = smem_u32(xb) + j * (2 * RP_NBH * 16);
+                        const uint64_t x_hi = make_smem_desc(blk, RP_NBH * 16, 128, LAYOUT_NONE);
+                        const uint64_t x_lo = make_smem_desc(blk + RX_PLANE, RP_NBH * 16, 128, LAYOUT_NONE);
+                        const uint32_t w_hi = tmem_base + RX_TMEM + j * 8, w_lo = w_hi + 8 * RX_KSTEPS;
+                        mma_f16_ts(d_tmem, w_hi, x_hi, idesc, j != 0);
+                        mma_f16_ts(d_tmem, w_lo, x_hi, idesc, 1);
+                        mma_f16_ts(d_tmem, w_hi, x_lo, idesc, 1);
+                    }
+                    mma_commit(&x_empty[s]);
+                }
 #pragma unroll
                 for (int gi = 0; gi < RP_G; ++gi) {
                     const int g = (g0 + gi) & (RP_G - 1);
@@ -1304,14 +1367,17 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
                         const uint64_t b_hi = make_smem_desc(blk, RP_PIECE, 128, LAYOUT_NONE);
                         const uint64_t b_lo = make_smem_desc(blk + RP_PIECE / 2, RP_PIECE, 128, LAYOUT_NONE);
                         const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
-                        mma_f16_ts(d_tmem, a_hi, b_hi, idesc, (gi | jj) != 0);
-                        if (p.debug & 8) continue;                     // (timing experiment: one MMA per K16 step)
+                        mma_f16_ts(d_tmem, a_hi, b_hi, idesc, FUSE_X || (gi | jj) != 0);
                         mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
                         mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
                     }
                 }
                 mma_commit(&d_full[s]);
                 RM_TRACE(TR_MMA_ISSUED, t, s);
+                if (FUSE_X && t + 1 < Ti) {
+                    mbar_wait(&x_empty[s], (uint32_t)(t & 1));      // long since complete: the h part was issued behind it
+                    load_x_operand(t + 1);
+                }
             }
         }
     } else {
@@ -1325,7 +1391,9 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
         const bool unit_ok = u < RC_U;
         const long long b0 = sub_b0(s);
         const bool tracer = (q == 0 && lane == 0 && half == 0);
-        unsigned char *out_tile = out_tiles + (warp - S) * C::TILE_BYTES;
+        // fused: the relu(h) tile (fp16 hi / lo) lives in this warp's own two runs of its image piece, free once its publish completed
+        unsigned char *out_tile = FUSE_X ? image(s) + q * RP_PIECE + cbase * 16 : out_tiles + (warp - S) * C::TILE_BYTES;
+        constexpr int LO_OFF = FUSE_X ? RP_PIECE / 2 : C::NW * 16;      // lo plane of the tile
 
         if (s == 0 && half == 0) {
             // one-time: W_hh slice -> TMEM.  This thread owns lane 32q + lane; column c holds k' = 2c, 2c+1.
@@ -1338,6 +1406,20 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
                     const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
                     const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                     tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
+                }
+            }
+            if (FUSE_X) {
+                // W_ih slice (rows in the same fragment order, K = 16*RX_KSTEPS features): hi plane, then lo plane
+                const __half *xrow = p.wih0 + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * 64;
+#pragma unroll 1
+                for (int plane = 0; plane < 2; ++plane) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(xrow + (size_t)plane * 128 * 64);
+#pragma unroll
+                    for (int c8 = 0; c8 < RX_KSTEPS; ++c8) {
+                        const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
+                        const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + RX_TMEM + plane * 8 * RX_KSTEPS + c8 * 8, r);
+                    }
                 }
             }
             tmem_st_wait();
@@ -1364,10 +1446,17 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
                     const int c = col_of(i);
+                    if (FUSE_X) continue;               // fused: xnext holds the (constant) biases of this unit's four gates
                     xnext[i] = (c < ncols && !(p.debug & 1)) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 xp_next += xstep;
             };
+            if (FUSE_X) {
+                const float *bz = p.bias0 + ((size_t)dir * RC_CL + rank) * 128 + q * 32 + ul;      // rows 32q + 8*gate + ul
+                const float4 b4 = make_float4(__ldg(bz), __ldg(bz + 8), __ldg(bz + 16), __ldg(bz + 24));
+#pragma unroll
+                for (int i = 0; i < NI; ++i) xnext[i] = b4;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * RP_NBH + cbase;
             const int out_c0 = dir * (TC_OP / 2) + (int)rank * 32 + 8 * q;      // first column of this warp's 8 units
             const size_t state_o = ((size_t)dir * B + b0) * TC_H + rank * RC_U + u;      // + column * TC_H
@@ -1375,6 +1464,10 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
             // h_t -> this warp's piece [plane][col][8 units] of the fp16 hi/lo image; then one thread stores the 4 KB image
             // to its L2 slot and multicasts it into slot `rank` of every CTA's B buffer for step t + 1
             auto publish = [&](const float (&hv)[NI], int t) {
+                if (FUSE_X) {                       // the previous step's output store has read the tile that shares this piece
+                    if (elect_one()) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
                 const uint32_t img = smem_u32(image(s)) + q * RP_PIECE + ul * 2;
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
@@ -1452,6 +1545,10 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
                     }
                     tmem_ld_wait();
                     tc_fence_before();
+                    if (FUSE_X) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&d_empty[s]);       // the issuer may start W_ih . x_{t+1} into this accumulator
+                    }
                     float ei[NI], ef[NI], eg[NI], eo[NI];
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
@@ -1493,7 +1590,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
                         __half hh, hl;
                         split_f16(fmaxf(hv[i], 0.f), hh, hl);
                         sts_b16(tile + (col_of(i) - cbase) * 16 + ul * 2, hh);
-                        sts_b16(tile + NW * 16 + (col_of(i) - cbase) * 16 + ul * 2, hl);
+                        sts_b16(tile + LO_OFF + (col_of(i) - cbase) * 16 + ul * 2, hl);
                     }
                 }
                 fence_proxy_async_smem();
@@ -1501,7 +1598,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW>::THREADS, 1) tc_recurrent_mc_kern
                 if (!(p.debug & 2) && elect_one()) {
                     const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;       // box of 32 / 16 batch columns
                     tma_store_3d(&om[0], out_tile, out_c0, t_idx, (int)b0 + cbase);
-                    if (!p.out_f32) tma_store_3d(&om[1], out_tile + NW * 16, out_c0, t_idx, (int)b0 + cbase);
+                    if (!p.out_f32) tma_store_3d(&om[1], out_tile + LO_OFF, out_c0, t_idx, (int)b0 + cbase);
                     tma_store_commit();
                 }
                 t_idx += dir ? -1 : 1;
@@ -1543,6 +1640,44 @@ __global__ void pack_whh_kernel(const float *__restrict__ w, int dir, int frag, 
         hi[kp] = h;
         lo[kp] = l;
     }
+}
+
+// Fused layer-1 projection: torch W_ih[960][F] -> planes [dir][rank][plane][128 rows, lane = 32*(u/8) + 8*gate + u%8][64] fp16 and
+// the folded bias b_ih + b_hh [dir][rank][128] in the same row order (zero rows for the padding units 30, 31)
+__global__ void pack_wih0_frag_kernel(const float *__restrict__ w, const float *__restrict__ b_ih, const float *__restrict__ b_hh, int F,
+                                      int dir, __half *__restrict__ dst, float *__restrict__ bias)
+{
+    const int rank = blockIdx.x / 128, row = blockIdx.x % 128;
+    const int u = (row / 32) * 8 + row % 8, q = (row % 32) / 8;
+    const int trow = q * TC_H + RC_U * rank + u;
+    __half *hi = dst + ((((size_t)dir * RC_CL + rank) * 2 + 0) * 128 + row) * 64;
+    __half *lo = dst + ((((size_t)dir * RC_CL + rank) * 2 + 1) * 128 + row) * 64;
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+        __half h = __float2half_rn(0.f), l = h;
+        if (u < RC_U && k < F) split_f16(w[(size_t)trow * F + k], h, l);
+        hi[k] = h;
+        lo[k] = l;
+    }
+    if (threadIdx.x == 0) bias[((size_t)dir * RC_CL + rank) * 128 + row] = (u < RC_U) ? b_ih[trow] + b_hh[trow] : 0.f;
+}
+
+// x[M][F] fp32 -> hi/lo fp16 planes in k-chunk-major order [8 chunks][M][8 features] (zero padded): the layout from which one 4-D TMA
+// box lands as the [chunk][column][8] K-major operand of the fused projection
+__global__ void split_planes_chunked_kernel(const float *__restrict__ x, long long M, int F, __half *__restrict__ hi, __half *__restrict__ lo)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (chunk, m)
+    if (i >= 8 * M) return;
+    const long long m = i % M;
+    const int c = (int)(i / M);
+    __half h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = 8 * c + e;
+        h[e] = l[e] = __float2half_rn(0.f);
+        if (k < F) split_f16(__ldg(x + m * F + k), h[e], l[e]);
+    }
+    *reinterpret_cast<uint4 *>(hi + i * 8) = *reinterpret_cast<const uint4 *>(h);
+    *reinterpret_cast<uint4 *>(lo + i * 8) = *reinterpret_cast<const uint4 *>(l);
 }
 
 // linear.weight[4][480] -> slot layout [4][512]
@@ -1659,14 +1794,15 @@ static int launch_recurrent_pair(const RecurParams &prm_in, const __half *whh_fr
     return 0;
 }
 
-template <int S, bool WARP_PUBLISH, int EW>
+template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X = false>
 static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
 {
-    using C = RmCfg<S, EW>;
+    using C = RmCfg<S, EW, FUSE_X>;
     RecurParams prm = prm_in;
     prm.whh = whh_frag;
     prm.trace = g_trace_buf;
     prm.trace_steps = g_trace_steps;
+    if (const char *e = getenv("HSSB_TRACE_LAYER")) if (atoi(e) != prm.layer) prm.trace = nullptr;
     static int max_clusters = 0;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = {};
@@ -1678,11 +1814,11 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_mc_kernel)");
         cfg.gridDim = dim3(16 * RC_CL);
         int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, &cfg);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_mc_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         max_clusters = std::min(n, 16);
@@ -1697,17 +1833,31 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     if (const char *e = getenv("HSSB_RC_DEBUG")) prm.debug = atoi(e);
     cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
     ProfScope prof("tc_recurrent", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW>, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
     return 0;
 }
 
 // One layer's recurrence for batch columns [0, B): picks the sub-tile geometry from B.
 static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const float *h0, const float *c0, float *hn, float *cn,
-                        __half *out_hi, __half *out_lo, float *out_f32, unsigned char *gather, int64_t B, int64_t T, cudaStream_t st)
+                        __half *out_hi, __half *out_lo, float *out_f32, unsigned char *gather, int64_t B, int64_t T, cudaStream_t st,
+                        const __half *x_hi = nullptr, const __half *x_lo = nullptr)
 {
+    // x_hi / x_lo != nullptr: layer 1 with the input projection fused into the recurrence (chunk-major x planes, no xproj)
+    const bool fused = x_hi != nullptr;
     RecurParams prm = {};
     prm.gather = gather;
+    prm.layer = layer;
+    if (fused) {
+        const uint64_t M = (uint64_t)B * T;
+        const uint64_t dims[4] = {8, (uint64_t)T, (uint64_t)B, 8};
+        const uint64_t strides[3] = {16, (uint64_t)T * 16, M * 16};
+        const uint32_t box[4] = {8, 1, RP_NBH, RX_CHUNKS};
+        if (int rc = make_tmap(&prm.x_map[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        if (int rc = make_tmap(&prm.x_map[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        prm.wih0 = m->tc_wih0_frag;
+        prm.bias0 = m->tc_bias0_frag;
+    }
     prm.whh = m->tc_whh[layer];
     prm.h0 = h0; prm.c0 = c0; prm.hn = hn; prm.cn = cn;
     prm.out_hi = out_hi; prm.out_lo = out_lo; prm.out_f32 = out_f32;
@@ -1746,6 +1896,16 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         else if (per_group <= 32) { nb = 32; s = 1; pair = 4; }
         else if (per_group <= 64) { nb = 32; s = 2; pair = 4; }
         else { nb = 32; s = 3; pair = 3; }
+        if (fused) {
+            if (force_nb) return fail(HSSB_E_MODE, "HSSB_RC_GEOM cannot be combined with the fused projection");
+            int rcf, donef = 0;
+            if (s == 1) rcf = launch_recurrent_mc<1, true, 2, true>(prm, m->tc_whh_frag[layer], rem, &donef, xproj, st);
+            else if (s == 2) rcf = launch_recurrent_mc<2, true, 2, true>(prm, m->tc_whh_frag[layer], rem, &donef, xproj, st);
+            else rcf = launch_recurrent_mc<3, true, 1, true>(prm, m->tc_whh_frag[layer], rem, &donef, xproj, st);
+            if (rcf) return rcf;
+            base += donef;
+            continue;
+        }
         // (the CTA-pair variants -- cta_group::2, half the all-gather volume -- are validated but measured slower on
         //  B200: at N = 32 the paired MMA is issue-overhead bound, ~30 cycles each against ~18 for cta_group::1)
         int rc, done = 0;
@@ -1815,13 +1975,27 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     float *hn = reinterpret_cast<float *>(base + w.hn), *cn = reinterpret_cast<float *>(base + w.cn);
     unsigned char *gather = reinterpret_cast<unsigned char *>(base + w.gather);
     const int64_t M = B * T;
-    {
-        ProfScope prof("split_planes", st);
-        split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo);
-        HSSB_LAUNCH_OK("split_planes_kernel");
+    // Layer 1's input projection (K = input_size <= 48) rides in the recurrence kernel: W_ih . x_t is issued into the accumulator
+    // while the step's h_{t-1} is still in flight, so no xproj tensor (7.7 KB per sample written and read back) exists for it.
+    // HSSB_FUSE_X=0 or a forced recurrence geometry selects the separate projection kernel instead.
+    const char *fx = getenv("HSSB_FUSE_X");
+    const bool fused = m->F <= 16 * RX_KSTEPS && !getenv("HSSB_RC_GEOM") && !(fx && fx[0] == '0');
+    if (fused) {
+        {
+            ProfScope prof("split_planes", st);
+            split_planes_chunked_kernel<<<(unsigned)((8 * M + 255) / 256), 256, 0, st>>>(x, M, m->F, xhi, xlo);
+            HSSB_LAUNCH_OK("split_planes_chunked_kernel");
+        }
+        if (int rc = tc_recurrent(m, 0, nullptr, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, xhi, xlo)) return rc;
+    } else {
+        {
+            ProfScope prof("split_planes", st);
+            split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo);
+            HSSB_LAUNCH_OK("split_planes_kernel");
+        }
+        if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st)) return rc;
+        if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st)) return rc;
     }
-    if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st)) return rc;
-    if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st)) return rc;
     if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st)) return rc;
     if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, st)) return rc;
     return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st);

@@ -21,6 +21,8 @@ struct hssb_model {
     __half *tc_whh_frag[2];   // the same W_hh planes with the TMEM lanes in fragment order (see pack_whh_kernel)
     float *tc_bias[2];        // layer l: [2 dirs][960]
     float *tc_lin_w;          // [4][512] linear weights in slot layout
+    __half *tc_wih0_frag;     // layer-1 W_ih slices [dir][rank][plane][128 rows in fragment order][64] (fused projection)
+    float *tc_bias0_frag;     // their folded biases [dir][rank][128]
     void *all;                // single allocation backing everything above
     size_t all_bytes;
 };
