@@ -105,6 +105,32 @@ def test_recurrence_geometries(lib, geom, B, T, monkeypatch):
     check(logp.cpu(), labels.cpu(), lo.forward_torch(params, h0, c0, x))
 
 
+@pytest.mark.parametrize("F", [7, 48, 60])
+def test_other_input_sizes(lib, F):
+    """input_size <= 48 rides the fused projection (K = 16, 32 or 48 features), larger ones the separate projection kernel."""
+    B, T = 5, 37
+    m = make_model(F, F, B, 240)
+    x = torch.randn(B, T, F, generator=torch.Generator().manual_seed(F))
+    params, h0, c0 = lo.reference_params(F, F, B, 240)
+    logp, labels = m.forward_with_labels(x.cuda())
+    check(logp.cpu(), labels.cpu(), lo.forward_torch(params, h0, c0, x))
+
+
+def test_fused_and_separate_projection_agree(lib, monkeypatch):
+    """HSSB_FUSE_X=0 (xproj tensor + projection kernel for layer 1) against the default fused recurrence, full-size batch."""
+    B, T = 200, 50
+    m = make_model(11, 44, B, 240)
+    x = torch.randn(B, T, 44, generator=torch.Generator().manual_seed(3)).cuda()
+    a, la = m.forward_with_labels(x)
+    monkeypatch.setenv("HSSB_FUSE_X", "0")
+    b, lb = m.forward_with_labels(x)
+    assert (a - b).abs().max().item() < LOGP_TOL
+    params, h0, c0 = lo.reference_params(11, 44, B, 240)
+    ref = lo.forward_torch(params, h0, c0, x.cpu())
+    check(a.cpu(), la.cpu(), ref)
+    check(b.cpu(), lb.cpu(), ref)
+
+
 def test_state_dict_reload_repacks_weights(lib):
     m = make_model(3, 44, 2, 240)
     x = torch.randn(2, 20, 44)
