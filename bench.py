@@ -39,6 +39,11 @@ FLOP_PER_SAMPLE = {"tc_inproj_l0": 2 * 44 * 1920.0, "tc_inproj_l1": 2 * 480 * 19
 BYTES_PER_SAMPLE = {"stft_hop1": 4 + 2 * K_BINS * 8, "if_reassign": 2 * K_BINS * 8 + KT * 8, "normalise": 16 * KT * 2}
 
 
+def workload_name(windows: int) -> str:
+    return (f"config 4 shard: FSST(kaiser128,25-200Hz,stack)+BiLSTM(44->240x2x2->4), {windows} windows x {N_SAMPLES} "
+            "samples per GPU")
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -177,7 +182,7 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": "PCG samples/s through FSST+BiLSTM", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"FSST(kaiser128,25-200Hz,stack)+BiLSTM(44->240x2x2->4), {WINDOWS_PER_GPU} windows x {N_SAMPLES} samples per GPU",
+        "config": {"workload": workload_name(args.windows), "windows_per_gpu": args.windows, "samples_per_window": N_SAMPLES,
                    "sample_windows_per_step": batch},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{batch} windows x {N_SAMPLES} samples per step; FSST = C/OpenMP restatement of MATLAB fsst "
@@ -330,7 +335,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FSST fp32; LSTM gate GEMMs split-fp16 x3 on tcgen05, fp32 accumulate)"
             if os.environ.get("HSSB_LSTM_IMPL", "auto") != "simt" else "f32",
             "data": "synthetic",
-            "config": {"workload": f"config 4 shard: FSST(kaiser128,25-200Hz,stack)+BiLSTM(44->240x2x2->4), {B} windows x {N_SAMPLES} samples per GPU",
+            "config": {"workload": workload_name(B),
                        "windows_per_gpu": B, "samples_per_window": N_SAMPLES, "l2": "flushed between timed steps (256 MiB write)",
                        "lstm_impl": os.environ.get("HSSB_LSTM_IMPL", "auto")},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),

@@ -32,6 +32,9 @@ constexpr int TC_NG = 2 * TC_G;    // both directions
 // k-chunk is then a 16-byte aligned, non-overlapping run, which is what lets the recurrence write its outputs
 // with TMA stores straight from the shared-memory image.
 constexpr int TC_OP = 512;
+// xproj is [dir][t][Bp][960] with an odd number of batch rows per time step: with B = 512 the t stride would be 15 * 2^17 bytes and
+// every one of the 128 rows a projection tile writes would fall on the same HBM channel / L2 slice.
+static inline long long xproj_pitch(long long B) { return B | 1; }
 constexpr size_t TC_GATHER_BYTES = (size_t)16 * 8 * 3 * 2 * 4096;   // L2 scratch of the multicast all-gather: [cluster][rank][S][parity][4 KB]
 
 // ------------------------------------------------------------------------------------------------
@@ -155,9 +158,9 @@ static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
 struct InprojParams {
     CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (32, 64, 1), SW64   (half of the A stage)
     CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 48), SW64  (quarter of the W stage)
-    float *out;               // xproj [dir][t][b][960] fp32
+    float *out;               // xproj [dir][t][Bp][960] fp32
     const float *bias;        // [1920]
-    long long B;
+    long long B, Bp;          // batch, and the row pitch of xproj in batch rows (see xproj_pitch)
     int debug;                // HSSB_IP_DEBUG bit 0: skip the global stores (timing experiment; results are wrong when set)
     int k_real;               // true K rounded up to 16 (48 / 512)
     int T;
@@ -309,13 +312,13 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
                     }
                     __syncwarp();
                     const int rsub = lane >> 3, c16 = lane & 7;
-                    float *gout = p.out + (((size_t)dir * p.T + t0 + q * 32) * p.B + b) * TC_G + nl0 + c * 32 + c16 * 4;
+                    float *gout = p.out + (((size_t)dir * p.T + t0 + q * 32) * p.Bp + b) * TC_G + nl0 + c * 32 + c16 * 4;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int row = 4 * j + rsub;
                         const float4 o = *reinterpret_cast<const float4 *>(ob + row * 128 + ((c16 ^ (row & 7)) << 4));
                         if (b < p.B && t0 + q * 32 + row < p.T && !(p.debug & 1))                    // (b >= B: padding tiles of the last m-group)
-                            __stcs(reinterpret_cast<float4 *>(gout + (size_t)row * p.B * TC_G), o);
+                            __stcs(reinterpret_cast<float4 *>(gout + (size_t)row * p.Bp * TC_G), o);
                     }
                     __syncwarp();
                 }
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
 }
 
 // xproj[dir][t][b][g'] -> canonical [dir][b*T + t][q*240 + unit]   (debug / validation only)
-__global__ void unpermute_xproj_kernel(const float *__restrict__ src, long long B, long long T, float *__restrict__ dst)
+__global__ void unpermute_xproj_kernel(const float *__restrict__ src, long long B, long long Bp, long long T, float *__restrict__ dst)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = 2 * B * T * TC_G;
@@ -338,7 +341,7 @@ __global__ void unpermute_xproj_kernel(const float *__restrict__ src, long long 
     const long long rest = i / TC_G;
     const long long b = rest % B, t = (rest / B) % T, dir = rest / (B * T);
     const int r = gp / 120, u = (gp % 120) / 4, q = gp % 4;
-    dst[((size_t)dir * B * T + b * T + t) * TC_G + q * TC_H + 30 * r + u] = src[i];
+    dst[((size_t)dir * B * T + b * T + t) * TC_G + q * TC_H + 30 * r + u] = src[((size_t)(dir * T + t) * Bp + b) * TC_G + gp];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -481,6 +484,7 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     }
     prm.out = xproj;
     prm.B = B;
+    prm.Bp = xproj_pitch(B);
     prm.debug = 0;
     if (const char *e = getenv("HSSB_IP_DEBUG")) prm.debug = atoi(e);
     prm.bias = m->tc_bias[layer];
@@ -553,6 +557,7 @@ struct RecurParams {
     __half *out_hi, *out_lo;    // layer 1: relu(h) planes [B*T][480]  (nullptr for layer 2)
     float *out_f32;             // layer 2: relu(h) [B*T][480]         (nullptr for layer 1)
     long long B, T;
+    long long Bp;               // row pitch of xproj in batch rows (xproj_pitch(B))
     int b_base;                 // first batch column handled by this launch
     int groups;                 // groups of S*NB columns per direction in this launch
     int stagger_ns;             // initial phase offset between the sub-tiles of a cluster
@@ -731,9 +736,9 @@ __global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_k
             // xproj of this thread's gate row (padding lanes re-read row 119, result unused):
             // element (t, b) at xp_base + (t*B + b)*960
             const int xrow = unit_ok ? row : RC_XW - 1;
-            const float *xp_base = p.xproj + (size_t)dir * T * B * TC_G + (size_t)b0 * TC_G + rank * RC_XW + xrow;
-            const long long xstep = (dir ? -1 : 1) * B * TC_G;          // one time step
-            const float *xp_next = xp_base + (dir ? (size_t)(T - 1) * B * TC_G : 0);
+            const float *xp_base = p.xproj + (size_t)dir * T * p.Bp * TC_G + (size_t)b0 * TC_G + rank * RC_XW + xrow;
+            const long long xstep = (dir ? -1 : 1) * p.Bp * TC_G;       // one time step
+            const float *xp_next = xp_base + (dir ? (size_t)(T - 1) * p.Bp * TC_G : 0);
             float c_state[NI], hv[NI], xnext[NB];
             auto load_x = [&]() {                                        // xproj of the next step -> registers
                 if (full) {
@@ -1062,8 +1067,8 @@ __global__ void __launch_bounds__(RpCfg<S>::THREADS, 1) tc_recurrent_pair_kernel
             auto col_of = [&](int i) { return 8 * (i >> 1) + 2 * cp + (i & 1); };
             // xproj of (unit u, column c): 4 consecutive floats i, f, g, o at xp + c*960 (16-byte aligned)
             const int ux = unit_ok ? u : RC_U - 1;
-            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * B * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
-            const long long xstep = (dir ? -1 : 1) * B * TC_G;
+            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * p.Bp * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
+            const long long xstep = (dir ? -1 : 1) * p.Bp * TC_G;
             float4 xnext[NI];
             float c_state[NI];
             // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
@@ -1436,8 +1441,8 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
             const int ncols = (int)(left < RP_NBH ? left : RP_NBH);
             auto col_of = [&](int i) { return cbase + 8 * (i >> 1) + 2 * cp + (i & 1); };
             const int ux = unit_ok ? u : RC_U - 1;
-            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * B * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
-            const long long xstep = (dir ? -1 : 1) * B * TC_G;
+            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * p.Bp * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
+            const long long xstep = (dir ? -1 : 1) * p.Bp * TC_G;
             float4 xnext[NI];
             float c_state[NI];
             // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
@@ -1862,6 +1867,7 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
     prm.h0 = h0; prm.c0 = c0; prm.hn = hn; prm.cn = cn;
     prm.out_hi = out_hi; prm.out_lo = out_lo; prm.out_f32 = out_f32;
     prm.B = B; prm.T = T;
+    prm.Bp = xproj_pitch(B);
     {
         const bool f32 = out_f32 != nullptr;
         const uint64_t es = f32 ? 4 : 2;
@@ -1948,7 +1954,7 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
     size_t off = 0;
     w.xhi = off;   off += align_up(sizeof(__half) * M * 64, 1024);
     w.xlo = off;   off += align_up(sizeof(__half) * M * 64, 1024);
-    w.xproj = off; off += align_up(sizeof(float) * 2 * M * TC_G, 1024);
+    w.xproj = off; off += align_up(sizeof(float) * 2 * (size_t)T * xproj_pitch(B) * TC_G, 1024);
     w.o1hi = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
     w.o1lo = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
     w.out2 = off;  off += align_up(sizeof(float) * M * TC_OP, 1024);
@@ -2022,7 +2028,7 @@ extern "C" int hssb_debug_trace(unsigned long long *buf, int steps)
 // ------------------------------------------------------------------------------------------------
 // Diagnostic entry point: layer-1 input projection only, canonical layout, for kernel-level parity
 // tests (impl 0 = tcgen05 kernel, 1 = SIMT kernel).  xproj: [2][B*T][960] fp32 (torch gate order).
-// workspace: 2*B*T*960*4 + 2*B*T*64*2*2 bytes.
+// workspace: 2*T*(B|1)*960*4 + 2*B*T*64*2*2 bytes (xproj rows are pitched to an odd batch count).
 // ------------------------------------------------------------------------------------------------
 extern "C" int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B, int64_t T, int impl, float *xproj, void *workspace,
                                  size_t workspace_bytes, void *stream)
@@ -2038,14 +2044,15 @@ extern "C" int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B,
         return 0;
     }
     if (m->H != TC_H || m->F > 64 || !m->tc_wih[0]) return fail(HSSB_E_MODEL, "tcgen05 kernels need hidden_size 240");
-    const size_t need = sizeof(float) * 2 * M * TC_G + sizeof(__half) * 2 * M * 64;
+    const size_t raw_floats = (size_t)2 * T * xproj_pitch(B) * TC_G;
+    const size_t need = sizeof(float) * raw_floats + sizeof(__half) * 2 * M * 64;
     if (!workspace || workspace_bytes < need) return fail(HSSB_E_WORKSPACE, "hssb_debug_inproj: workspace %zu < %zu", workspace_bytes, need);
     float *raw = static_cast<float *>(workspace);
-    __half *hi = reinterpret_cast<__half *>(raw + 2 * M * TC_G), *lo = hi + M * 64;
+    __half *hi = reinterpret_cast<__half *>(raw + raw_floats), *lo = hi + M * 64;
     split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, hi, lo);
     HSSB_LAUNCH_OK("split_planes_kernel");
     if (int rc = tc_inproj(m, 0, hi, lo, 64, B, T, raw, st)) return rc;
-    unpermute_xproj_kernel<<<(unsigned)((2 * M * TC_G + 255) / 256), 256, 0, st>>>(raw, B, T, xproj);
+    unpermute_xproj_kernel<<<(unsigned)((2 * M * TC_G + 255) / 256), 256, 0, st>>>(raw, B, xproj_pitch(B), T, xproj);
     HSSB_LAUNCH_OK("unpermute_xproj_kernel");
     return 0;
 }

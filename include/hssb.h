@@ -126,7 +126,7 @@ int hssb_model_forward(const hssb_model *m, const float *x, int64_t B, int64_t T
 
 /* Diagnostic: layer-1 input projection only (kernel-level parity tests of K4).  impl 0 = tcgen05
  * kernel, 1 = SIMT kernel.  xproj [2,B*T,4H] f32 device, torch gate order.  workspace >=
- * 2*B*T*(4H*4 + 256) bytes. */
+ * 2*T*(B+1)*4H*4 + 2*B*T*256 bytes. */
 int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B, int64_t T, int impl, float *xproj,
                       void *workspace, size_t workspace_bytes, void *stream);
 

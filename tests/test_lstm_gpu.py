@@ -165,7 +165,7 @@ def test_k4_tcgen05_inproj_matches_simt(lib, B, T):
     x = (torch.randn(B, T, 44) * 3).cuda()
     handle = m._packed(x.device)
     M = B * T
-    ws = torch.empty(2 * M * (960 * 4 + 256), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(2 * T * (B + 1) * 960 * 4 + 2 * M * 256, dtype=torch.uint8, device="cuda")
     outs = []
     for impl in (0, 1):
         out = torch.full((2, M, 960), float("nan"), device="cuda")
