@@ -566,9 +566,11 @@ struct RecurParams {
     // pair kernel: TMA stores of relu(h) into the slot-layout outputs [B][T][512] (fp16 hi, lo planes or one fp32 tensor)
     alignas(64) CUtensorMap out_map[2];
     alignas(64) CUtensorMap out_map16[2];   // the same with boxes of 16 batch columns (two epilogue warps per quadrant)
-    // fused layer-1 input projection (multicast kernel): x planes [chunk][b][t][8] fp16 (hi, lo), W_ih slices
-    // [dir][rank][plane][128 rows in fragment order][64] fp16 and b_ih + b_hh [dir][rank][128] in the same row order
-    alignas(64) CUtensorMap x_map[2];
+    // fused layer-1 input projection (multicast kernel): x planes [t][32-column tile][chunk 8][32 cols][8] fp16 (hi, lo) -- the
+    // operand of one sub-tile and step is one contiguous 3 KB run --, W_ih slices [dir][rank][plane][128 rows in fragment
+    // order][64] fp16 and b_ih + b_hh [dir][rank][128] in the same row order
+    const __half *x_hi, *x_lo;
+    long long x_tiles;          // 32-column tiles per time step = ceil(B / 32)
     const __half *wih0;
     const float *bias0;
     unsigned char *gather;      // multicast kernel: L2 scratch [cluster][rank][S][2][4 KB] of the all-gather
@@ -1246,12 +1248,12 @@ struct RmCfg {
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-__device__ __forceinline__ void tma_load_4d_nomc(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3)
+// global -> own shared memory, completing `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_load_global(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 __device__ __forceinline__ void bulk_store_global(void *gdst, const void *ssrc, uint32_t bytes)
@@ -1304,7 +1306,6 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
         for (int i = 0; i < 2 * S * RP_G + 4 * S; ++i) mbar_init(&bars[i], 1);
         for (int i = 0; i < S; ++i) mbar_init(&d_empty[i], 4 * EW);
         fence_barrier_init();
-        if (FUSE_X) { prefetch_tmap(&p.x_map[0]); prefetch_tmap(&p.x_map[1]); }
         const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;
         prefetch_tmap(&om[0]);
         if (!p.out_f32) prefetch_tmap(&om[1]);
@@ -1329,11 +1330,12 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
             const uint32_t d_tmem = tmem_base + 256 + s * RP_NBH;
             const int Ti = (int)T;
             unsigned char *xb = xbufs + s * 2 * RX_PLANE;
-            auto load_x_operand = [&](int t) {           // x_t of this sub-tile's 32 columns: both fp16 planes, [chunk][col][8]
+            auto load_x_operand = [&](int t) {           // x_t of this sub-tile's 32 columns: both fp16 planes, [chunk][col][8], 3 KB each
                 const int t_idx = dir ? Ti - 1 - t : t;
+                const size_t off = ((size_t)t_idx * p.x_tiles + (size_t)(sub_b0(s) / RP_NBH)) * (8 * RP_NBH * 8);     // halves
                 mbar_arrive_expect_tx(&x_full[s], 2 * RX_PLANE);
-                tma_load_4d_nomc(xb, &p.x_map[0], &x_full[s], 0, t_idx, (int)sub_b0(s), 0);
-                tma_load_4d_nomc(xb + RX_PLANE, &p.x_map[1], &x_full[s], 0, t_idx, (int)sub_b0(s), 0);
+                bulk_load_global(xb, p.x_hi + off, RX_PLANE, &x_full[s]);
+                bulk_load_global(xb + RX_PLANE, p.x_lo + off, RX_PLANE, &x_full[s]);
             };
             if (FUSE_X) load_x_operand(0);
             for (int t = 0; t < Ti; ++t) {
@@ -1666,20 +1668,23 @@ __global__ void pack_wih0_frag_kernel(const float *__restrict__ w, const float *
     if (threadIdx.x == 0) bias[((size_t)dir * RC_CL + rank) * 128 + row] = (u < RC_U) ? b_ih[trow] + b_hh[trow] : 0.f;
 }
 
-// x[M][F] fp32 -> hi/lo fp16 planes in k-chunk-major order [8 chunks][M][8 features] (zero padded): the layout from which one 4-D TMA
-// box lands as the [chunk][column][8] K-major operand of the fused projection
-__global__ void split_planes_chunked_kernel(const float *__restrict__ x, long long M, int F, __half *__restrict__ hi, __half *__restrict__ lo)
+// x[B][T][F] fp32 -> hi/lo fp16 planes [t][32-column tile][chunk 8][32 cols][8 features] (zero padded features and columns): the
+// K-major operand of the fused projection for one (step, sub-tile) is then one contiguous run, fetched by a single bulk copy
+__global__ void split_planes_tiled_kernel(const float *__restrict__ x, long long B, long long T, int F, __half *__restrict__ hi,
+                                          __half *__restrict__ lo)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (chunk, m)
-    if (i >= 8 * M) return;
-    const long long m = i % M;
-    const int c = (int)(i / M);
+    const long long tiles = (B + RP_NBH - 1) / RP_NBH;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((t * tiles + tile) * 8 + chunk) * 32 + col
+    if (i >= T * tiles * 8 * RP_NBH) return;
+    const int col = (int)(i % RP_NBH), c = (int)((i / RP_NBH) % 8);
+    const long long tile = (i / (8 * RP_NBH)) % tiles, t = i / (8 * RP_NBH * tiles);
+    const long long b = tile * RP_NBH + col;
     __half h[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = 8 * c + e;
         h[e] = l[e] = __float2half_rn(0.f);
-        if (k < F) split_f16(__ldg(x + m * F + k), h[e], l[e]);
+        if (k < F && b < B) split_f16(__ldg(x + (b * T + t) * F + k), h[e], l[e]);
     }
     *reinterpret_cast<uint4 *>(hi + i * 8) = *reinterpret_cast<const uint4 *>(h);
     *reinterpret_cast<uint4 *>(lo + i * 8) = *reinterpret_cast<const uint4 *>(l);
@@ -1854,12 +1859,9 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
     prm.gather = gather;
     prm.layer = layer;
     if (fused) {
-        const uint64_t M = (uint64_t)B * T;
-        const uint64_t dims[4] = {8, (uint64_t)T, (uint64_t)B, 8};
-        const uint64_t strides[3] = {16, (uint64_t)T * 16, M * 16};
-        const uint32_t box[4] = {8, 1, RP_NBH, RX_CHUNKS};
-        if (int rc = make_tmap(&prm.x_map[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-        if (int rc = make_tmap(&prm.x_map[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        prm.x_hi = x_hi;
+        prm.x_lo = x_lo;
+        prm.x_tiles = (B + RP_NBH - 1) / RP_NBH;
         prm.wih0 = m->tc_wih0_frag;
         prm.bias0 = m->tc_bias0_frag;
     }
@@ -1952,8 +1954,9 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
     const size_t M = (size_t)B * T;
     TcWs w{};
     size_t off = 0;
-    w.xhi = off;   off += align_up(sizeof(__half) * M * 64, 1024);
-    w.xlo = off;   off += align_up(sizeof(__half) * M * 64, 1024);
+    const size_t Mp = (size_t)T * ((B + 31) / 32) * 32;          // batch padded to whole 32-column tiles (fused projection operand)
+    w.xhi = off;   off += align_up(sizeof(__half) * Mp * 64, 1024);
+    w.xlo = off;   off += align_up(sizeof(__half) * Mp * 64, 1024);
     w.xproj = off; off += align_up(sizeof(float) * 2 * (size_t)T * xproj_pitch(B) * TC_G, 1024);
     w.o1hi = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
     w.o1lo = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
@@ -1989,8 +1992,9 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     if (fused) {
         {
             ProfScope prof("split_planes", st);
-            split_planes_chunked_kernel<<<(unsigned)((8 * M + 255) / 256), 256, 0, st>>>(x, M, m->F, xhi, xlo);
-            HSSB_LAUNCH_OK("split_planes_chunked_kernel");
+            const long long n = T * ((B + RP_NBH - 1) / RP_NBH) * 8 * RP_NBH;
+            split_planes_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, B, T, m->F, xhi, xlo);
+            HSSB_LAUNCH_OK("split_planes_tiled_kernel");
         }
         if (int rc = tc_recurrent(m, 0, nullptr, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, xhi, xlo)) return rc;
     } else {
