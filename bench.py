@@ -53,7 +53,7 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "tensor_tflops_burst": 1590.0, "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
-TRAFFIC_FILE = "r01c_traffic.json"
+TRAFFIC_FILE = "r01d_traffic.json"
 
 
 def traffic_source():
