@@ -159,25 +159,43 @@ head_kernel(const float *__restrict__ act, long long M, int H2, const float *__r
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
-        const float *a = act + (size_t)row * H2;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        for (int k = lane; k < H2; k += 32) {
-            const float v = __ldcs(a + k);
-            s0 = fmaf(v, w_s[k], s0);
-            s1 = fmaf(v, w_s[H2 + k], s1);
-            s2 = fmaf(v, w_s[2 * H2 + k], s2);
-            s3 = fmaf(v, w_s[3 * H2 + k], s3);
+    const bool vec = (H2 & 127) == 0;        // 16-byte loads, two rows in flight per warp (the tcgen05 path: H2 = 512)
+    for (long long row0 = 2 * ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); row0 < M; row0 += 2 * warps_total) {
+        float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const int nrow = (row0 + 1 < M) ? 2 : 1;
+        if (vec) {
+            const float4 *a0 = reinterpret_cast<const float4 *>(act + (size_t)row0 * H2);
+            const float4 *a1 = reinterpret_cast<const float4 *>(act + (size_t)(row0 + nrow - 1) * H2);
+            for (int k4 = lane; k4 < H2 / 4; k4 += 32) {
+                const float4 v0 = __ldcs(a0 + k4), v1 = __ldcs(a1 + k4);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 w = *reinterpret_cast<const float4 *>(w_s + c * H2 + 4 * k4);
+                    s[0][c] = fmaf(v0.w, w.w, fmaf(v0.z, w.z, fmaf(v0.y, w.y, fmaf(v0.x, w.x, s[0][c]))));
+                    s[1][c] = fmaf(v1.w, w.w, fmaf(v1.z, w.z, fmaf(v1.y, w.y, fmaf(v1.x, w.x, s[1][c]))));
+                }
+            }
+        } else {
+            for (int r = 0; r < nrow; ++r) {
+                const float *a = act + (size_t)(row0 + r) * H2;
+                for (int k = lane; k < H2; k += 32) {
+                    const float v = __ldcs(a + k);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[r][c] = fmaf(v, w_s[c * H2 + k], s[r][c]);
+                }
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-        }
-        if (lane == 0) {
-            const float z[4] = {s0 + lin_b[0], s1 + lin_b[1], s2 + lin_b[2], s3 + lin_b[3]};
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s[r][c] += __shfl_xor_sync(0xffffffffu, s[r][c], o);
+        if (lane < nrow) {
+            const int r = lane;
+            const long long row = row0 + r;
+            const float z[4] = {(r ? s[1][0] : s[0][0]) + lin_b[0], (r ? s[1][1] : s[0][1]) + lin_b[1], (r ? s[1][2] : s[0][2]) + lin_b[2],
+                                (r ? s[1][3] : s[0][3]) + lin_b[3]};
             const float mx = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
             const float lse = mx + logf(expf(z[0] - mx) + expf(z[1] - mx) + expf(z[2] - mx) + expf(z[3] - mx));
             const float o[4] = {z[0] - lse, z[1] - lse, z[2] - lse, z[3] - lse};
@@ -197,7 +215,7 @@ int head_forward(const float *act, int64_t M, int H2, const float *lin_w, const 
                  int32_t *labels, cudaStream_t st)
 {
     if (M == 0) return 0;
-    long long blocks = (M + 7) / 8;
+    long long blocks = (M + 15) / 16;
     if (blocks > 148 * 8) blocks = 148 * 8;
     ProfScope prof("head", st);
     head_kernel<<<(unsigned)blocks, 256, sizeof(float) * 4 * H2, st>>>(act, M, H2, lin_w, lin_b, logp, labels);
