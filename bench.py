@@ -77,7 +77,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.mark_at = index, [], None, 0
+
+    def mark(self):
+        """Samples from here on belong to the timed region (the process is started before the warm-up: nvidia-smi can take
+        longer to come up than a short timed region lasts)."""
+        self.mark_at = len(self.lines)
 
     def start(self):
         try:
@@ -97,7 +102,8 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        lines = self.lines[self.mark_at:] if len(self.lines) > self.mark_at else self.lines   # else: warm-up samples, also under load
+        for ln in lines:
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -232,13 +238,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(x_dev)
     barrier()
 
     # ---- device-resident timing: K steps, CUDA events per step, L2 flushed between steps ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     _lib.prof_enable(True)
     _lib.prof_read()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
