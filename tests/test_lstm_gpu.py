@@ -83,7 +83,7 @@ def test_config3_shape_vs_torch_cpu(lib, impl, monkeypatch):
 
 
 def test_odd_batch_and_short_sequences(lib):
-    for B, T in ((1, 1), (3, 2), (5, 17), (9, 33)):
+    for B, T in ((1, 1), (3, 2), (5, 17), (9, 33), (700, 3)):       # 700 columns: more than one recurrence launch per layer
         m = make_model(B * 31 + T, 44, B, 240)
         x = torch.randn(B, T, 44)
         params, h0, c0 = lo.reference_params(B * 31 + T, 44, B, 240)
