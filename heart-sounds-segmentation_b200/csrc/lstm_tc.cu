@@ -11,36 +11,19 @@
 // torch row = q*240 + 30*r + u), so that every recurrence CTA owns one contiguous 120-wide slice and
 // the four gates of a unit sit in four adjacent TMEM lanes (= four adjacent threads of one warp).
 //
-// K4  tc_inproj_kernel : xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']   (see the kernel)
-// K5  tc_recurrent_kernel : the T sequential steps, 8-CTA clusters, weights resident in TMEM (see the kernel)
-#include "model.cuh"
-#include "tc_ptx.cuh"
-#include <cudaTypedefs.h>
+// This file: operand packing, K4 tc_inproj_kernel (xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']), the
+// per-layer recurrence dispatch and the forward.  The recurrence kernels (T sequential steps, 8-CTA clusters, weights
+// resident in TMEM) live in lstm_rc_mc.cu (K5m, the default) and lstm_rc_dsmem.cu (K5 / K5p); shared declarations in
+// lstm_tc_common.cuh.
+#include "lstm_tc_common.cuh"
 #include <mutex>
-#include <cstdlib>
-#include <algorithm>
 
 namespace hssb {
-
-using namespace ptx;
-
-constexpr int TC_H = 240;
-constexpr int TC_G = 960;          // gate rows per direction
-constexpr int TC_NG = 2 * TC_G;    // both directions
-// "slot layout" of the hidden state handed from one layer to the next: column = dir*256 + rank*32 + slot
-// (rank = recurrence CTA 0..7, slot = unit within the rank 0..29; slots 30, 31 are zero).  Every CTA's 8-unit
-// k-chunk is then a 16-byte aligned, non-overlapping run, which is what lets the recurrence write its outputs
-// with TMA stores straight from the shared-memory image.
-constexpr int TC_OP = 512;
-// xproj is [dir][t][Bp][960] with an odd number of batch rows per time step: with B = 512 the t stride would be 15 * 2^17 bytes and
-// every one of the 128 rows a projection tile writes would fall on the same HBM channel / L2 slice.
-static inline long long xproj_pitch(long long B) { return B | 1; }
-constexpr size_t TC_GATHER_BYTES = (size_t)16 * 8 * 3 * 2 * 4096;   // L2 scratch of the multicast all-gather: [cluster][rank][S][parity][4 KB]
 
 // ------------------------------------------------------------------------------------------------
 // host: tensor maps
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_whh_kernel(const float *__restrict__ w, int dir, int frag, __half *__restrict__ dst);   // defined with K5
+__global__ void pack_whh_kernel(const float *__restrict__ w, int dir, int frag, __half *__restrict__ dst);   // defined below
 __global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict__ dst);
 __global__ void pack_wih0_frag_kernel(const float *__restrict__ w, const float *__restrict__ b_ih, const float *__restrict__ b_hh, int F,
                                       int dir, __half *__restrict__ dst, float *__restrict__ bias);
@@ -75,12 +58,6 @@ static int make_tmap(CUtensorMap *m, CUtensorMapDataType dt, int rank, const voi
 // ------------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo)
-{
-    hi = __float2half_rn(v);
-    lo = __float2half_rn(v - __half2float(hi));
-}
-
 // x[M,F] fp32 -> hi/lo fp16 planes [M,Kp] (zero padded columns)
 __global__ void split_planes_kernel(const float *__restrict__ x, long long M, int F, int Kp, __half *__restrict__ hi,
                                     __half *__restrict__ lo)
@@ -502,1134 +479,6 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     return launch_inproj<5, 4>(prm, n_items, "tc_inproj_l1", st);
 }
 
-// ------------------------------------------------------------------------------------------------
-// K5: recurrence.  One 8-CTA cluster per (direction, group of S*NB batch columns).
-//
-// Orientation: gates are the MMA M dimension and stay put, the batch is N:
-//     G^T[g' (128 lanes), b (NB cols)] = W_hh,slice[g', k] . h_{t-1}^T[k, b]  (+ xproj^T added in the epilogue)
-// CTA rank r owns units 30r..30r+29 -> gate rows (TMEM lanes) 4*u + q (q = i,f,g,o; lanes 120..127 are zero
-// padding), so the four gates of a unit are four adjacent lanes of one warp.
-//   * W_hh slice (hi and lo fp16 planes, K padded 240 -> 8*32) is loaded ONCE into TMEM columns
-//     [0,256) and is the A operand of every MMA (tcgen05.mma with A in TMEM) -- weights never move.
-//   * h_{t-1}^T lives in shared memory as the B operand (K-major, no swizzle, [rank][plane][k-chunk][b][8]).
-//     After its epilogue each CTA owns 30 fresh h values per batch column; it writes them as an fp16
-//     hi/lo "image" and one elected thread pushes that image into the B buffer of all 8 CTAs with
-//     cp.async.bulk shared::cta -> shared::cluster, completing on the receiver's mbarrier
-//     (the all-gather of the recurrence, no global memory round trip, no cluster barrier).
-//   * Epilogue per step (4 warps per sub-tile, one TMEM lane quadrant each): tcgen05.ld the 32 x NB
-//     accumulator slice, add xproj (plain coalesced 128-byte loads, prefetched one step ahead into
-//     registers), branch-free sigmoid / tanh (tanh x = 2 sigmoid 2x - 1; MUFU.EX2 + MUFU.RCP), 4x4
-//     lane transposes (shfl.xor 1, 2) that hand thread (u, j) the four gates of unit u for the batch
-//     columns b = j (mod 4), then the c/h update with the cell state in registers.  No shared-memory
-//     round trip and no block barrier between the gate activations and the cell update.
-// Sub-tiles: S independent groups of NB batch columns are interleaved per cluster so that the tensor
-// pipe (one sub-tile's MMAs) overlaps the MUFU work of another's epilogue and the DSMEM all-gather of
-// the third.
-// ------------------------------------------------------------------------------------------------
-constexpr int RC_CL = 8;            // CTAs per cluster
-constexpr int RC_U = 30;            // real units per CTA
-constexpr int RC_KP = 256;          // padded K (8 ranks x 32 slots)
-constexpr int RC_XW = 4 * RC_U;     // xproj floats per (t, b) owned by one CTA (120)
-
-// PAIR: the two CTAs of a TPC issue one tcgen05.mma.cta_group::2 (M = 256 gate rows, N = NB columns) whose B
-// operand is split between them (NB/2 columns each), so each CTA receives only half of the all-gather.
-template <int NB, int S, bool PAIR>
-struct RcCfg {
-    static constexpr int NBH = PAIR ? NB / 2 : NB;              // batch columns of the B operand held by one CTA
-    static constexpr int SLICE_BYTES = NBH * 32 * 2 * 2;        // one rank's slot: [plane][4 chunks][NBH][8] fp16
-    static constexpr int HBUF_BYTES = RC_CL * SLICE_BYTES;      // one B-operand buffer (hi+lo planes)
-    static constexpr int IMG_BYTES = NB * 32 * 2 * 2;           // this CTA's h_t of all NB columns ([half] x slot layout)
-    static constexpr int PER_SUB = 2 * HBUF_BYTES + 2 * IMG_BYTES;
-    static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = S * PER_SUB + BAR_BYTES + 1024;
-    static constexpr int THREADS = 32 * S + 128 * S;         // S MMA-issuer warps + S epilogue groups of 4 warps
-    static_assert(NB % 16 == 0 && NB <= 64, "NB must be 16, 32, 48 or 64");
-    static_assert(S * NB <= 256, "accumulators must fit in the TMEM columns left of the weights");
-    static_assert(5 * S * 8 <= BAR_BYTES - 8, "barrier area too small");
-    static_assert(!PAIR || NB % 32 == 0, "pair mode splits NB in two halves of a multiple of 16 columns");
-};
-
-struct RecurParams {
-    const float *xproj;         // [dir][t][b][g'(960)] fp32 (cluster gate order)
-    const __half *whh;          // [dir][rank][plane][128][256] fp16 (cluster gate order, zero padded)
-    const float *h0, *c0;       // [2][B][240]
-    float *hn, *cn;             // [2][B][240]  raw final state
-    __half *out_hi, *out_lo;    // layer 1: relu(h) planes [B*T][480]  (nullptr for layer 2)
-    float *out_f32;             // layer 2: relu(h) [B*T][480]         (nullptr for layer 1)
-    long long B, T;
-    long long Bp;               // row pitch of xproj in batch rows (xproj_pitch(B))
-    int b_base;                 // first batch column handled by this launch
-    int groups;                 // groups of S*NB columns per direction in this launch
-    int stagger_ns;             // initial phase offset between the sub-tiles of a cluster
-    unsigned long long *trace;  // diagnostic (hssb_debug_trace): clock64 stamps of cluster 0 / rank 0, or nullptr
-    int trace_steps;
-    // pair kernel: TMA stores of relu(h) into the slot-layout outputs [B][T][512] (fp16 hi, lo planes or one fp32 tensor)
-    alignas(64) CUtensorMap out_map[2];
-    alignas(64) CUtensorMap out_map16[2];   // the same with boxes of 16 batch columns (two epilogue warps per quadrant)
-    // fused layer-1 input projection (multicast kernel): x planes [t][32-column tile][chunk 8][32 cols][8] fp16 (hi, lo) -- the
-    // operand of one sub-tile and step is one contiguous 3 KB run --, W_ih slices [dir][rank][plane][128 rows in fragment
-    // order][64] fp16 and b_ih + b_hh [dir][rank][128] in the same row order
-    const __half *x_hi, *x_lo;
-    long long x_tiles;          // 32-column tiles per time step = ceil(B / 32)
-    const __half *wih0;
-    const float *bias0;
-    unsigned char *gather;      // multicast kernel: L2 scratch [cluster][rank][S][2][4 KB] of the all-gather
-    int debug;                  // HSSB_RC_DEBUG knock-out switches for timing experiments (results are wrong when set)
-    int layer;
-};
-
-// trace events (per step, per sub-tile): see scripts/trace_recurrent.py
-enum { TR_MMA_HFULL = 0, TR_MMA_ISSUED, TR_EPI_DFULL, TR_EPI_ACT, TR_EPI_CELL, TR_EPI_IMAGE, TR_EPI_COPIES, TR_EVENTS = 16 };
-#define HSSB_TRACE(ev, step, sub)                                                                         \
-    do {                                                                                                  \
-        if (p.trace && blockIdx.x == 0 && (step) >= 0 && (step) < p.trace_steps)                          \
-            p.trace[(((step) * 4 + (sub)) * TR_EVENTS) + (ev)] = clock64();                               \
-    } while (0)
-
-__device__ __forceinline__ float ex2_approx(float x)
-{
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// 4x4 transpose across the 4 lanes of a quad: in r[c] = a[lane j][c]  ->  out r[g] = a[lane g][j]
-__device__ __forceinline__ void quad_transpose(float (&r)[4], int j)
-{
-    const bool o1 = (j & 1) != 0, o2 = (j & 2) != 0;
-    float s0 = o1 ? r[0] : r[1], s1 = o1 ? r[2] : r[3];
-    s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
-    s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-    if (o1) { r[0] = s0; r[2] = s1; } else { r[1] = s0; r[3] = s1; }
-    s0 = o2 ? r[0] : r[2];
-    s1 = o2 ? r[1] : r[3];
-    s0 = __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
-    if (o2) { r[0] = s0; r[1] = s1; } else { r[2] = s0; r[3] = s1; }
-}
-
-template <int NB, int S, bool PAIR>
-__global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_kernel(const __grid_constant__ RecurParams p)
-{
-    using C = RcCfg<NB, S, PAIR>;
-    constexpr int NBH = C::NBH;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * C::HBUF_BYTES; };
-    auto image = [&](int s, int par) { return smem + s * C::PER_SUB + 2 * C::HBUF_BYTES + par * C::IMG_BYTES; };
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S * C::PER_SUB);
-    uint64_t *h_full = bars;                 // [S][2]  my B-operand buffer is complete
-    uint64_t *d_full = bars + 2 * S;         // [S]     accumulator complete
-    uint64_t *peer_full = bars + 3 * S;      // [S][2]  (pair leader) the odd CTA's buffer is complete
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 * S);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int cid = blockIdx.x / RC_CL;
-    const int dir = cid & 1;
-    const int group = cid >> 1;
-    const long long T = p.T, B = p.B;
-    auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * NB; };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&h_full[2 * s], 1); mbar_init(&h_full[2 * s + 1], 1); mbar_init(&d_full[s], 1);
-            mbar_init(&peer_full[2 * s], 1); mbar_init(&peer_full[2 * s + 1], 1);
-        }
-        fence_barrier_init();
-    }
-    if (PAIR) cluster_sync();                // both CTAs of a pair are resident before the paired TMEM allocation
-    if (warp == 0) { if (PAIR) tmem_alloc2<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
-    // zero the buffers (padding slots u = 30, 31 of every image must be finite zeros forever)
-    for (int i = threadIdx.x; i < S * C::PER_SUB / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    cluster_sync();     // every CTA's barriers are initialised before any remote copy can target them
-
-    if (warp < S) {
-        // ================= MMA issuer of sub-tile s = warp (one elected thread) =================
-        const int s = warp;
-        named_barrier(S + 1, 32 * S + 128);      // weights are in TMEM (loaded by epilogue group 0)
-        tc_fence_after();
-        if (sub_b0(s) < B && elect_one()) {
-            if (PAIR && (rank & 1)) {
-                // odd CTA of a pair: tell the leader when my half of the B operand has landed
-                for (long long t = 0; t < T; ++t) {
-                    const int par = (int)(t & 1);
-                    mbar_wait_cluster(&h_full[2 * s + par], (uint32_t)((t >> 1) & 1));
-                    mbar_arrive_remote(&peer_full[2 * s + par], rank ^ 1u);
-                }
-            } else {
-                constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, NB);
-                const uint32_t d_tmem = tmem_base + 256 + s * NB;
-                const uint16_t pair_mask = (uint16_t)(3u << (rank & ~1u));
-                for (long long t = 0; t < T; ++t) {
-                    const int par = (int)(t & 1);
-                    mbar_wait_cluster(&h_full[2 * s + par], (uint32_t)((t >> 1) & 1));
-                    if (PAIR) mbar_wait_cluster(&peer_full[2 * s + par], (uint32_t)((t >> 1) & 1));
-                    tc_fence_after();
-                    HSSB_TRACE(TR_MMA_HFULL, t, s);
-                    const uint32_t hb = smem_u32(hbuf(s, par));
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t blk = hb + (j >> 1) * (NBH * 128) + (j & 1) * (NBH * 32);
-                        const uint64_t b_hi = make_smem_desc(blk, NBH * 16, 128, LAYOUT_NONE);
-                        const uint64_t b_lo = make_smem_desc(blk + NBH * 64, NBH * 16, 128, LAYOUT_NONE);
-                        const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
-                        if (PAIR) {
-                            mma_f16_ts2(d_tmem, a_hi, b_hi, idesc, j != 0);
-                            mma_f16_ts2(d_tmem, a_lo, b_hi, idesc, 1);
-                            mma_f16_ts2(d_tmem, a_hi, b_lo, idesc, 1);
-                        } else {
-                            mma_f16_ts(d_tmem, a_hi, b_hi, idesc, j != 0);
-                            mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                            mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
-                        }
-                    }
-                    if (PAIR) mma_commit2_mc(&d_full[s], pair_mask); else mma_commit(&d_full[s]);
-                    HSSB_TRACE(TR_MMA_ISSUED, t, s);
-                }
-            }
-        }
-    } else {
-        // ================= epilogue group s: warps S+4s .. S+4s+3 =================
-        const int s = (warp - S) >> 2;
-        const int q = warp & 3;                  // TMEM lane quadrant of this warp
-        const int row = q * 32 + lane;           // TMEM lane = gate row 4*u + j of this CTA
-        const int u = row >> 2, j = lane & 3;    // unit 0..31 (30, 31 padding), gate / column residue
-        const bool unit_ok = u < RC_U;
-        const long long b0 = sub_b0(s);
-        const int hcol = dir * (TC_OP / 2) + (int)rank * 32 + u;    // column in the [.., 512] slot-layout outputs
-        const bool leader = (warp == S + 4 * s);
-
-        if (s == 0) {
-            // one-time: W_hh slice -> TMEM.  This thread owns lane `row`; column c holds k' = 2c, 2c+1.
-            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + row) * RC_KP;
-#pragma unroll 1
-            for (int plane = 0; plane < 2; ++plane) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
-#pragma unroll 4
-                for (int c8 = 0; c8 < 16; ++c8) {
-                    const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
-                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            named_barrier(S + 1, 32 * S + 128);
-        }
-
-        if (b0 < B) {
-            constexpr int NI = NB / 4;
-            constexpr float LOG2E = 1.4426950408889634f;
-            // sigmoid for i, f, o; tanh x = 2 sigmoid(2x) - 1 for g: act = ksc * rcp(1 + 2^(nsc * x)) + kof
-            const float ksc = (j == 2) ? 2.0f : 1.0f, nsc = -ksc * LOG2E, kof = 1.0f - ksc;
-            const int ncols = (int)((B - b0 < NB) ? (B - b0) : NB);
-            const bool full = ncols == NB;
-            const int ni_valid = (ncols - j + 3) / 4;                   // columns 4i + j < ncols  <=>  i < ni_valid
-            // xproj of this thread's gate row (padding lanes re-read row 119, result unused):
-            // element (t, b) at xp_base + (t*B + b)*960
-            const int xrow = unit_ok ? row : RC_XW - 1;
-            const float *xp_base = p.xproj + (size_t)dir * T * p.Bp * TC_G + (size_t)b0 * TC_G + rank * RC_XW + xrow;
-            const long long xstep = (dir ? -1 : 1) * p.Bp * TC_G;       // one time step
-            const float *xp_next = xp_base + (dir ? (size_t)(T - 1) * p.Bp * TC_G : 0);
-            float c_state[NI], hv[NI], xnext[NB];
-            auto load_x = [&]() {                                        // xproj of the next step -> registers
-                if (full) {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) xnext[b] = __ldcs(xp_next + b * TC_G);
-                } else {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) xnext[b] = (b < ncols) ? __ldcs(xp_next + b * TC_G) : 0.0f;
-                }
-                xp_next += xstep;
-            };
-            load_x();
-            // outputs of (unit u, column 4i + j): element offset of step tt = o_base + i*o_stride + tt*480
-            const size_t o_stride = (size_t)4 * T * TC_OP;
-            size_t o_next = ((size_t)(b0 + j) * T + (dir ? T - 1 : 0)) * TC_OP + hcol;
-            const long long o_step = (dir ? -1 : 1) * TC_OP;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * NB;
-            if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const long long bg = b0 + 4 * i + j;
-                const bool ok = unit_ok && i < ni_valid;
-                hv[i] = ok ? __ldg(p.h0 + ((size_t)dir * B + bg) * TC_H + rank * RC_U + u) : 0.f;
-                c_state[i] = ok ? __ldg(p.c0 + ((size_t)dir * B + bg) * TC_H + rank * RC_U + u) : 0.f;
-            }
-            for (long long t = -1; t < T; ++t) {
-                if (t >= 0) {
-                    mbar_wait(&d_full[s], (uint32_t)(t & 1));
-                    tc_fence_after();
-                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_DFULL, t, s);
-                    uint32_t v[NB];
-#pragma unroll
-                    for (int c16 = 0; c16 < NB / 16; ++c16) tmem_ld_x16(taddr + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    float act[NB];
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) act[b] = (__uint_as_float(v[b]) + xnext[b]) * nsc;
-                    if (t + 1 < T) load_x();               // lands during this step's math and the all-gather
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) act[b] = fmaf(rcp_approx(1.0f + ex2_approx(act[b])), ksc, kof);
-                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_ACT, t, s);
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        float g4[4] = {act[4 * i], act[4 * i + 1], act[4 * i + 2], act[4 * i + 3]};
-                        quad_transpose(g4, j);                         // -> i, f, g, o of (unit u, column 4i + j)
-                        const float c = fmaf(g4[1], c_state[i], g4[0] * g4[2]);
-                        c_state[i] = c;
-                        const float th = fmaf(rcp_approx(1.0f + ex2_approx(c * (-2.0f * LOG2E))), 2.0f, -1.0f);
-                        hv[i] = unit_ok ? g4[3] * th : 0.0f;
-                    }
-                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_CELL, t, s);
-                }
-                // h_t of (unit u, columns 4i + j) -> fp16 hi/lo image [plane][k-chunk q][b][8 units]
-                if (t + 1 < T) {
-                    // (pair mode: columns [0, NB/2) form the half sent to the even CTAs, the rest goes to the odd ones)
-                    __half *img_hi = reinterpret_cast<__half *>(image(s, (int)(t & 1))) + q * (NBH * 8) + j * 8 + (lane >> 2);
-                    __half *img_lo = img_hi + NBH * 32;
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        __half hh, hl;
-                        split_f16(hv[i], hh, hl);
-                        const int off = (4 * i >= NBH) ? (NBH * 64 + (4 * i - NBH) * 8) : 4 * i * 8;   // [half][plane][chunk][col][8]
-                        img_hi[off] = hh;
-                        img_lo[off] = hl;
-                    }
-                    fence_proxy_async_smem();
-                    named_barrier(1 + s, 128);
-                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_IMAGE, t, s);
-                    if (leader) {
-                        // all-gather: this CTA's image -> slot `rank` of every CTA's B buffer for step t+1;
-                        // lane r pushes to CTA r
-                        const int par = (int)((t + 1) & 1);
-                        if (lane == 0) mbar_arrive_expect_tx(&h_full[2 * s + par], C::HBUF_BYTES);
-                        __syncwarp();
-                        if (lane < RC_CL)
-                            bulk_copy_to_cta(hbuf(s, par) + rank * C::SLICE_BYTES, image(s, (int)(t & 1)) + (PAIR ? (lane & 1) * C::SLICE_BYTES : 0),
-                                             C::SLICE_BYTES, &h_full[2 * s + par], lane);
-                    }
-                    if (leader && lane == 0) HSSB_TRACE(TR_EPI_COPIES, t, s);
-                }
-                // ---- off the critical path: this step's outputs to global memory ----
-                if (t >= 0) {
-                    {                                   // padding slots 30, 31 are written too (zeros)
-                        size_t o = o_next;
-                        if (p.out_f32) {
-#pragma unroll
-                            for (int i = 0; i < NI; ++i, o += o_stride)
-                                if (i < ni_valid) p.out_f32[o] = fmaxf(hv[i], 0.f);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < NI; ++i, o += o_stride)
-                                if (i < ni_valid) {
-                                    __half hh, hl;
-                                    split_f16(fmaxf(hv[i], 0.f), hh, hl);
-                                    p.out_hi[o] = hh;
-                                    p.out_lo[o] = hl;
-                                }
-                        }
-                    }
-                    o_next += o_step;
-                }
-            }
-            if (unit_ok) {
-#pragma unroll
-                for (int i = 0; i < NI; ++i)
-                    if (i < ni_valid) {
-                        const size_t o = ((size_t)dir * B + b0 + 4 * i + j) * TC_H + rank * RC_U + u;
-                        p.hn[o] = hv[i];
-                        p.cn[o] = c_state[i];
-                    }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync();
-    if (warp == 0) { if (PAIR) tmem_dealloc2<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5p: recurrence for large batches -- CTA pairs (cta_group::2), 64 batch columns per MMA.
-//
-// What bounds the kernel above is the per-step chain (MMA -> TMEM load -> activations -> all-gather) and, at 96
-// columns per cluster, the all-gather itself: every CTA pushes 1 KB per column to 7 peers through DSMEM
-// (~17 B/cycle/SM measured, scripts/microbench/ub_cluster.cu), about twice the tensor time of the same columns.
-// Here the two CTAs of a TPC issue ONE tcgen05.mma.cta_group::2 (M = 256 gate rows, N = 64 columns; 33 cycles,
-// the same as a cta_group::1 MMA of that N) whose B operand is split between them: the even CTA holds columns
-// [0, 32) of h_{t-1}, the odd CTA columns [32, 64), so every CTA receives -- and sends -- half as much.
-//   * TMEM lanes in "fragment order" (lane = 32*(u/8) + 8*gate + u%8): two tcgen05.ld.16x256b.x4 hand thread
-//     (ul = lane/4, cp = lane%4) the four gates of unit 8q+ul for the 8 columns 8k + 2cp + {0,1} -- no shuffles,
-//     and the matching xproj values are 8 coalesced 16-byte loads (xproj keeps the 4*u + gate order of K4).
-//   * 8 epilogue warps per sub-tile = 4 TMEM lane quadrants x 2 column halves; the warps of half `hf` produce
-//     exactly the part of the image that goes to the CTAs of parity `hf` (4 bulk copies of 4 KB per half).
-//   * every B buffer has one mbarrier per SOURCE PAIR, so the MMA issuer starts on the K range of a pair as soon
-//     as that pair's slices landed (the group holding this pair's own slices first: its arrival also proves that
-//     all 16 epilogue warps of the pair have read the previous accumulator).  The odd CTA relays its arrivals to
-//     the even (issuing) CTA.
-//   * activations with 8 instead of 10 MUFU ops per (unit, column): the reciprocals of i.g and o.tanh(c) are
-//     shared, i*g = (1 - e_g) / ((1 + e_i)(1 + e_g)) with e_x = exp(-x) (exp(-2x) for g and c).
-//   * outputs (relu(h) of the step) leave through a per-warp shared-memory tile and one TMA tensor store per
-//     plane (box 8 units x 32 columns of the slot-layout [B][T][512] tensors; ragged batches are clipped by the
-//     TMA unit) instead of 16 scattered 2-byte global stores per thread.
-// Layout of one B buffer: [source rank 8][k-chunk 4][plane 2][column 32][8 units] fp16 (K-major core matrices:
-// LBO = 1 KB between k-chunks, SBO = 128 B between 8-column groups).
-// ------------------------------------------------------------------------------------------------
-constexpr int RP_NB = 64;                          // columns of one sub-tile (pair MMA N)
-constexpr int RP_NBH = 32;                         // columns held (and produced per epilogue warp) per CTA half
-constexpr int RP_G = 4;                            // arrival groups per buffer (= source pairs)
-constexpr int RP_PIECE = RP_NBH * 8 * 2 * 2;       // [plane][32 cols][8 units] fp16 = 1 KB: one epilogue warp's output
-constexpr int RP_SLICE = 4 * RP_PIECE;             // one source rank: 4 k-chunks
-constexpr int RP_HBUF = RC_CL * RP_SLICE;          // 32 KB
-
-template <int S>
-struct RpCfg {
-    static constexpr int PER_SUB = 2 * RP_HBUF + 4 * RP_SLICE;       // 2 B buffers + images [parity][half]
-    static constexpr int OUT_BYTES = S * 8 * 1024;                   // per epilogue warp: relu(h) tile for the TMA store
-    static constexpr int BAR_BYTES = 512;
-    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + BAR_BYTES + 1024;
-    static constexpr int THREADS = 32 * S + 256 * S;                 // S issuer / relay warps + S x 8 epilogue warps
-    static_assert(S * RP_NB <= 256, "accumulators must fit in the TMEM columns left of the weights");
-    static_assert((4 * S * RP_G + S) * 8 + 8 <= BAR_BYTES, "barrier area too small");
-};
-
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *src, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void sts_b16(uint32_t addr, __half v)
-{
-    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(v)) : "memory");
-}
-__device__ __forceinline__ void sts_b32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-
-template <int S>
-__global__ void __launch_bounds__(RpCfg<S>::THREADS, 1) tc_recurrent_pair_kernel(const __grid_constant__ RecurParams p)
-{
-    using C = RpCfg<S>;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * RP_HBUF; };
-    auto image = [&](int s, int par, int hf) { return smem + s * C::PER_SUB + 2 * RP_HBUF + (par * 2 + hf) * RP_SLICE; };
-    unsigned char *out_tiles = smem + S * C::PER_SUB;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(out_tiles + C::OUT_BYTES);
-    uint64_t *own_full = bars;                       // [S][2][G]  slices of source pair g have landed in my buffer
-    uint64_t *peer_full = bars + 2 * S * RP_G;       // [S][2][G]  (even CTA) ... and in the odd CTA's buffer
-    uint64_t *d_full = bars + 4 * S * RP_G;          // [S]        accumulator complete
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + S);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int cid = blockIdx.x / RC_CL;
-    const int dir = cid & 1;
-    const int group = cid >> 1;
-    const long long T = p.T, B = p.B;
-    auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * RP_NB; };
-    unsigned long long *const tr_buf = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
-#define RP_TRACE(ev, step, sub)                                                                                       \
-    do {                                                                                                              \
-        if (tr_buf && (step) >= 0 && (step) < p.trace_steps) tr_buf[(((step) * 4 + (sub)) * TR_EVENTS) + (ev)] = clock64(); \
-    } while (0)
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 4 * S * RP_G + S; ++i) mbar_init(&bars[i], 1);
-        fence_barrier_init();
-        prefetch_tmap(&p.out_map[0]);
-        if (!p.out_f32) prefetch_tmap(&p.out_map[1]);
-    }
-    cluster_sync();                          // both CTAs of a pair are resident before the paired TMEM allocation
-    if (warp == 0) tmem_alloc2<512>(tmem_slot);
-    for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    cluster_sync();                          // every CTA's barriers are initialised before any remote copy can target them
-
-    if (warp < S) {
-        // ================= MMA issuer (even CTA) / arrival relay (odd CTA) of sub-tile s = warp =================
-        const int s = warp;
-        named_barrier(9, 32 * S + 128);          // weights are in TMEM
-        tc_fence_after();
-        if (sub_b0(s) < B && elect_one()) {
-            const int g0 = (int)(rank >> 1);
-            for (int i = 0; i < 2 * RP_G; ++i) mbar_arrive_expect_tx(&own_full[s * 2 * RP_G + i], 2 * RP_SLICE);
-            if (rank & 1) {
-                for (long long t = 0; t < T; ++t) {
-                    const int par = (int)(t & 1);
-                    const uint32_t ph = (uint32_t)((t >> 1) & 1);
-#pragma unroll
-                    for (int gi = 0; gi < RP_G; ++gi) {
-                        const int bi = (s * 2 + par) * RP_G + ((g0 + gi) & (RP_G - 1));
-                        mbar_wait_cluster(&own_full[bi], ph);
-                        mbar_arrive_remote(&peer_full[bi], rank ^ 1u);
-                        if (t + 2 < T) mbar_arrive_expect_tx(&own_full[bi], 2 * RP_SLICE);
-                    }
-                }
-            } else {
-                constexpr uint32_t idesc = make_idesc_f16(256, RP_NB);
-                const uint32_t d_tmem = tmem_base + 256 + s * RP_NB;
-                const uint16_t pair_mask = (uint16_t)(3u << rank);
-                for (long long t = 0; t < T; ++t) {
-                    const int par = (int)(t & 1);
-                    const uint32_t ph = (uint32_t)((t >> 1) & 1);
-                    const uint32_t hb = smem_u32(hbuf(s, par));
-#pragma unroll
-                    for (int gi = 0; gi < RP_G; ++gi) {
-                        const int g = (g0 + gi) & (RP_G - 1);
-                        const int bi = (s * 2 + par) * RP_G + g;
-                        mbar_wait_cluster(&own_full[bi], ph);
-                        mbar_wait_cluster(&peer_full[bi], ph);
-                        if (t + 2 < T) mbar_arrive_expect_tx(&own_full[bi], 2 * RP_SLICE);
-                        tc_fence_after();
-                        if (gi == 0) RP_TRACE(TR_MMA_HFULL, t, s);
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int j = 4 * g + jj;                      // K16 step: source rank j >> 1, k-chunks 2(j&1), 2(j&1)+1
-                            const uint32_t blk = hb + (j >> 1) * RP_SLICE + (j & 1) * (2 * RP_PIECE);
-                            const uint64_t b_hi = make_smem_desc(blk, RP_PIECE, 128, LAYOUT_NONE);
-                            const uint64_t b_lo = make_smem_desc(blk + RP_PIECE / 2, RP_PIECE, 128, LAYOUT_NONE);
-                            const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
-                            mma_f16_ts2(d_tmem, a_hi, b_hi, idesc, (gi | jj) != 0);
-                            mma_f16_ts2(d_tmem, a_lo, b_hi, idesc, 1);
-                            mma_f16_ts2(d_tmem, a_hi, b_lo, idesc, 1);
-                        }
-                    }
-                    mma_commit2_mc(&d_full[s], pair_mask);
-                    RP_TRACE(TR_MMA_ISSUED, t, s);
-                }
-            }
-        }
-    } else {
-        // ================= epilogue warp: sub-tile s, column half hf, TMEM lane quadrant q =================
-        const int k = (warp - S) >> 2;
-        const int s = k >> 1, hf = k & 1;
-        const int q = warp & 3;
-        const int ul = lane >> 2, cp = lane & 3;     // unit within the k-chunk q; column pair
-        const int u = 8 * q + ul;                    // unit 0..31 of this CTA (30, 31 padding)
-        const bool unit_ok = u < RC_U;
-        const long long b0 = sub_b0(s) + hf * RP_NBH;
-        const bool tracer = (hf == 0 && q == 0 && lane == 0);
-        unsigned char *out_tile = out_tiles + (warp - S) * 1024;
-
-        if (k == 0) {
-            // one-time: W_hh slice -> TMEM.  This thread owns lane 32q + lane; column c holds k' = 2c, 2c+1.
-            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * RC_KP;
-#pragma unroll 1
-            for (int plane = 0; plane < 2; ++plane) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
-#pragma unroll 4
-                for (int c8 = 0; c8 < 16; ++c8) {
-                    const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
-                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            named_barrier(9, 32 * S + 128);
-        }
-
-        if (sub_b0(s) < B) {
-            constexpr int NI = RP_NBH / 4;              // 8 (unit, column) cells per thread: columns 8*(i/2) + 2*cp + (i&1)
-            constexpr float LOG2E = 1.4426950408889634f;
-            constexpr float EMAX = 60.0f;               // exponent clamp: (1 + 2^60)^2 is finite, sigmoid(-41) = 0 in fp32 anyway
-            const long long left = B - b0;
-            const int ncols = (int)(left < 0 ? 0 : (left < RP_NBH ? left : RP_NBH));    // valid columns of this half (may be 0)
-            auto col_of = [&](int i) { return 8 * (i >> 1) + 2 * cp + (i & 1); };
-            // xproj of (unit u, column c): 4 consecutive floats i, f, g, o at xp + c*960 (16-byte aligned)
-            const int ux = unit_ok ? u : RC_U - 1;
-            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * p.Bp * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
-            const long long xstep = (dir ? -1 : 1) * p.Bp * TC_G;
-            float4 xnext[NI];
-            float c_state[NI];
-            // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
-            // wait of the warp (spill reloads, TMA issue, ...) would otherwise sit behind these HBM loads.
-            auto load_x = [&]() {
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const int c = col_of(i);
-                    xnext[i] = (c < ncols) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                xp_next += xstep;
-            };
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * RP_NB + hf * RP_NBH;
-            const uint32_t my_group = rank >> 1;          // my slices complete barrier `my_group` of every destination
-            const int out_c0 = dir * (TC_OP / 2) + (int)rank * 32 + 8 * q;      // first column of this warp's 8 units
-            const size_t state_o = ((size_t)dir * B + b0) * TC_H + rank * RC_U + u;      // + column * TC_H
-            // h_t of (unit u, 8 columns) -> this warp's piece [plane][col][8 units] of the fp16 hi/lo image, then
-            // (after the 4 warps of this half have written theirs) 4 bulk copies of the 4 KB half-image
-            auto publish = [&](const float (&hv)[NI], int t) {
-                const uint32_t img = smem_u32(image(s, (int)(t & 1), hf)) + q * RP_PIECE + ul * 2;
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    __half hh, hl;
-                    split_f16(hv[i], hh, hl);
-                    sts_b16(img + col_of(i) * 16, hh);
-                    sts_b16(img + RP_NBH * 16 + col_of(i) * 16, hl);
-                }
-                fence_proxy_async_smem();
-                named_barrier(1 + k, 128);
-                if (tracer) RP_TRACE(TR_EPI_IMAGE, t, s);
-                if (q == 0 && elect_one()) {
-                    const int par = (int)((t + 1) & 1);
-                    uint64_t *bar = &own_full[(s * 2 + par) * RP_G + my_group];
-#pragma unroll
-                    for (int d = 0; d < 4; ++d)
-                        bulk_copy_to_cta(hbuf(s, par) + rank * RP_SLICE, image(s, (int)(t & 1), hf), RP_SLICE, bar, (uint32_t)(2 * d + hf));
-                }
-                if (tracer) RP_TRACE(TR_EPI_COPIES, t, s);
-            };
-            {
-                float h_init[NI];
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const bool ok = unit_ok && col_of(i) < ncols;
-                    h_init[i] = ok ? __ldg(p.h0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
-                    c_state[i] = ok ? __ldg(p.c0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
-                }
-                if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster
-                publish(h_init, -1);
-            }
-            load_x();
-            const int Ti = (int)T;
-            int t_idx = dir ? Ti - 1 : 0;
-            for (int t = 0; t < Ti; ++t) {
-                mbar_wait(&d_full[s], (uint32_t)(t & 1));
-                tc_fence_after();
-                if (tracer) RP_TRACE(TR_EPI_DFULL, t, s);
-                float hv[NI];
-                {
-                    // two passes of 16 columns keep the register peak (xproj prefetch + accumulators + exponentials) under 96
-                    float ei[NI], ef[NI], eg[NI], eo[NI];
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        uint32_t a[8], b[8];    // a: gates i (lane ul), f (lane ul+8);  b: gates g, o;  [4k + 2*gate + c] = column 16*pass + 8k + 2cp + c
-                        tmem_ld_16x256b_x2(taddr + 16 * pass, a);
-                        tmem_ld_16x256b_x2(taddr + (16u << 16) + 16 * pass, b);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int ii = 0; ii < 4; ++ii) {
-                            const int i = 4 * pass + ii, r = 4 * (ii >> 1) + (ii & 1);
-                            ei[i] = ex2_approx(fminf((__uint_as_float(a[r]) + xnext[i].x) * -LOG2E, EMAX));
-                            ef[i] = ex2_approx(fminf((__uint_as_float(a[r + 2]) + xnext[i].y) * -LOG2E, EMAX));
-                            eg[i] = ex2_approx(fminf((__uint_as_float(b[r]) + xnext[i].z) * (-2.0f * LOG2E), EMAX));
-                            eo[i] = ex2_approx(fminf((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E, EMAX));
-                        }
-                    }
-                    tc_fence_before();
-                    if (tracer) RP_TRACE(TR_EPI_ACT, t, s);
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        const float ig = (1.0f - eg[i]) * rcp_approx((1.0f + ei[i]) * (1.0f + eg[i]));      // sigmoid(i) tanh(g)
-                        const float c = fmaf(rcp_approx(1.0f + ef[i]), c_state[i], ig);
-                        c_state[i] = c;
-                        const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EMAX));
-                        const float h = (1.0f - ec) * rcp_approx((1.0f + eo[i]) * (1.0f + ec));             // sigmoid(o) tanh(c)
-                        hv[i] = unit_ok ? h : 0.0f;
-                    }
-                    if (tracer) RP_TRACE(TR_EPI_CELL, t, s);
-                }
-                if (t + 1 < Ti) publish(hv, t);
-                // ---- off the critical path: relu(h_t) -> global memory by TMA from this warp's tile ----
-                if (elect_one()) tma_store_wait_read<0>();        // the previous step's store has read the tile
-                __syncwarp();
-                const uint32_t tile = smem_u32(out_tile);
-                if (p.out_f32) {
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) sts_b32(tile + col_of(i) * 32 + ul * 4, fmaxf(hv[i], 0.f));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        __half hh, hl;
-                        split_f16(fmaxf(hv[i], 0.f), hh, hl);
-                        sts_b16(tile + col_of(i) * 16 + ul * 2, hh);
-                        sts_b16(tile + 512 + col_of(i) * 16 + ul * 2, hl);
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (ncols > 0 && elect_one()) {
-                    tma_store_3d(&p.out_map[0], out_tile, out_c0, t_idx, (int)b0);
-                    if (!p.out_f32) tma_store_3d(&p.out_map[1], out_tile + 512, out_c0, t_idx, (int)b0);
-                    tma_store_commit();
-                }
-                t_idx += dir ? -1 : 1;
-                if (t + 1 < Ti) {
-                    load_x();
-                } else if (unit_ok) {
-#pragma unroll
-                    for (int i = 0; i < NI; ++i)
-                        if (col_of(i) < ncols) {
-                            p.hn[state_o + (size_t)col_of(i) * TC_H] = hv[i];
-                            p.cn[state_o + (size_t)col_of(i) * TC_H] = c_state[i];
-                        }
-                }
-            }
-            if (elect_one()) tma_store_wait<0>();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync();
-    if (warp == 0) tmem_dealloc2<512>(tmem_base);
-#undef RP_TRACE
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5m: recurrence with the all-gather through L2 (bulk store + TMA multicast) -- the large-batch kernel.
-//
-// Measured on B200 (scripts/microbench/ub_cluster.cu): a CTA can push ~17 B/cycle into DSMEM, so the 8-way
-// all-gather of the kernels above costs 5 750 cycles per step at 96 columns per cluster -- twice the tensor time.
-// The same exchange through L2 -- every CTA bulk-stores its 4 KB image once and then issues ONE multicast bulk
-// load that delivers it to all 8 CTAs of the cluster -- moves 50-60 B/cycle into every SM and takes ~1 100
-// cycles end to end, with two bulk operations per sub-tile and step instead of eight.
-//   * one CTA per 30 units as before (cta_group::1, M = 128, N = 32, W_hh hi/lo resident in TMEM), S = 1..3
-//     independent sub-tiles of 32 batch columns interleaved per cluster;
-//   * TMEM lanes in fragment order, xproj as 16-byte loads issued at the END of a step, outputs by TMA store:
-//     see the pair kernel above (same epilogue);
-//   * every B buffer has one mbarrier per pair of source ranks; the MMA issuer starts on a pair's K range as
-//     soon as its two slices landed (own pair first: its arrival proves that the four epilogue warps have
-//     read the previous accumulator);
-//   * the image is single-buffered: the issuing thread waits for its bulk store (cp.async.bulk.wait_group)
-//     before it issues the multicast load, and nobody rewrites the image before the next accumulator, which
-//     depends on that load; the L2 scratch slot is double-buffered by step parity.
-// ------------------------------------------------------------------------------------------------
-constexpr int RX_KSTEPS = 3;                       // fused layer-1 input projection: K16 steps of the x operand (input_size <= 48)
-constexpr int RX_CHUNKS = 2 * RX_KSTEPS;           // 8-feature k-chunks
-constexpr int RX_PLANE = RX_CHUNKS * RP_NBH * 16;  // [chunk][32 cols][8 features] fp16 = 3 KB
-constexpr int RX_TMEM = 256 + 96;                  // TMEM column of the W_ih slice (hi plane; lo plane 8*RX_KSTEPS columns further)
-
-template <int S, int EW, bool FUSE_X = false>
-struct RmCfg {
-    static constexpr int NW = RP_NBH / EW;                           // batch columns per epilogue warp
-    static constexpr int PER_SUB = 2 * RP_HBUF + RP_SLICE;           // 2 B buffers + one image
-    static constexpr int TILE_BYTES = 1024 / EW;                     // per epilogue warp: relu(h) tile for the TMA store
-    // fused: the relu(h) tile of a warp reuses its piece of the image (free again once the bulk store of the publish has
-    // completed), which makes room for the x operand buffers
-    static constexpr int OUT_BYTES = FUSE_X ? 0 : S * 4 * EW * TILE_BYTES;
-    static constexpr int X_BYTES = FUSE_X ? S * 2 * RX_PLANE : 0;
-    static constexpr int BAR_BYTES = 512;
-    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + X_BYTES + BAR_BYTES + 1024;
-    static constexpr int THREADS = 32 * S + 128 * S * EW;            // S issuer warps + S x 4 x EW epilogue warps
-    static_assert(EW == 1 || EW == 2, "one or two epilogue warps per TMEM lane quadrant and sub-tile");
-    static_assert(S * RP_NBH <= 96, "accumulators sit in TMEM columns [256, 352)");
-    static_assert((2 * S * RP_G + 4 * S) * 8 + 8 <= BAR_BYTES, "barrier area too small");
-    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-};
-
-// global -> own shared memory, completing `bytes` on the mbarrier
-__device__ __forceinline__ void bulk_load_global(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void bulk_store_global(void *gdst, const void *ssrc, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-// global -> the same smem offset in every CTA of `mask`, completing `bytes` on each one's mbarrier
-__device__ __forceinline__ void bulk_load_multicast(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint16_t mask)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
-}
-
-template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X>
-__global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
-{
-    using C = RmCfg<S, EW, FUSE_X>;
-    static_assert(EW == 1 || WARP_PUBLISH, "two warps per quadrant publish per warp");
-    static_assert(!FUSE_X || WARP_PUBLISH, "the fused kernel reuses each warp's image piece as its output tile");
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    auto hbuf = [&](int s, int par) { return smem + s * C::PER_SUB + par * RP_HBUF; };
-    auto image = [&](int s) { return smem + s * C::PER_SUB + 2 * RP_HBUF; };
-    unsigned char *out_tiles = smem + S * C::PER_SUB;
-    unsigned char *xbufs = out_tiles + C::OUT_BYTES;             // fused: [S][plane][chunk][32 cols][8 features] fp16
-    uint64_t *bars = reinterpret_cast<uint64_t *>(xbufs + C::X_BYTES);
-    uint64_t *h_full = bars;                         // [S][2][G]  slices of source pair g have landed in my buffer
-    uint64_t *d_full = bars + 2 * S * RP_G;          // [S]        accumulator complete
-    uint64_t *d_empty = d_full + S;                  // [S]        (fused) every epilogue warp has read the accumulator
-    uint64_t *x_full = d_full + 2 * S;               // [S]        (fused) x_t operand landed
-    uint64_t *x_empty = d_full + 3 * S;              // [S]        (fused) the MMAs reading the x operand are complete
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + 4 * S);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int cid = blockIdx.x / RC_CL;
-    const int dir = cid & 1;
-    const int group = cid >> 1;
-    const long long T = p.T, B = p.B;
-    auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * RP_NBH; };
-    unsigned long long *const tr_buf = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
-#define RM_TRACE(ev, step, sub)                                                                                       \
-    do {                                                                                                              \
-        if (tr_buf && (step) >= 0 && (step) < p.trace_steps) tr_buf[(((step) * 4 + (sub)) * TR_EVENTS) + (ev)] = clock64(); \
-    } while (0)
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * S * RP_G + 4 * S; ++i) mbar_init(&bars[i], 1);
-        for (int i = 0; i < S; ++i) mbar_init(&d_empty[i], 4 * EW);
-        fence_barrier_init();
-        const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;
-        prefetch_tmap(&om[0]);
-        if (!p.out_f32) prefetch_tmap(&om[1]);
-    }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES + C::X_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    cluster_sync();                          // every CTA's barriers are initialised before any multicast can target them
-
-    if (warp < S) {
-        // ================= MMA issuer of sub-tile s = warp (one elected thread) =================
-        const int s = warp;
-        named_barrier(9, 32 * S + 128);          // weights are in TMEM
-        tc_fence_after();
-        if (sub_b0(s) < B && elect_one()) {
-            const int g0 = (int)(rank >> 1);
-            for (int i = 0; i < 2 * RP_G; ++i) mbar_arrive_expect_tx(&h_full[s * 2 * RP_G + i], 2 * RP_SLICE);
-            constexpr uint32_t idesc = make_idesc_f16(128, RP_NBH);
-            const uint32_t d_tmem = tmem_base + 256 + s * RP_NBH;
-            const int Ti = (int)T;
-            unsigned char *xb = xbufs + s * 2 * RX_PLANE;
-            auto load_x_operand = [&](int t) {           // x_t of this sub-tile's 32 columns: both fp16 planes, [chunk][col][8], 3 KB each
-                const int t_idx = dir ? Ti - 1 - t : t;
-                const size_t off = ((size_t)t_idx * p.x_tiles + (size_t)(sub_b0(s) / RP_NBH)) * (8 * RP_NBH * 8);     // halves
-                mbar_arrive_expect_tx(&x_full[s], 2 * RX_PLANE);
-                bulk_load_global(xb, p.x_hi + off, RX_PLANE, &x_full[s]);
-                bulk_load_global(xb + RX_PLANE, p.x_lo + off, RX_PLANE, &x_full[s]);
-            };
-            if (FUSE_X) load_x_operand(0);
-            for (int t = 0; t < Ti; ++t) {
-                const int par = t & 1;
-                const uint32_t ph = (uint32_t)((t >> 1) & 1);
-                const uint32_t hb = smem_u32(hbuf(s, par));
-                if (FUSE_X) {
-                    // W_ih . x_t first: it does not depend on h_{t-1}, only on the epilogue having read the previous accumulator
-                    if (t > 0) mbar_wait(&d_empty[s], (uint32_t)((t - 1) & 1));
-                    mbar_wait(&x_full[s], (uint32_t)(t & 1));
-                    tc_fence_after();
-#pragma unroll
-                    for (int j = 0; j < RX_KSTEPS; ++j) {
-                        const uint32_t blk = smem_u32(xb) + j * (2 * RP_NBH * 16);
-                        const uint64_t x_hi = make_smem_desc(blk, RP_NBH * 16, 128, LAYOUT_NONE);
-                        const uint64_t x_lo = make_smem_desc(blk + RX_PLANE, RP_NBH * 16, 128, LAYOUT_NONE);
-                        const uint32_t w_hi = tmem_base + RX_TMEM + j * 8, w_lo = w_hi + 8 * RX_KSTEPS;
-                        mma_f16_ts(d_tmem, w_hi, x_hi, idesc, j != 0);
-                        mma_f16_ts(d_tmem, w_lo, x_hi, idesc, 1);
-                        mma_f16_ts(d_tmem, w_hi, x_lo, idesc, 1);
-                    }
-                    mma_commit(&x_empty[s]);
-                }
-#pragma unroll
-                for (int gi = 0; gi < RP_G; ++gi) {
-                    const int g = (g0 + gi) & (RP_G - 1);
-                    uint64_t *bar = &h_full[(s * 2 + par) * RP_G + g];
-                    mbar_wait_cluster(bar, ph);
-                    if (t + 2 < Ti) mbar_arrive_expect_tx(bar, 2 * RP_SLICE);
-                    tc_fence_after();
-                    if (gi == 0) RM_TRACE(TR_MMA_HFULL, t, s);
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = 4 * g + jj;                      // K16 step: source rank j >> 1, k-chunks 2(j&1), 2(j&1)+1
-                        const uint32_t blk = hb + (j >> 1) * RP_SLICE + (j & 1) * (2 * RP_PIECE);
-                        const uint64_t b_hi = make_smem_desc(blk, RP_PIECE, 128, LAYOUT_NONE);
-                        const uint64_t b_lo = make_smem_desc(blk + RP_PIECE / 2, RP_PIECE, 128, LAYOUT_NONE);
-                        const uint32_t a_hi = tmem_base + j * 8, a_lo = tmem_base + 128 + j * 8;
-                        mma_f16_ts(d_tmem, a_hi, b_hi, idesc, FUSE_X || (gi | jj) != 0);
-                        mma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                        mma_f16_ts(d_tmem, a_hi, b_lo, idesc, 1);
-                    }
-                }
-                mma_commit(&d_full[s]);
-                RM_TRACE(TR_MMA_ISSUED, t, s);
-                if (FUSE_X && t + 1 < Ti) {
-                    mbar_wait(&x_empty[s], (uint32_t)(t & 1));      // long since complete: the h part was issued behind it
-                    load_x_operand(t + 1);
-                }
-            }
-        }
-    } else {
-        // ================= epilogue warp: sub-tile s, TMEM lane quadrant q =================
-        const int s = (warp - S) / (4 * EW);
-        const int half = ((warp - S) >> 2) % EW;     // which NW-column part of the sub-tile this warp drains
-        const int cbase = half * C::NW;
-        const int q = warp & 3;
-        const int ul = lane >> 2, cp = lane & 3;     // unit within the k-chunk q; column pair
-        const int u = 8 * q + ul;                    // unit 0..31 of this CTA (30, 31 padding)
-        const bool unit_ok = u < RC_U;
-        const long long b0 = sub_b0(s);
-        const bool tracer = (q == 0 && lane == 0 && half == 0);
-        // fused: the relu(h) tile (fp16 hi / lo) lives in this warp's own two runs of its image piece, free once its publish completed
-        unsigned char *out_tile = FUSE_X ? image(s) + q * RP_PIECE + cbase * 16 : out_tiles + (warp - S) * C::TILE_BYTES;
-        constexpr int LO_OFF = FUSE_X ? RP_PIECE / 2 : C::NW * 16;      // lo plane of the tile
-
-        if (s == 0 && half == 0) {
-            // one-time: W_hh slice -> TMEM.  This thread owns lane 32q + lane; column c holds k' = 2c, 2c+1.
-            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * RC_KP;
-#pragma unroll 1
-            for (int plane = 0; plane < 2; ++plane) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
-#pragma unroll 4
-                for (int c8 = 0; c8 < 16; ++c8) {
-                    const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
-                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
-                }
-            }
-            if (FUSE_X) {
-                // W_ih slice (rows in the same fragment order, K = 16*RX_KSTEPS features): hi plane, then lo plane
-                const __half *xrow = p.wih0 + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * 64;
-#pragma unroll 1
-                for (int plane = 0; plane < 2; ++plane) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(xrow + (size_t)plane * 128 * 64);
-#pragma unroll
-                    for (int c8 = 0; c8 < RX_KSTEPS; ++c8) {
-                        const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
-                        const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                        tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + RX_TMEM + plane * 8 * RX_KSTEPS + c8 * 8, r);
-                    }
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            named_barrier(9, 32 * S + 128);
-        }
-
-        if (b0 < B) {
-            constexpr int NW = C::NW;
-            constexpr int NI = NW / 4;                  // (unit, column) cells per thread: columns cbase + 8*(i/2) + 2*cp + (i&1)
-            constexpr float LOG2E = 1.4426950408889634f;
-            constexpr float EMAX = 60.0f;               // exponent clamp: (1 + 2^60)^2 is finite, sigmoid(-41) = 0 in fp32 anyway
-            const long long left = B - b0;
-            const int ncols = (int)(left < RP_NBH ? left : RP_NBH);
-            auto col_of = [&](int i) { return cbase + 8 * (i >> 1) + 2 * cp + (i & 1); };
-            const int ux = unit_ok ? u : RC_U - 1;
-            const float *xp_next = p.xproj + ((size_t)dir * T + (dir ? T - 1 : 0)) * p.Bp * TC_G + (size_t)b0 * TC_G + rank * RC_XW + 4 * ux;
-            const long long xstep = (dir ? -1 : 1) * p.Bp * TC_G;
-            float4 xnext[NI];
-            float c_state[NI];
-            // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
-            // wait of the warp (TMA issue, spill reloads, ...) would otherwise sit behind these HBM loads.
-            auto load_x = [&]() {
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const int c = col_of(i);
-                    if (FUSE_X) continue;               // fused: xnext holds the (constant) biases of this unit's four gates
-                    xnext[i] = (c < ncols && !(p.debug & 1)) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                xp_next += xstep;
-            };
-            if (FUSE_X) {
-                const float *bz = p.bias0 + ((size_t)dir * RC_CL + rank) * 128 + q * 32 + ul;      // rows 32q + 8*gate + ul
-                const float4 b4 = make_float4(__ldg(bz), __ldg(bz + 8), __ldg(bz + 16), __ldg(bz + 24));
-#pragma unroll
-                for (int i = 0; i < NI; ++i) xnext[i] = b4;
-            }
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * RP_NBH + cbase;
-            const int out_c0 = dir * (TC_OP / 2) + (int)rank * 32 + 8 * q;      // first column of this warp's 8 units
-            const size_t state_o = ((size_t)dir * B + b0) * TC_H + rank * RC_U + u;      // + column * TC_H
-            unsigned char *gslot = p.gather + ((((size_t)cid * RC_CL + rank) * S + s) * 2) * RP_SLICE;     // [parity][4 KB]
-            // h_t -> this warp's piece [plane][col][8 units] of the fp16 hi/lo image; then one thread stores the 4 KB image
-            // to its L2 slot and multicasts it into slot `rank` of every CTA's B buffer for step t + 1
-            auto publish = [&](const float (&hv)[NI], int t) {
-                if (FUSE_X) {                       // the previous step's output store has read the tile that shares this piece
-                    if (elect_one()) tma_store_wait_read<0>();
-                    __syncwarp();
-                }
-                const uint32_t img = smem_u32(image(s)) + q * RP_PIECE + ul * 2;
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    __half hh, hl;
-                    split_f16(hv[i], hh, hl);
-                    sts_b16(img + col_of(i) * 16, hh);
-                    sts_b16(img + RP_NBH * 16 + col_of(i) * 16, hl);
-                }
-                fence_proxy_async_smem();
-                const int par = (t + 1) & 1;
-                uint64_t *bar = &h_full[(s * 2 + par) * RP_G + (rank >> 1)];
-                if (WARP_PUBLISH) {
-                    // every warp publishes its own piece: no block barrier, the exchange starts with the first warp done
-                    __syncwarp();
-                    if (tracer) RM_TRACE(TR_EPI_IMAGE, t, s);
-                    if (elect_one()) {
-                        if (EW == 1) {
-                            unsigned char *g = gslot + par * RP_SLICE + q * RP_PIECE;
-                            bulk_store_global(g, image(s) + q * RP_PIECE, RP_PIECE);
-                            tma_store_commit();
-                            tma_store_wait<0>();
-                            bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + q * RP_PIECE, g, RP_PIECE, bar, (uint16_t)0xFF);
-                        } else {
-                            // my NW columns are one run of NW*16 bytes in each plane of the piece
-                            const int o0 = q * RP_PIECE + cbase * 16, o1 = o0 + RP_PIECE / 2;
-                            unsigned char *g = gslot + par * RP_SLICE;
-                            bulk_store_global(g + o0, image(s) + o0, NW * 16);
-                            bulk_store_global(g + o1, image(s) + o1, NW * 16);
-                            tma_store_commit();
-                            tma_store_wait<0>();
-                            bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + o0, g + o0, NW * 16, bar, (uint16_t)0xFF);
-                            bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE + o1, g + o1, NW * 16, bar, (uint16_t)0xFF);
-                        }
-                    }
-                } else {
-                    named_barrier(1 + s, 128);
-                    if (tracer) RM_TRACE(TR_EPI_IMAGE, t, s);
-                    if (q == 0 && elect_one()) {
-                        unsigned char *g = gslot + par * RP_SLICE;
-                        bulk_store_global(g, image(s), RP_SLICE);
-                        tma_store_commit();
-                        tma_store_wait<0>();
-                        bulk_load_multicast(hbuf(s, par) + rank * RP_SLICE, g, RP_SLICE, bar, (uint16_t)0xFF);
-                    }
-                }
-                if (tracer) RM_TRACE(TR_EPI_COPIES, t, s);
-            };
-            {
-                float h_init[NI];
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const bool ok = unit_ok && col_of(i) < ncols;
-                    h_init[i] = ok ? __ldg(p.h0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
-                    c_state[i] = ok ? __ldg(p.c0 + state_o + (size_t)col_of(i) * TC_H) : 0.f;
-                }
-                if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster
-                publish(h_init, -1);
-            }
-            load_x();
-            const int Ti = (int)T;
-            int t_idx = dir ? Ti - 1 : 0;
-            for (int t = 0; t < Ti; ++t) {
-                mbar_wait(&d_full[s], (uint32_t)(t & 1));
-                tc_fence_after();
-                if (tracer) RM_TRACE(TR_EPI_DFULL, t, s);
-                float hv[NI];
-                {
-                    uint32_t a[2 * NI], b[2 * NI];      // a: gates i (lane ul), f (lane ul+8);  b: gates g, o;  [4k + 2*gate + c] = column cbase + 8k + 2cp + c
-                    if (EW == 1) {
-                        tmem_ld_16x256b_x4(taddr, *reinterpret_cast<uint32_t(*)[16]>(&a[0]));
-                        tmem_ld_16x256b_x4(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[16]>(&b[0]));
-                    } else {
-                        tmem_ld_16x256b_x2(taddr, *reinterpret_cast<uint32_t(*)[8]>(&a[0]));
-                        tmem_ld_16x256b_x2(taddr + (16u << 16), *reinterpret_cast<uint32_t(*)[8]>(&b[0]));
-                    }
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    if (FUSE_X) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&d_empty[s]);       // the issuer may start W_ih . x_{t+1} into this accumulator
-                    }
-                    float ei[NI], ef[NI], eg[NI], eo[NI];
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        const int r = 4 * (i >> 1) + (i & 1);
-                        // e_i, e_f, e_o may overflow to +inf (1/inf = 0 is the right limit); e_g and e_c are clamped because
-                        // (1 - e) * 0 must not become inf * 0
-                        ei[i] = ex2_approx((__uint_as_float(a[r]) + xnext[i].x) * -LOG2E);
-                        ef[i] = ex2_approx((__uint_as_float(a[r + 2]) + xnext[i].y) * -LOG2E);
-                        eg[i] = ex2_approx(fminf((__uint_as_float(b[r]) + xnext[i].z) * (-2.0f * LOG2E), EMAX));
-                        eo[i] = ex2_approx((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E);
-                    }
-                    if (tracer) RM_TRACE(TR_EPI_ACT, t, s);
-                    if (p.debug & 4) {                                  // (timing experiment: no cell math)
-#pragma unroll
-                        for (int i = 0; i < NI; ++i) hv[i] = unit_ok ? 0.25f * (ei[i] + ef[i]) * 1e-3f + 1e-3f * (eg[i] + eo[i]) : 0.0f;
-                    } else
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        const float ig = (1.0f - eg[i]) * rcp_approx((1.0f + ei[i]) * (1.0f + eg[i]));      // sigmoid(i) tanh(g)
-                        const float c = fmaf(rcp_approx(1.0f + ef[i]), c_state[i], ig);
-                        c_state[i] = c;
-                        const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EMAX));
-                        const float h = (1.0f - ec) * rcp_approx((1.0f + eo[i]) * (1.0f + ec));             // sigmoid(o) tanh(c)
-                        hv[i] = unit_ok ? h : 0.0f;
-                    }
-                    if (tracer) RM_TRACE(TR_EPI_CELL, t, s);
-                }
-                if (t + 1 < Ti) publish(hv, t);
-                // ---- off the critical path: relu(h_t) -> global memory by TMA from this warp's tile ----
-                if (elect_one()) tma_store_wait_read<0>();        // the previous step's store has read the tile
-                __syncwarp();
-                const uint32_t tile = smem_u32(out_tile);
-                if (p.out_f32) {
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) sts_b32(tile + (col_of(i) - cbase) * 32 + ul * 4, fmaxf(hv[i], 0.f));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        __half hh, hl;
-                        split_f16(fmaxf(hv[i], 0.f), hh, hl);
-                        sts_b16(tile + (col_of(i) - cbase) * 16 + ul * 2, hh);
-                        sts_b16(tile + LO_OFF + (col_of(i) - cbase) * 16 + ul * 2, hl);
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (!(p.debug & 2) && elect_one()) {
-                    const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;       // box of 32 / 16 batch columns
-                    tma_store_3d(&om[0], out_tile, out_c0, t_idx, (int)b0 + cbase);
-                    if (!p.out_f32) tma_store_3d(&om[1], out_tile + LO_OFF, out_c0, t_idx, (int)b0 + cbase);
-                    tma_store_commit();
-                }
-                t_idx += dir ? -1 : 1;
-                if (t + 1 < Ti) {
-                    load_x();
-                } else if (unit_ok) {
-#pragma unroll
-                    for (int i = 0; i < NI; ++i)
-                        if (col_of(i) < ncols) {
-                            p.hn[state_o + (size_t)col_of(i) * TC_H] = hv[i];
-                            p.cn[state_o + (size_t)col_of(i) * TC_H] = c_state[i];
-                        }
-                }
-            }
-            if (elect_one()) tma_store_wait<0>();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
-#undef RM_TRACE
-}
-
 // torch W_hh[960][240] -> planes [dir][rank][plane][128 rows][256 k' = 32 r' + u'];  row (TMEM lane) order:
 //   frag == 0: lane = 4*u + gate                          (tc_recurrent_kernel: 32x32b loads + quad shuffles)
 //   frag == 1: lane = 32*(u/8) + 8*gate + u%8             (tc_recurrent_pair_kernel: 16x256b fragment loads)
@@ -1697,156 +546,8 @@ __global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict_
     dst[c * TC_OP + k] = slot < 30 ? w[c * 2 * TC_H + (k >> 8) * TC_H + ((k >> 5) & 7) * 30 + slot] : 0.f;
 }
 
-static unsigned long long *g_trace_buf = nullptr;
-static int g_trace_steps = 0;
-
-template <int NB, int S, bool PAIR>
-static cudaLaunchConfig_t recurrent_config(int clusters, cudaStream_t st, cudaLaunchAttribute *attr)
-{
-    using C = RcCfg<NB, S, PAIR>;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * RC_CL));
-    cfg.blockDim = dim3(C::THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cfg;
-}
-
-// How many 8-CTA clusters of this geometry are co-resident on the current device (cached per geometry).
-template <int NB, int S, bool PAIR>
-static int max_resident_clusters(int *out)
-{
-    using C = RcCfg<NB, S, PAIR>;
-    static int cached = 0;
-    if (!cached) {
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_kernel<NB, S, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_kernel)");
-        cudaLaunchAttribute attr[1];
-        cudaLaunchConfig_t cfg = recurrent_config<NB, S, PAIR>(16, nullptr, attr);
-        int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_kernel<NB, S, PAIR>, &cfg);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_kernel)");
-        if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
-        cached = n;
-    }
-    *out = cached;
-    return 0;
-}
-
-template <int NB, int S, bool PAIR>
-static int launch_recurrent(const RecurParams &prm_in, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
-{
-    RecurParams prm = prm_in;
-    prm.trace = g_trace_buf;
-    prm.trace_steps = g_trace_steps;
-    int max_clusters = 0;
-    if (int rc = max_resident_clusters<NB, S, PAIR>(&max_clusters)) return rc;
-    // one cluster per (direction, group): never launch more groups than are co-resident, a second wave
-    // of clusters would double the latency of the whole launch
-    const int per = NB * S;
-    const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);
-    *cols_done = groups * per;
-    prm.xproj = xproj;
-    prm.groups = groups;
-    prm.stagger_ns = 800;
-    if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
-    cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg = recurrent_config<NB, S, PAIR>(2 * groups, st, attr);
-    ProfScope prof("tc_recurrent", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_kernel<NB, S, PAIR>, prm);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_kernel)");
-    return 0;
-}
-
-template <int S>
-static int launch_recurrent_pair(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
-{
-    using C = RpCfg<S>;
-    RecurParams prm = prm_in;
-    prm.whh = whh_frag;
-    prm.trace = g_trace_buf;
-    prm.trace_steps = g_trace_steps;
-    static int max_clusters = 0;
-    cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(C::THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_pair_kernel)");
-        cfg.gridDim = dim3(16 * RC_CL);
-        int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_pair_kernel<S>, &cfg);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_pair_kernel)");
-        if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
-        max_clusters = n;
-    }
-    const int per = RP_NB * S;
-    const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);
-    *cols_done = groups * per;
-    prm.xproj = xproj;
-    prm.groups = groups;
-    prm.stagger_ns = 1500;
-    if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
-    cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
-    ProfScope prof("tc_recurrent", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_pair_kernel<S>, prm);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_pair_kernel)");
-    return 0;
-}
-
-template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X = false>
-static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
-{
-    using C = RmCfg<S, EW, FUSE_X>;
-    RecurParams prm = prm_in;
-    prm.whh = whh_frag;
-    prm.trace = g_trace_buf;
-    prm.trace_steps = g_trace_steps;
-    if (const char *e = getenv("HSSB_TRACE_LAYER")) if (atoi(e) != prm.layer) prm.trace = nullptr;
-    static int max_clusters = 0;
-    cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(C::THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_mc_kernel)");
-        cfg.gridDim = dim3(16 * RC_CL);
-        int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, &cfg);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_mc_kernel)");
-        if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
-        max_clusters = std::min(n, 16);
-    }
-    const int per = RP_NBH * S;
-    const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);
-    *cols_done = groups * per;
-    prm.xproj = xproj;
-    prm.groups = groups;
-    prm.stagger_ns = 600;
-    if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
-    if (const char *e = getenv("HSSB_RC_DEBUG")) prm.debug = atoi(e);
-    cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
-    ProfScope prof("tc_recurrent", st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, prm);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
-    return 0;
-}
+unsigned long long *g_trace_buf = nullptr;
+int g_trace_steps = 0;
 
 // One layer's recurrence for batch columns [0, B): picks the sub-tile geometry from B.
 static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const float *h0, const float *c0, float *hn, float *cn,
@@ -1891,7 +592,7 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
     int force_nb = 0, force_s = 0, force_pair = -1;
     if (const char *e = getenv("HSSB_RC_GEOM")) sscanf(e, "%d,%d,%d", &force_nb, &force_s, &force_pair);
     int max_clusters = 0;
-    if (int rc = max_resident_clusters<32, 3, false>(&max_clusters)) return rc;
+    if (int rc = rc_dsmem_max_clusters(&max_clusters)) return rc;
     const int max_groups = max_clusters / 2;
     for (int64_t base = 0; base < B;) {
         const int64_t rem = B - base;
@@ -1904,43 +605,12 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         else if (per_group <= 32) { nb = 32; s = 1; pair = 4; }
         else if (per_group <= 64) { nb = 32; s = 2; pair = 4; }
         else { nb = 32; s = 3; pair = 3; }
-        if (fused) {
-            if (force_nb) return fail(HSSB_E_MODE, "HSSB_RC_GEOM cannot be combined with the fused projection");
-            int rcf, donef = 0;
-            if (s == 1) rcf = launch_recurrent_mc<1, true, 2, true>(prm, m->tc_whh_frag[layer], rem, &donef, xproj, st);
-            else if (s == 2) rcf = launch_recurrent_mc<2, true, 2, true>(prm, m->tc_whh_frag[layer], rem, &donef, xproj, st);
-            else rcf = launch_recurrent_mc<3, true, 1, true>(prm, m->tc_whh_frag[layer], rem, &donef, xproj, st);
-            if (rcf) return rcf;
-            base += donef;
-            continue;
-        }
-        // (the CTA-pair variants -- cta_group::2, half the all-gather volume -- are validated but measured slower on
-        //  B200: at N = 32 the paired MMA is issue-overhead bound, ~30 cycles each against ~18 for cta_group::1)
+        if (fused && force_nb) return fail(HSSB_E_MODE, "HSSB_RC_GEOM cannot be combined with the fused projection");
+        // pair: 0 = DSMEM all-gather (K5), 1 = its cta_group::2 mode or, with nb = 64, the CTA-pair kernel (K5p); 2..4 = K5m variants
         int rc, done = 0;
-        const int key = nb * 100 + s * 10 + pair;
-        switch (key) {
-        case 1610: rc = launch_recurrent<16, 1, false>(prm, rem, &done, xproj, st); break;
-        case 1620: rc = launch_recurrent<16, 2, false>(prm, rem, &done, xproj, st); break;
-        case 1630: rc = launch_recurrent<16, 3, false>(prm, rem, &done, xproj, st); break;
-        case 3220: rc = launch_recurrent<32, 2, false>(prm, rem, &done, xproj, st); break;
-        case 3230: rc = launch_recurrent<32, 3, false>(prm, rem, &done, xproj, st); break;
-        case 3211: rc = launch_recurrent<32, 1, true>(prm, rem, &done, xproj, st); break;
-        case 3221: rc = launch_recurrent<32, 2, true>(prm, rem, &done, xproj, st); break;
-        case 3231: rc = launch_recurrent<32, 3, true>(prm, rem, &done, xproj, st); break;
-        case 3241: rc = launch_recurrent<32, 4, true>(prm, rem, &done, xproj, st); break;
-        case 3212: rc = launch_recurrent_mc<1, false, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3222: rc = launch_recurrent_mc<2, false, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3232: rc = launch_recurrent_mc<3, false, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3213: rc = launch_recurrent_mc<1, true, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3223: rc = launch_recurrent_mc<2, true, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3233: rc = launch_recurrent_mc<3, true, 1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3214: rc = launch_recurrent_mc<1, true, 2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3224: rc = launch_recurrent_mc<2, true, 2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 3234: rc = launch_recurrent_mc<3, true, 2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 6411: rc = launch_recurrent_pair<1>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        case 6421: rc = launch_recurrent_pair<2>(prm, m->tc_whh_frag[layer], rem, &done, xproj, st); break;
-        default: return fail(HSSB_E_MODE, "HSSB_RC_GEOM=%d,%d,%d unsupported", nb, s, pair);
-        }
+        if (nb == 32 && pair >= 2) rc = rc_mc_launch(s, pair, fused, prm, m->tc_whh_frag[layer], rem, &done, xproj, st);
+        else if (nb == 64) rc = rc_pair_launch(s, prm, m->tc_whh_frag[layer], rem, &done, xproj, st);
+        else rc = rc_dsmem_launch(nb, s, pair, prm, rem, &done, xproj, st);
         if (rc) return rc;
         base += done;
     }
@@ -2018,7 +688,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
 extern "C" int hssb_debug_max_clusters(void)
 {
     int n = 0;
-    if (hssb::max_resident_clusters<32, 3, false>(&n)) return -1;
+    if (hssb::rc_dsmem_max_clusters(&n)) return -1;
     return n;
 }
 
@@ -2060,3 +730,4 @@ extern "C" int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B,
     HSSB_LAUNCH_OK("unpermute_xproj_kernel");
     return 0;
 }
+
