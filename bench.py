@@ -13,6 +13,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -250,35 +251,58 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     _lib.prof_read()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    gc.collect()
+    gc.disable()
     for a, b in ev:
         flush.zero_()
         a.record()
         step(x_dev)
         b.record()
     barrier()
+    gc.enable()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     prof = _lib.prof_read()
     _lib.prof_enable(False)
     clocks = sampler.stop()
 
     # ---- end to end: pinned host input -> H2D -> path -> labels + counters back on the host ----
+    # (the input lands in a preallocated device buffer and the Python GC is off inside the timed region: a torch allocator miss
+    #  or a gen-2 collection costs 30-90 ms of host time, which used to hit one of the five steps every few runs)
     labels_host = torch.empty((B, N_SAMPLES), dtype=torch.int32).pin_memory()
-    for _ in range(2):
-        step(x_host.to(dev, non_blocking=True))
+    x_in = torch.empty_like(x_dev)
+
+    def e2e_step():
+        x_in.copy_(x_host, non_blocking=True)
+        labels, cm = step(x_in)
+        labels_host.copy_(labels, non_blocking=True)
+        return cm.cpu()
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
     barrier()
+    gc.collect()
+    gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    wall = [time.perf_counter()]
+    debug = bool(os.environ.get("HSSB_BENCH_DEBUG"))
+    if debug:
+        _lib.prof_enable(True)
+        _lib.prof_read()
+    wall, per_step = [time.perf_counter()], []
     for _ in range(args.steps):
-        labels, cm = step(x_host.to(dev, non_blocking=True))
-        labels_host.copy_(labels, non_blocking=True)
-        cm_host = cm.cpu()
+        cm_host = e2e_step()
         wall.append(time.perf_counter())
+        if debug:
+            per_step.append({k: round(v[1], 2) for k, v in _lib.prof_read().items() if v[1] > 0.05})
     e1.record()
     barrier()
+    gc.enable()
     ms_e2e = e0.elapsed_time(e1)
-    if os.environ.get("HSSB_BENCH_DEBUG"):
+    if debug:
+        _lib.prof_enable(False)
         print("e2e wall per step (ms):", [round(1e3 * (b - a), 3) for a, b in zip(wall, wall[1:])], "events total", ms_e2e, file=sys.stderr)
+        for i, d in enumerate(per_step):
+            print("  e2e step", i, d, file=sys.stderr)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
