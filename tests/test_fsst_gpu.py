@@ -229,3 +229,21 @@ def test_config5_long_windows_at_2khz(lib):
     for b in range(B):
         ref = fo.fsst_features(x[b].numpy(), fs, w, stack=True, truncate_freq=(50, 400))
         assert np.abs(out[b] - ref).max() < 5e-4
+
+
+def test_recording_to_frames_equals_the_dataset_loop(lib):
+    """hss.utils.ingest.recording_to_frames == frame_signal(x, y - 1) + per-frame FSST of reference heart_sounds.py:155-169."""
+    from hss.transforms import FSST
+    from hss.utils import frame_signal, recording_to_frames
+    from workloads import synthetic_targets
+
+    x = torch.from_numpy(fo.synth_pcg_batch(1, 6500, seed=9)[0])
+    y = torch.from_numpy(synthetic_targets(1, 6500)[0]) + 1
+    f = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True)
+    feats, labels = recording_to_frames(x, y, f)
+    frames, lab = frame_signal(x, y - 1, 1000, 2000)
+    assert feats.shape == (len(frames), 2000, 44) and labels.shape == (len(frames), 2000) and feats.is_cuda
+    for i, (fr, lb) in enumerate(zip(frames, lab)):
+        assert torch.equal(feats[i].cpu(), f(fr)) and torch.equal(labels[i].cpu(), lb[:, 0])
+    short = recording_to_frames(x[:1500], y[:1500], f)
+    assert short[0].shape[0] == 0 and short[1].shape[0] == 0

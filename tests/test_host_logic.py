@@ -120,3 +120,25 @@ def test_frame_signal_matches_reference_contract():
             assert f.shape == (n, 1) and torch.equal(f[:, 0], x[i * stride:i * stride + n]) and torch.equal(l[:, 0], y[i * stride:i * stride + n])
         fb = frame_batch(x, stride, n)
         assert fb.shape == (L, n) and torch.equal(fb, torch.stack([f[:, 0] for f in frames]))
+
+
+def test_load_recording_csv_matches_the_reference_reader(tmp_path):
+    """hss.utils.ingest.load_recording_csv == pd.read_csv(skiprows=1, names=[Signals, Labels]) (reference heart_sounds.py:193-197)."""
+    import numpy as np
+    import pandas as pd
+    import torch
+    from hss.utils.ingest import load_recording_csv
+    from workloads import synth_pcg, synthetic_targets
+
+    x = synth_pcg(5000, seed=3).astype(np.float64)
+    y = synthetic_targets(1, 5000)[0] + 1                       # file labels are 1..4
+    path = tmp_path / "0001.csv"
+    with open(path, "w") as f:
+        f.write("Signals,Labels\n")
+        for a, b in zip(x, y):
+            f.write(f"{float(a)!r},{int(b)}\n")
+    xs, ys = load_recording_csv(str(path))
+    df = pd.read_csv(path, skiprows=1, names=["Signals", "Labels"])
+    assert torch.equal(xs, torch.tensor(df.loc[:, "Signals"].to_numpy(), dtype=torch.float32))
+    assert torch.equal(ys, torch.tensor(df.loc[:, "Labels"].to_numpy(), dtype=torch.int64))
+    assert xs.shape == (5000,) and ys.dtype == torch.int64 and int(ys.min()) == 1 and int(ys.max()) == 4
