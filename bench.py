@@ -37,7 +37,7 @@ WINDOWS_PER_GPU = 512       # BASELINE config 4 shard
 # useful FLOPs (1x, the fp32 contraction) per PCG sample of every launch of the kernel in one step
 FLOP_PER_SAMPLE = {"tc_inproj_l0": 2 * 44 * 1920.0, "tc_inproj_l1": 2 * 480 * 1920.0, "simt_inproj": 2 * (44 + 480) * 1920.0,
                    "tc_recurrent": 2 * 2 * 240 * 1920.0, "simt_recurrent": 2 * 2 * 240 * 1920.0}
-BYTES_PER_SAMPLE = {"stft_hop1": 4 + 2 * K_BINS * 8, "if_reassign": 2 * K_BINS * 8 + KT * 8, "normalise": 16 * KT * 2}
+BYTES_PER_SAMPLE = {"stft_hop1": 4 + 2 * K_BINS * 8, "if_reassign": 2 * K_BINS * 8 + KT * 8, "normalise": 16 * KT}
 
 
 def workload_name(windows: int) -> str:

@@ -9,6 +9,7 @@
 #include "hssb_common.cuh"
 #include "fsst_phases.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace hssb {
 
@@ -74,10 +75,7 @@ stft_hop1_kernel(const float *__restrict__ x, long long N, const float *__restri
 // K2
 // ------------------------------------------------------------------------------------------------
 constexpr int RT = 128;        // time columns (= threads) per CTA of the reassignment kernel
-#ifndef HSSB_RU
-#define HSSB_RU 8
-#endif
-constexpr int RU = HSSB_RU;    // bins loaded ahead per thread (memory-level parallelism)
+// RU = bins loaded ahead per thread (memory-level parallelism); 8 by default, HSSB_RU=5|13 selects the other instantiations
 
 __device__ __forceinline__ Moments shfl_xor_moments(Moments m, int lane_mask)
 {
@@ -88,6 +86,7 @@ __device__ __forceinline__ Moments shfl_xor_moments(Moments m, int lane_mask)
     return o;
 }
 
+template <int RU>
 __global__ void __launch_bounds__(RT)
 if_reassign_kernel(const float2 *__restrict__ Sg, const float2 *__restrict__ Sdg, long long N, int nfft,
                    float bins_per_hz, int k_lo, int k_hi, float2 *__restrict__ T,
@@ -214,14 +213,16 @@ normalise_kernel(const float2 *__restrict__ T, const float *__restrict__ final_s
         mr = final_stats[b * 4 + 0]; sr = final_stats[b * 4 + 1];
         mi = final_stats[b * 4 + 2]; si = final_stats[b * 4 + 3];
     }
+    // (v - mean) * (1 / std): one reciprocal per CTA instead of an IEEE division per element (<= 1 ulp from the quotient)
+    const float ir = 1.0f / sr, ii = 1.0f / si;
     const float2 *tin = T + (size_t)b * Kt * N + t0;
     for (int idx = tid; idx < Kt * FT; idx += 256) {
         const int r = idx / FT, c = idx % FT;
         if (c < ncols) {
             const float2 v = __ldcs(tin + (size_t)r * N + c);
             if (mode == HSSB_MODE_STACK) {
-                tile[c * WS + r] = (v.x - mr) / sr;          // IEEE sub then div, as the reference's two torch ops
-                tile[c * WS + Kt + r] = (v.y - mi) / si;
+                tile[c * WS + r] = (v.x - mr) * ir;
+                tile[c * WS + Kt + r] = (v.y - mi) * ii;
             } else {
                 tile[c * WS + r] = hypotf(v.x, v.y);
             }
@@ -230,7 +231,22 @@ normalise_kernel(const float2 *__restrict__ T, const float *__restrict__ final_s
     __syncthreads();
     float *o = out + ((size_t)b * N + t0) * W;
     const int total = ncols * W;
-    for (int i = tid; i < total; i += 256) __stcs(o + i, tile[(i / W) * WS + (i % W)]);
+    if (((((size_t)b * N + t0) * W) & 3) == 0) {          // 16-byte stores over the contiguous [ncols][W] block
+        for (int i4 = tid * 4; i4 < total; i4 += 256 * 4) {
+            if (i4 + 3 < total) {
+                float4 v;
+                v.x = tile[(i4 / W) * WS + (i4 % W)];
+                v.y = tile[((i4 + 1) / W) * WS + ((i4 + 1) % W)];
+                v.z = tile[((i4 + 2) / W) * WS + ((i4 + 2) % W)];
+                v.w = tile[((i4 + 3) / W) * WS + ((i4 + 3) % W)];
+                __stcs(reinterpret_cast<float4 *>(o + i4), v);
+            } else {
+                for (int i = i4; i < total; ++i) __stcs(o + i, tile[(i / W) * WS + (i % W)]);
+            }
+        }
+    } else {
+        for (int i = tid; i < total; i += 256) __stcs(o + i, tile[(i / W) * WS + (i % W)]);
+    }
 }
 
 }  // namespace hssb
@@ -294,12 +310,23 @@ extern "C" int hssb_fsst_reassign(const hssb_c32 *Sg, const hssb_c32 *Sdg, int64
     const int Kout = k_hi - k_lo + 1;
     const size_t smem = sizeof(float2) * (size_t)Kout * RT;
     static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(if_reassign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * 129 * RT)); });
+    std::call_once(once, [] {
+        const int mx = (int)(sizeof(float2) * 129 * RT);
+        cudaFuncSetAttribute(if_reassign_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(if_reassign_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(if_reassign_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    });
     dim3 grid((unsigned)ntiles_reassign(N), (unsigned)B);
     const float bins_per_hz = (float)((double)nwin / (double)fs);
+    const char *ru_env = getenv("HSSB_RU");
+    const int ru = ru_env ? atoi(ru_env) : 8;
     ProfScope prof("if_reassign", as_stream(stream));
-    if_reassign_kernel<<<grid, RT, smem, as_stream(stream)>>>((const float2 *)Sg, (const float2 *)Sdg, N, nwin,
-                                                               bins_per_hz, k_lo, k_hi, (float2 *)T, stats);
+    if (ru == 5)
+        if_reassign_kernel<5><<<grid, RT, smem, as_stream(stream)>>>((const float2 *)Sg, (const float2 *)Sdg, N, nwin, bins_per_hz, k_lo, k_hi, (float2 *)T, stats);
+    else if (ru == 13)
+        if_reassign_kernel<13><<<grid, RT, smem, as_stream(stream)>>>((const float2 *)Sg, (const float2 *)Sdg, N, nwin, bins_per_hz, k_lo, k_hi, (float2 *)T, stats);
+    else
+        if_reassign_kernel<8><<<grid, RT, smem, as_stream(stream)>>>((const float2 *)Sg, (const float2 *)Sdg, N, nwin, bins_per_hz, k_lo, k_hi, (float2 *)T, stats);
     HSSB_LAUNCH_OK("if_reassign_kernel");
     return 0;
 }
