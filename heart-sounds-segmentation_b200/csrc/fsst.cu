@@ -193,7 +193,7 @@ stats_finalize_kernel(const double *__restrict__ partials, int ntiles, float *__
     }
 }
 
-constexpr int FT = 64;   // time columns per CTA of the normalise kernel
+constexpr int FT = 128;  // time columns per CTA of the normalise kernel (64-column CTAs were launch / latency bound)
 
 __global__ void __launch_bounds__(256)
 normalise_kernel(const float2 *__restrict__ T, const float *__restrict__ final_stats, long long N, int Kt,
@@ -216,15 +216,25 @@ normalise_kernel(const float2 *__restrict__ T, const float *__restrict__ final_s
     // (v - mean) * (1 / std): one reciprocal per CTA instead of an IEEE division per element (<= 1 ulp from the quotient)
     const float ir = 1.0f / sr, ii = 1.0f / si;
     const float2 *tin = T + (size_t)b * Kt * N + t0;
-    for (int idx = tid; idx < Kt * FT; idx += 256) {
-        const int r = idx / FT, c = idx % FT;
-        if (c < ncols) {
-            const float2 v = __ldcs(tin + (size_t)r * N + c);
-            if (mode == HSSB_MODE_STACK) {
-                tile[c * WS + r] = (v.x - mr) * ir;
-                tile[c * WS + Kt + r] = (v.y - mi) * ii;
-            } else {
-                tile[c * WS + r] = hypotf(v.x, v.y);
+    // 8 loads in flight per thread (one load per loop trip left the kernel latency bound at half the HBM rate)
+    constexpr int MLP = 8;
+    for (int base = tid; base < Kt * FT; base += 256 * MLP) {
+        float2 v[MLP];
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            const int idx = base + 256 * u, r = idx / FT, c = idx % FT;
+            if (idx < Kt * FT && c < ncols) v[u] = __ldcs(tin + (size_t)r * N + c);
+        }
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            const int idx = base + 256 * u, r = idx / FT, c = idx % FT;
+            if (idx < Kt * FT && c < ncols) {
+                if (mode == HSSB_MODE_STACK) {
+                    tile[c * WS + r] = (v[u].x - mr) * ir;
+                    tile[c * WS + Kt + r] = (v[u].y - mi) * ii;
+                } else {
+                    tile[c * WS + r] = hypotf(v[u].x, v[u].y);
+                }
             }
         }
     }
