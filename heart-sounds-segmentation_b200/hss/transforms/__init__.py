@@ -1,3 +1,4 @@
+from .resample import Resample
 from .synchrosqueeze import FSST
 
-__all__ = ["FSST"]
+__all__ = ["Resample", "FSST"]

@@ -142,3 +142,20 @@ def test_load_recording_csv_matches_the_reference_reader(tmp_path):
     assert torch.equal(xs, torch.tensor(df.loc[:, "Signals"].to_numpy(), dtype=torch.float32))
     assert torch.equal(ys, torch.tensor(df.loc[:, "Labels"].to_numpy(), dtype=torch.int64))
     assert xs.shape == (5000,) and ys.dtype == torch.int64 and int(ys.min()) == 1 and int(ys.max()) == 4
+
+
+def test_resample_matches_scipy_fourier_method():
+    """hss.transforms.Resample == scipy.signal.resample, the call behind reference hss/transforms/resample.py:21."""
+    import numpy as np
+    import scipy.signal
+    import torch
+    from hss.transforms import Resample
+
+    rng = np.random.default_rng(4)
+    for n, num in ((2000, 1000), (2000, 4000), (1001, 500), (1000, 1501), (35000, 17500), (64, 64), (7, 12)):
+        x = rng.standard_normal(n)
+        ref = scipy.signal.resample(x, num)
+        got = Resample(num)(torch.from_numpy(x), dtype=torch.float64).numpy()
+        assert got.shape == (num,) and np.abs(got - ref).max() < 1e-10, (n, num, np.abs(got - ref).max())
+    y = (np.arange(2000) % 4 + 1).astype(np.float64)          # label track, as heart_sounds.py:206 resamples it
+    assert Resample(1000)(torch.from_numpy(y)).dtype == torch.float32
