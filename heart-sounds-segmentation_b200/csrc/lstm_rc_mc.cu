@@ -5,23 +5,34 @@
 namespace hssb {
 
 // ------------------------------------------------------------------------------------------------
-// K5m: recurrence with the all-gather through L2 (bulk store + TMA multicast) -- the large-batch kernel.
+// K5m: the T sequential steps of one BiLSTM layer.  One 8-CTA cluster per (direction, S <= 3 sub-tiles of 32 batch columns).
 //
-// Measured on B200 (scripts/microbench/ub_cluster.cu): a CTA can push ~17 B/cycle into DSMEM, so the 8-way
-// all-gather of the kernels above costs 5 750 cycles per step at 96 columns per cluster -- twice the tensor time.
-// The same exchange through L2 -- every CTA bulk-stores its 4 KB image once and then issues ONE multicast bulk
-// load that delivers it to all 8 CTAs of the cluster -- moves 50-60 B/cycle into every SM and takes ~1 100
-// cycles end to end, with two bulk operations per sub-tile and step instead of eight.
-//   * one CTA per 30 units as before (cta_group::1, M = 128, N = 32, W_hh hi/lo resident in TMEM), S = 1..3
-//     independent sub-tiles of 32 batch columns interleaved per cluster;
-//   * TMEM lanes in fragment order, xproj as 16-byte loads issued at the END of a step, outputs by TMA store:
-//     see the pair kernel above (same epilogue);
-//   * every B buffer has one mbarrier per pair of source ranks; the MMA issuer starts on a pair's K range as
-//     soon as its two slices landed (own pair first: its arrival proves that the four epilogue warps have
-//     read the previous accumulator);
-//   * the image is single-buffered: the issuing thread waits for its bulk store (cp.async.bulk.wait_group)
-//     before it issues the multicast load, and nobody rewrites the image before the next accumulator, which
-//     depends on that load; the L2 scratch slot is double-buffered by step parity.
+// Orientation: gates are the MMA M dimension and stay put, the batch is N:
+//     G^T[gate row (128 TMEM lanes), b (32 cols)] = W_hh,slice . h_{t-1}^T  (+ W_ih,slice . x_t^T when fused, else + xproj^T)
+// CTA rank r owns units 30r..30r+29.  Its W_hh slice (fp16 hi and lo planes, K padded 240 -> 8 x 32) is loaded ONCE into TMEM
+// columns [0, 256) and is the A operand of every MMA (tcgen05.mma with A in TMEM): weights never move.  h_{t-1}^T lives in
+// shared memory as the K-major B operand [source rank 8][k-chunk 4][plane 2][column 32][8 units] (no swizzle: LBO = 1 KB
+// between k-chunks, SBO = 128 B between 8-column groups), double-buffered by step parity.
+//
+// All-gather through L2.  Measured on B200 (scripts/microbench/ub_cluster.cu): a CTA pushes ~17 B/cycle into DSMEM, so an
+// 8-way DSMEM all-gather of 96 columns costs 5 750 cycles per step -- twice the tensor time (that is lstm_rc_dsmem.cu).  Here
+// every epilogue warp bulk-stores its 1 KB piece of h_t (fp16 hi / lo image) to an L2-resident scratch slot, waits for the
+// store (cp.async.bulk.wait_group) and issues ONE multicast bulk load that lands the piece in slot `rank` of all 8 CTAs' B
+// buffers and completes bytes on their mbarriers: 50-60 B/cycle into every SM, ~1 100-1 600 cycles end to end.
+//   * every B buffer has one mbarrier per pair of source ranks; the MMA issuer starts on a pair's K range as soon as its two
+//     slices landed (own pair first: its arrival proves that this CTA's epilogue warps have read the previous accumulator);
+//   * the image is single-buffered (the publishing thread has waited for its bulk store, and nobody rewrites the image before
+//     the next accumulator, which depends on that publish); the L2 scratch slot is double-buffered by step parity.
+// Epilogue (4 warps per sub-tile, or 8 with EW = 2: one or two per TMEM lane quadrant).  TMEM lanes are in "fragment order"
+// (lane = 32*(u/8) + 8*gate + u%8), so two tcgen05.ld.16x256b hand thread (ul = lane/4, cp = lane%4) the four gates of unit
+// 8q+ul for the columns 8k + 2cp + {0,1}: no shuffles, and the matching xproj values are coalesced 16-byte loads, issued as
+// the LAST thing of a step (an LDG in flight stalls every later long-scoreboard wait of the warp).  Activations with 8
+// instead of 10 MUFU ops per cell: i*g = (1 - e_g) / ((1 + e_i)(1 + e_g)) with e_x = exp(-x) (exp(-2x) for g and c).
+// relu(h_t) leaves through a per-warp shared-memory tile and one TMA tensor store per plane (slot-layout [B][T][512]
+// outputs; ragged batches are clipped by the TMA unit).
+// FUSE_X (layer 1): W_ih's slice sits in TMEM too; x_t (fp16 hi / lo planes, tile-major: one contiguous 3 KB run per step and
+// sub-tile) is bulk-loaded one step ahead and W_ih . x_t is issued into the accumulator as soon as the epilogue has read the
+// previous one (d_empty), i.e. while h_{t-1} is still in flight; the relu tile then reuses the warp's image piece.
 // ------------------------------------------------------------------------------------------------
 constexpr int RX_CHUNKS = 2 * RX_KSTEPS;           // 8-feature k-chunks
 constexpr int RX_PLANE = RX_CHUNKS * RP_NBH * 16;  // [chunk][32 cols][8 features] fp16 = 3 KB

@@ -554,7 +554,7 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
                         __half *out_hi, __half *out_lo, float *out_f32, unsigned char *gather, int64_t B, int64_t T, cudaStream_t st,
                         const __half *x_hi = nullptr, const __half *x_lo = nullptr)
 {
-    // x_hi / x_lo != nullptr: layer 1 with the input projection fused into the recurrence (chunk-major x planes, no xproj)
+    // x_hi / x_lo != nullptr: layer 1 with the input projection fused into the recurrence (tile-major x planes, no xproj)
     const bool fused = x_hi != nullptr;
     RecurParams prm = {};
     prm.gather = gather;
