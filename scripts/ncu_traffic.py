@@ -25,8 +25,8 @@ for r in rows[2:]:
     key = next((v for k, v in names if k in kname), None)
     if key is None:
         continue
-    if key == "tc_inproj":
-        key = f"tc_inproj_l{n_inproj}"
+    if key == "tc_inproj":          # <3, 8> = the (optional, HSSB_FUSE_X=0) layer-1 projection, <5, 4> / <4, x> = layer 2's
+        key = "tc_inproj_l0" if "<3, 8>" in kname or "(int)3, (int)8" in kname else "tc_inproj_l1"
         n_inproj += 1
     b = float(r[idx["dram__bytes_read.sum"]]) * mult[units[idx["dram__bytes_read.sum"]]] + \
         float(r[idx["dram__bytes_write.sum"]]) * mult[units[idx["dram__bytes_write.sum"]]]
