@@ -205,3 +205,29 @@ def test_k4_tcgen05_inproj_matches_simt(lib, B, T):
         err_simt = (outs[1][d].double() - truth).abs().max().item()
         assert not torch.isnan(outs[0][d]).any()
         assert err_simt < 5e-6 and err_tc < 5e-6, (err_tc, err_simt)
+
+
+def test_config5_shard_full_size_long_sequences(lib):
+    """BASELINE config 5's per-GPU shard at FULL size: 64 windows x 120 000 samples @ 2 kHz (60 s), band (50, 400) Hz -> 44
+    features, T = 120 000 dependent LSTM steps (64-bit indexing everywhere: xproj alone is 60 GB).  FSST features of two
+    windows are checked against the fp64 oracle; the labels of four windows (first / last column of both batch groups)
+    against torch-CPU on the same rows -- batch rows are independent (segmenter.py:38-41), so that is the reference's result."""
+    from hss.transforms import FSST
+
+    fs, N, B = 2000.0, 120_000, 64
+    x = torch.from_numpy(fo.synth_pcg_batch(B, N, fs=fs, seed=5))
+    w = fo.reference_window()
+    feats = FSST(fs, window=w, truncate_freq=(50, 400), stack=True).batch(x.cuda())
+    assert feats.shape == (B, N, 44) and torch.isfinite(feats).all()
+    for b in (0, B - 1):
+        ref = fo.fsst_features(x[b].numpy(), fs, w, stack=True, truncate_freq=(50, 400))
+        assert np.abs(feats[b].cpu().numpy() - ref).max() < 5e-4
+    m = make_model(5, 44, B, 240)
+    logp, labels = m.forward_with_labels(feats)
+    assert logp.shape == (B, N, 4) and torch.isfinite(logp).all()
+    assert (logp.exp().sum(-1) - 1).abs().max().item() < 1e-5
+    rows = [0, 31, 32, 63]
+    params, h0, c0 = lo.reference_params(5, 44, B, 240)
+    ref = lo.forward_torch(params, h0[:, rows].contiguous(), c0[:, rows].contiguous(), feats[rows].cpu())
+    rep = check(logp[rows].cpu(), labels[rows].cpu(), ref)
+    print("config 5 shard (4 of 64 windows checked):", rep)
