@@ -90,6 +90,48 @@ __global__ void confusion_kernel(const int32_t *__restrict__ pred, const int64_t
     if (threadIdx.x < 16 && local[threadIdx.x]) atomicAdd(&cm[threadIdx.x], (unsigned long long)local[threadIdx.x]);
 }
 
+// One-vs-rest score histograms for the binned multiclass AUROC (reference main.py:48,60: torchmetrics AUROC on the
+// class probabilities).  hist[c][target == c][bin(exp(logp[c]))] += 1 -- plain counters, so shards and ranks add up
+// (all-reduce) exactly like the confusion counts.  Block-private shared histograms, one warp-aggregated shared atomic
+// per distinct bin of a warp (trained models put most scores into the two end bins), one global atomic per non-empty bin.
+__global__ void __launch_bounds__(512)
+auroc_hist_kernel(const float4 *__restrict__ logp, const int64_t *__restrict__ target, long long n, int nbins,
+                  unsigned long long *__restrict__ hist)
+{
+    extern __shared__ unsigned int sh[];   // [4][2][nbins]
+    const int words = 8 * nbins;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const float scale = (float)nbins;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rounds = (n + stride - 1) / stride;   // whole warps stay converged for __match_any_sync
+    for (long long r = 0; r < rounds; ++r) {
+        const long long i = first + r * stride;
+        const bool live = i < n;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        long long t = -1;
+        if (live) {
+            v = __ldcs(&logp[i]);
+            t = target[i];
+        }
+        const float lp[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float p = expf(lp[c]);
+            int b = (int)(p * scale);
+            b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);
+            if (!(p == p)) b = 0;              // NaN score: lowest bin (never ranks above anything)
+            const int key = live && t >= 0 && t < 4 ? (c * 2 + (t == c ? 1 : 0)) * nbins + b : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[key], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < words; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
 }  // namespace hssb
 
 extern "C" int hssb_version(void) { return HSSB_VERSION; }
@@ -142,5 +184,25 @@ extern "C" int hssb_confusion(const int32_t *pred, const int64_t *target, int64_
     ProfScope prof("confusion", as_stream(stream));
     confusion_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pred, target, n, reinterpret_cast<unsigned long long *>(cm16));
     HSSB_LAUNCH_OK("confusion_kernel");
+    return 0;
+}
+
+extern "C" int hssb_auroc_hist(const float *logp, const int64_t *target, int64_t n, int nbins, int64_t *hist, void *stream)
+{
+    using namespace hssb;
+    if (!logp || !target || !hist) return fail(HSSB_E_NULL, "hssb_auroc_hist: null pointer");
+    if (n < 0) return fail(HSSB_E_SHAPE, "hssb_auroc_hist: n=%lld", (long long)n);
+    if (nbins < 2 || nbins > 4096) return fail(HSSB_E_SHAPE, "hssb_auroc_hist: nbins=%d outside [2, 4096]", nbins);
+    if ((reinterpret_cast<uintptr_t>(logp) & 15) != 0) return fail(HSSB_E_SHAPE, "hssb_auroc_hist: logp must be 16-byte aligned");
+    if (n == 0) return 0;
+    if (int rc = require_sm100()) return rc;
+    const size_t smem = (size_t)8 * nbins * sizeof(unsigned int);
+    HSSB_CUDA_OK(cudaFuncSetAttribute(auroc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 4));
+    long long blocks = (n + 511) / 512;
+    if (blocks > 148) blocks = 148;          // one 128 KB histogram per SM at nbins = 4096
+    ProfScope prof("auroc_hist", as_stream(stream));
+    auroc_hist_kernel<<<(int)blocks, 512, smem, as_stream(stream)>>>(reinterpret_cast<const float4 *>(logp), target, n, nbins,
+                                                                      reinterpret_cast<unsigned long long *>(hist));
+    HSSB_LAUNCH_OK("auroc_hist_kernel");
     return 0;
 }

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "hssb_debug_trace": (c_int, [c_void_p, c_int]),
     "hssb_debug_max_clusters": (c_int, []),
     "hssb_confusion": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "hssb_auroc_hist": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "hssb_prof_enable": (c_int, [c_int]),
     "hssb_prof_read": (c_int, [c_char_p, c_size_t]),
 }

@@ -63,3 +63,41 @@ def metrics_from_counts(cm: torch.Tensor) -> dict:
         "accuracy": float(recall.mean()), "recall": float(recall.mean()), "precision": float(precision.mean()),
         "f1": float(f1.mean()), "micro_accuracy": float(tp.sum() / cm.sum().clamp(min=1)),
     }
+
+
+def score_histograms(logp: torch.Tensor, target: torch.Tensor, nbins: int = 4096) -> torch.Tensor:
+    """One-vs-rest score histograms ``hist[class, is_positive, bin]`` (int64) of this rank's log-probabilities.
+
+    State of the binned multiclass AUROC (reference main.py:48,60); plain counters, so
+    ``allreduce_counts`` merges ranks exactly like the confusion counts.  CUDA kernel ``hssb_auroc_hist``.
+    """
+    if not logp.is_cuda:
+        raise RuntimeError("score_histograms runs on the GPU (no CPU fallback)")
+    if logp.shape[-1] != 4:
+        raise ValueError(f"expected [..., 4] log-probabilities, got {tuple(logp.shape)}")
+    logp = logp.to(torch.float32).contiguous().reshape(-1, 4)
+    target = target.to(device=logp.device, dtype=torch.int64).contiguous().reshape(-1)
+    if logp.shape[0] != target.numel():
+        raise ValueError("logp / target size mismatch")
+    hist = torch.zeros(4, 2, nbins, dtype=torch.int64, device=logp.device)
+    with torch.cuda.device(logp.device):
+        rc = _lib.lib().hssb_auroc_hist(logp.data_ptr(), target.data_ptr(), target.numel(), nbins, hist.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "hssb_auroc_hist")
+    return hist
+
+
+def auroc_from_histograms(hist: torch.Tensor) -> dict:
+    """Per-class and macro one-vs-rest AUROC from (all-reduced) score histograms.
+
+    Area under the ROC curve whose thresholds are the bin edges, trapezoidal rule (scores sharing a bin
+    count as ties) -- the Mann-Whitney form ``sum_b pos[b] * (neg_below[b] + neg[b] / 2) / (P * N)``.
+    A class without positives or without negatives scores 0 (torchmetrics' convention for an undefined
+    curve); macro = mean over the four classes (reference main.py:60).
+    """
+    h = hist.to(torch.float64).cpu()
+    neg, pos = h[:, 0], h[:, 1]
+    below = torch.cumsum(neg, dim=1) - neg
+    num = (pos * (below + 0.5 * neg)).sum(dim=1)
+    den = pos.sum(dim=1) * neg.sum(dim=1)
+    per_class = torch.where(den > 0, num / den.clamp(min=1), torch.zeros_like(num))
+    return {"auroc_per_class": per_class, "auroc": float(per_class.mean())}

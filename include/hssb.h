@@ -9,6 +9,7 @@
  *             streaming mean / M2 recurrences              hss/moments/__init__.py:16,35-36
  *   BiLSTM    HeartSoundSegmenter.forward                  hss/model/segmenter.py:70-87
  *   metrics   multiclass confusion counts                  main.py:36-62 (torchmetrics)
+ *             one-vs-rest score histograms (AUROC)         main.py:48,60
  *
  * Conventions
  *   - plain C: pointers, sizes, no torch / C++ types.
@@ -142,6 +143,13 @@ int hssb_debug_max_clusters(void);
  * cm16 [4,4] int64 device, cm[target][pred] += 1 (accumulates; caller zeroes).
  * ------------------------------------------------------------------------------------------ */
 int hssb_confusion(const int32_t *pred, const int64_t *target, int64_t n, int64_t *cm16, void *stream);
+
+/* One-vs-rest score histograms for the binned AUROC of main.py:48,60 (torchmetrics multiclass AUROC on the class
+ * probabilities).  logp [n,4] f32 device (log-probabilities, 16-byte aligned), target [n] int64 device (rows with a
+ * target outside 0..3 are skipped); hist [4][2][nbins] int64 device,
+ *   hist[c][target == c][min(nbins-1, floor(exp(logp[c]) * nbins))] += 1   (accumulates; caller zeroes; 2 <= nbins <= 4096).
+ * Counters add across shards / ranks, so the job-wide AUROC comes from the all-reduced histogram. */
+int hssb_auroc_hist(const float *logp, const int64_t *target, int64_t n, int nbins, int64_t *hist, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-launch timing for bench.py: when enabled, every kernel launch is bracketed by CUDA events on

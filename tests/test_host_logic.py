@@ -159,3 +159,50 @@ def test_resample_matches_scipy_fourier_method():
         assert got.shape == (num,) and np.abs(got - ref).max() < 1e-10, (n, num, np.abs(got - ref).max())
     y = (np.arange(2000) % 4 + 1).astype(np.float64)          # label track, as heart_sounds.py:206 resamples it
     assert Resample(1000)(torch.from_numpy(y)).dtype == torch.float32
+
+
+def _scored_labels(n, seed, sharp=2.0):
+    g = torch.Generator().manual_seed(seed)
+    target = torch.randint(0, 4, (n,), generator=g)
+    logits = torch.randn(n, 4, generator=g) + sharp * torch.nn.functional.one_hot(target, 4) * (torch.rand(n, 1, generator=g) > 0.3)
+    return torch.log_softmax(logits, dim=1), target
+
+
+def test_auroc_oracle_matches_sklearn():
+    """oracle/metrics_oracle.auroc_exact (main.py:48,60 definition) against scikit-learn's independent implementation."""
+    from sklearn.metrics import roc_auc_score
+
+    from oracle import metrics_oracle as mo
+
+    logp, target = _scored_labels(5000, 3)
+    ours = mo.auroc_exact(logp.numpy(), target.numpy())
+    p = np.exp(logp.numpy())
+    for c in range(4):
+        assert abs(ours[c] - roc_auc_score((target.numpy() == c).astype(int), p[:, c])) < 1e-12
+    q = mo.auroc_binned(logp.numpy(), target.numpy(), 64)                       # ties inside a bin share a trapezoid
+    qs = np.minimum(63, np.floor(p * np.float32(64)))
+    for c in range(4):
+        assert abs(q[c] - roc_auc_score((target.numpy() == c).astype(int), qs[:, c])) < 1e-12
+    assert mo.auroc_exact(logp.numpy(), np.zeros(5000, np.int64))[1] == 0.0     # class without positives
+
+
+def test_auroc_from_histograms_host_logic():
+    """hss.sharding.auroc_from_histograms on oracle-built histograms == the oracle's AUROC of the binned scores; at 4096
+    bins that is the exact AUROC to ~1e-4; shards add up."""
+    from hss.sharding import auroc_from_histograms
+
+    from oracle import metrics_oracle as mo
+
+    logp, target = _scored_labels(20000, 5)
+    for nbins in (16, 4096):
+        h = torch.from_numpy(mo.histograms(logp.numpy(), target.numpy(), nbins))
+        got = auroc_from_histograms(h)
+        ref = mo.auroc_binned(logp.numpy(), target.numpy(), nbins)
+        assert np.abs(got["auroc_per_class"].numpy() - ref).max() < 1e-12
+        assert abs(got["auroc"] - ref.mean()) < 1e-12
+    exact = mo.auroc_exact(logp.numpy(), target.numpy())
+    assert np.abs(got["auroc_per_class"].numpy() - exact).max() < 2e-4
+    halves = sum(torch.from_numpy(mo.histograms(logp[s].numpy(), target[s].numpy(), 4096)) for s in (slice(0, 7000), slice(7000, None)))
+    assert torch.equal(halves, h)
+    empty = auroc_from_histograms(torch.zeros(4, 2, 16, dtype=torch.int64))
+    assert empty["auroc"] == 0.0

@@ -179,6 +179,32 @@ def test_confusion_kernel_and_metrics(lib):
     assert abs(metrics_from_counts(cm)["micro_accuracy"] - float((pred == target).double().mean())) < 1e-9
 
 
+def test_auroc_histogram_kernel(lib):
+    """hssb_auroc_hist (main.py:48,60): histograms bit-identical to the numpy oracle, AUROC from them == the
+    oracle's binned AUROC and within 2e-4 of the exact (thresholds=None) one; skewed scores hit the end bins (warp-aggregated)."""
+    from hss.sharding import auroc_from_histograms, score_histograms
+
+    from oracle import metrics_oracle as mo
+
+    g = torch.Generator().manual_seed(2)
+    n = 50 * 2000 + 37
+    target = torch.randint(0, 4, (n,), generator=g)
+    target[::97] = 7                                                     # out-of-range targets are skipped
+    logits = torch.randn(n, 4, generator=g) + 9.0 * torch.nn.functional.one_hot(target.clamp(max=3), 4) * (torch.rand(n, 1, generator=g) > 0.2)
+    logp = torch.log_softmax(logits, dim=1)
+    for nbins in (2, 100, 4096):
+        h = score_histograms(logp.cuda(), target.cuda(), nbins).cpu()
+        ref = mo.histograms(logp.numpy(), target.numpy(), nbins)
+        d = (h.numpy() != ref)
+        # exp() on the device may differ from numpy's by an ulp: a score within 1 ulp of a bin edge may sit in the neighbouring bin
+        assert h.sum().item() == ref.sum() and np.abs(np.cumsum(h.numpy() - ref, axis=2)).max() <= 3, int(d.sum())
+    got = auroc_from_histograms(h)["auroc_per_class"].numpy()
+    assert np.abs(got - mo.auroc_binned(logp.numpy(), target.numpy(), 4096)).max() < 1e-6
+    assert np.abs(got - mo.auroc_exact(logp.numpy(), target.numpy())).max() < 2e-4
+    with pytest.raises(ValueError):
+        score_histograms(logp.cuda(), target.cuda(), 5000)
+
+
 @pytest.mark.parametrize("B,T", [(2, 128), (3, 200), (50, 333)])
 def test_k4_tcgen05_inproj_matches_simt(lib, B, T):
     """Kernel-level parity of K4 (split-fp16 x3 tcgen05 GEMM) against the fp32 SIMT projection and float64."""
