@@ -250,9 +250,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     _lib.prof_enable(True)
     _lib.prof_read()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    gc.collect()        # (before the barrier: a gen-2 collection takes 10-50 ms and differs per rank -- after it, the skew would
+    gc.disable()        #  sit in the first step's all-reduce)
     barrier()
-    gc.collect()
-    gc.disable()
     for a, b in ev:
         flush.zero_()
         a.record()
@@ -268,41 +268,51 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # ---- end to end: pinned host input -> H2D -> path -> labels + counters back on the host ----
     # (the input lands in a preallocated device buffer and the Python GC is off inside the timed region: a torch allocator miss
     #  or a gen-2 collection costs 30-90 ms of host time, which used to hit one of the five steps every few runs)
-    labels_host = torch.empty((B, N_SAMPLES), dtype=torch.int32).pin_memory()
+    # Double buffered like a production ingest loop: step i is enqueued (H2D copy, kernels, D2H copies into pinned slot i % 2),
+    # then the host waits for step i-1's event and reads its results -- every step's labels and counters reach the host inside
+    # the timed region, one step behind the device, so host launch latency and scheduling jitter overlap with device work.
+    lab_slots = [torch.empty((B, N_SAMPLES), dtype=torch.int32).pin_memory() for _ in range(2)]
+    cm_slots = [torch.empty((4, 4), dtype=torch.int64).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
     x_in = torch.empty_like(x_dev)
 
-    def e2e_step():
+    def e2e_enqueue(i):
         x_in.copy_(x_host, non_blocking=True)
         labels, cm = step(x_in)
-        labels_host.copy_(labels, non_blocking=True)
-        return cm.cpu()
+        lab_slots[i & 1].copy_(labels, non_blocking=True)
+        cm_slots[i & 1].copy_(cm, non_blocking=True)
+        done[i & 1].record()
 
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    barrier()
+    def e2e_collect(i):
+        done[i & 1].synchronize()
+        return int(cm_slots[i & 1].sum()) + int(lab_slots[i & 1][0, 0])      # the host reads the step's results
+
+    def e2e_run(n):
+        seen = 0
+        for i in range(n):
+            e2e_enqueue(i)
+            if i:
+                seen += e2e_collect(i - 1)
+            wall.append(time.perf_counter())
+        return seen + e2e_collect(n - 1)
+
+    wall = []
+    e2e_run(max(args.warmup, 3))
     gc.collect()
     gc.disable()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     debug = bool(os.environ.get("HSSB_BENCH_DEBUG"))
-    if debug:
-        _lib.prof_enable(True)
-        _lib.prof_read()
-    wall, per_step = [time.perf_counter()], []
-    for _ in range(args.steps):
-        cm_host = e2e_step()
-        wall.append(time.perf_counter())
-        if debug:
-            per_step.append({k: round(v[1], 2) for k, v in _lib.prof_read().items() if v[1] > 0.05})
+    wall = [time.perf_counter()]
+    e0.record()
+    e2e_run(args.steps)
     e1.record()
     barrier()
     gc.enable()
     ms_e2e = e0.elapsed_time(e1)
+    cm_host = cm_slots[(args.steps - 1) & 1].clone()
     if debug:
-        _lib.prof_enable(False)
-        print("e2e wall per step (ms):", [round(1e3 * (b - a), 3) for a, b in zip(wall, wall[1:])], "events total", ms_e2e, file=sys.stderr)
-        for i, d in enumerate(per_step):
-            print("  e2e step", i, d, file=sys.stderr)
+        print(f"rank {rank} e2e wall per step (ms):", [round(1e3 * (b - a), 3) for a, b in zip(wall, wall[1:])], "events total", ms_e2e, file=sys.stderr)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -370,7 +380,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "windows_per_gpu": B, "samples_per_window": N_SAMPLES, "l2": "flushed between timed steps (256 MiB write)",
                        "lstm_impl": os.environ.get("HSSB_LSTM_IMPL", "auto")},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
-                    "d2h_bytes_per_step": int(labels_host.numel() * 4 + 128)},
+                    "d2h_bytes_per_step": int(lab_slots[0].numel() * 4 + 128), "pipeline": "double buffered: results of step i-1 read on the host while step i runs"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel, "cpu_baseline": cpu,
             "confusion_total": int(cm_host.sum()),
         }
