@@ -1,5 +1,6 @@
 // libhssb.so: error reporting, device check, metric counters.
 #include "hssb_common.cuh"
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -53,7 +54,7 @@ namespace {
 struct ProfRec { const char *name; cudaEvent_t start, stop; };
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
-bool g_prof_on = false;
+std::atomic<bool> g_prof_on{false};
 }  // namespace
 
 ProfScope::ProfScope(const char *name, cudaStream_t s) : slot(-1), st(s)

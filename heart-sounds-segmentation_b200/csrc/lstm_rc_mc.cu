@@ -453,7 +453,9 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     prm.groups = groups;
     prm.stagger_ns = 600;
     if (const char *e = getenv("HSSB_RC_STAGGER")) prm.stagger_ns = atoi(e);
+#ifdef HSSB_KNOCKOUTS   // timing experiments that skip parts of the step (results are WRONG): only in -DHSSB_KNOCKOUTS builds
     if (const char *e = getenv("HSSB_RC_DEBUG")) prm.debug = atoi(e);
+#endif
     cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
     ProfScope prof("tc_recurrent", st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, prm);

@@ -463,7 +463,9 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     prm.B = B;
     prm.Bp = xproj_pitch(B);
     prm.debug = 0;
+#ifdef HSSB_KNOCKOUTS   // timing experiment that skips the global stores (results are WRONG): only in -DHSSB_KNOCKOUTS builds
     if (const char *e = getenv("HSSB_IP_DEBUG")) prm.debug = atoi(e);
+#endif
     prm.bias = m->tc_bias[layer];
     prm.k_real = kreal;
     prm.T = (int)T;

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-kernel times of one BiLSTM forward (B=512, T=2000) -- used with the HSSB_IP_DEBUG / HSSB_RC_DEBUG knock-out switches."""
+"""Per-kernel times of one BiLSTM forward (B=512, T=2000) -- used with the HSSB_IP_DEBUG / HSSB_RC_DEBUG knock-out switches
+(those need a profiling build: HSSB_KNOCKOUTS=1 python __graft_entry__.py --force)."""
 import os
 import sys
 
