@@ -167,6 +167,10 @@ extern "C" int hssb_model_forward(const hssb_model *m, const float *x, int64_t B
     if (B > 65535 * 4) return fail(HSSB_E_SHAPE, "hssb_model_forward: B=%lld too large for one call", (long long)B);
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(HSSB_E_WORKSPACE, "model workspace must be 256-byte aligned");
     if (int rc = require_sm100()) return rc;
+    int dev = -1;
+    HSSB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev != m->device)
+        return fail(HSSB_E_DEVICE, "hssb_model_forward: model lives on device %d, current device is %d", m->device, dev);
     cudaStream_t st = as_stream(stream);
     if (impl == 1) return simt_forward(m, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, st);
     if (impl != 0) return fail(HSSB_E_MODE, "hssb_model_forward: impl %d", impl);

@@ -1,0 +1,98 @@
+"""Training-mode forward of the segmenter: one autograd function per bidirectional LSTM layer.
+
+The reference trains ``nn.LSTM`` under autograd (``main.py:67-82`` over ``hss/model/segmenter.py:80-87``).
+Here the two recurrences of a layer -- the forward that keeps the activated gates and cell states, and
+back-propagation through time -- are CUDA kernels of ``libhssb.so`` (``hssb_lstm_train_forward`` /
+``hssb_lstm_train_backward``); the plain GEMMs either side (``x W_ih^T + b``, ``dG^T x``, ``dG^T h_prev``,
+``dG W_ih``) are cuBLAS calls through ``torch``; ReLU, dropout, the linear head and log-softmax stay torch
+ops, so torch's RNG drives dropout exactly as in the reference.  fp32 throughout.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+
+
+class BiLSTMLayerFunction(torch.autograd.Function):
+    """``(x[B,T,F], h0[2,B,H], c0[2,B,H], 8 parameters) -> (out[B,T,2H], hn[2,B,H], cn[2,B,H])`` like
+    ``nn.LSTM(bidirectional=True, batch_first=True)``."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        if not x.is_cuda:
+            raise RuntimeError("the training recurrences run on the GPU (no CPU fallback)")
+        tensors = [t.detach().to(torch.float32).contiguous() for t in (x, h0, c0, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
+        x, h0, c0, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = tensors
+        B, T, Fin = x.shape
+        H = w_hh.shape[1]
+        dev = x.device
+        x2 = x.reshape(B * T, Fin)
+        gates = torch.empty((2, B * T, 4 * H), dtype=torch.float32, device=dev)
+        if B * T:
+            torch.addmm(b_ih + b_hh, x2, w_ih.t(), out=gates[0])
+            torch.addmm(b_ih_r + b_hh_r, x2, w_ih_r.t(), out=gates[1])
+        out = torch.empty((B, T, 2 * H), dtype=torch.float32, device=dev)
+        cells = torch.empty((2, B * T, H), dtype=torch.float32, device=dev)
+        hn = torch.empty((2, B, H), dtype=torch.float32, device=dev)
+        cn = torch.empty((2, B, H), dtype=torch.float32, device=dev)
+        whT, whT_r = w_hh.t().contiguous(), w_hh_r.t().contiguous()
+        with torch.cuda.device(dev):
+            rc = _lib.lib().hssb_lstm_train_forward(gates.data_ptr(), whT.data_ptr(), whT_r.data_ptr(), h0.data_ptr(), c0.data_ptr(),
+                                                    B, T, H, out.data_ptr(), cells.data_ptr(), hn.data_ptr(), cn.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "hssb_lstm_train_forward")
+        ctx.save_for_backward(x, h0, c0, w_ih, w_hh, w_ih_r, w_hh_r, gates, cells, out)
+        return out, hn, cn
+
+    @staticmethod
+    def backward(ctx, d_out, d_hn, d_cn):
+        x, h0, c0, w_ih, w_hh, w_ih_r, w_hh_r, gates, cells, out = ctx.saved_tensors
+        B, T, Fin = x.shape
+        H = w_hh.shape[1]
+        dev = x.device
+        d_out = torch.zeros_like(out) if d_out is None else d_out.to(torch.float32).contiguous()
+        d_hn = None if d_hn is None else d_hn.to(torch.float32).contiguous()
+        d_cn = None if d_cn is None else d_cn.to(torch.float32).contiguous()
+        dG = gates.clone()                       # the kernel turns activations into dG in place; keep the saved tensor intact
+        dh0 = torch.empty_like(h0)
+        dc0 = torch.empty_like(c0)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().hssb_lstm_train_backward(dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(),
+                                                     d_out.data_ptr(), d_hn.data_ptr() if d_hn is not None else None,
+                                                     d_cn.data_ptr() if d_cn is not None else None, B, T, H,
+                                                     dh0.data_ptr(), dc0.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "hssb_lstm_train_backward")
+        x2 = x.reshape(B * T, Fin)
+        # h_{prev}: forward direction = out[:, t-1, :H] (h0 at t = 0); reverse direction = out[:, t+1, H:] (h0 at t = T-1)
+        hp_f = torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(B * T, H)
+        hp_r = torch.cat([out[:, 1:, H:], h0[1].unsqueeze(1)], dim=1).reshape(B * T, H)
+        grads = []
+        for d, (wi, hp) in enumerate(((w_ih, hp_f), (w_ih_r, hp_r))):
+            g = dG[d]
+            db = g.sum(dim=0)
+            grads.append((g.t() @ x2, g.t() @ hp, db, db.clone()))
+        dx = (dG[0] @ w_ih + dG[1] @ w_ih_r).reshape(B, T, Fin) if ctx.needs_input_grad[0] else None
+        (dwi, dwh, dbi, dbh), (dwi_r, dwh_r, dbi_r, dbh_r) = grads
+        return dx, dh0, dc0, dwi, dwh, dbi, dbh, dwi_r, dwh_r, dbi_r, dbh_r
+
+
+def _layer(lstm: torch.nn.LSTM, x, h0, c0):
+    return BiLSTMLayerFunction.apply(
+        x, h0, c0, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
+        lstm.weight_ih_l0_reverse, lstm.weight_hh_l0_reverse, lstm.bias_ih_l0_reverse, lstm.bias_hh_l0_reverse)
+
+
+def training_forward(model, x: torch.Tensor) -> torch.Tensor:
+    """``HeartSoundSegmenter.forward`` in training mode: reference segmenter.py:80-87 with dropout active."""
+    p = model.linear.weight
+    if not (x.is_cuda and p.is_cuda and x.device == p.device):
+        raise RuntimeError("training mode needs the module and its input on the same CUDA device "
+                           "(model.to('cuda')); there is no CPU fallback")
+    h0 = model.h0.to(device=x.device, dtype=torch.float32)
+    c0 = model.c0.to(device=x.device, dtype=torch.float32)
+    out, hn, cn = _layer(model.lstm_1, x, h0, c0)
+    out = model.dropout(F.relu(out))
+    out, _, _ = _layer(model.lstm_2, out, hn, cn)
+    out = model.dropout(F.relu(out))
+    return F.log_softmax(model.linear(out), dim=2)

@@ -4,8 +4,8 @@ Constructor signature, parameter names (the 18 ``state_dict`` keys), the random 
 and their RNG draw order, the batch-size check and the ``forward(x[B,T,F]) -> logp[B,T,4]``
 contract follow reference ``hss/model/segmenter.py:20-87``.  ``nn.LSTM`` / ``nn.Linear`` modules are
 kept purely as parameter containers (so checkpoints load unchanged); the arithmetic of the eval-mode
-forward runs in ``libhssb.so`` (``hssb_model_forward``).  Training / backward is out of scope
- and raises.
+forward runs in ``libhssb.so`` (``hssb_model_forward``).  In training mode ``forward`` is differentiable
+(SURVEY.md 8f-4): see ``hss/model/_train.py``.
 """
 from __future__ import annotations
 
@@ -120,12 +120,7 @@ class HeartSoundSegmenter(nn.Module):
         return self._state_dev["h0"], self._state_dev["c0"]
 
     # ------------------------------------------------------------------------------------------
-    def _run(self, x: torch.Tensor, want_logp: bool, want_labels: bool):
-        if self.training:
-            raise NotImplementedError(
-                "HeartSoundSegmenter (B200 build) implements the inference forward only; call .eval(). "
-                "Training/backward is out of scope (SURVEY.md 8f-4)."
-            )
+    def _check_input(self, x: torch.Tensor) -> None:
         if x.dim() != 3:
             raise ValueError(f"expected input of shape (batch, seq, feature), got {tuple(x.shape)}")
         if x.shape[0] != self.batch_size:
@@ -135,6 +130,11 @@ class HeartSoundSegmenter(nn.Module):
             )
         if x.shape[2] != self.lstm_1.input_size:
             raise RuntimeError(f"input.size(-1) must be equal to input_size. Expected {self.lstm_1.input_size}, got {x.shape[2]}")
+
+    def _run(self, x: torch.Tensor, want_logp: bool, want_labels: bool):
+        if self.training:
+            raise RuntimeError("predict() / forward_with_labels() are inference calls: switch the module to .eval()")
+        self._check_input(x)
         lib = _lib.lib()
         was_cpu = not x.is_cuda
         dev = _lib.require_cuda() if was_cpu else x.device
@@ -166,7 +166,15 @@ class HeartSoundSegmenter(nn.Module):
         return logp, labels
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """``x[B, T, F]`` -> log-probabilities ``[B, T, 4]`` (reference segmenter.py:70-87, eval mode)."""
+        """``x[B, T, F]`` -> log-probabilities ``[B, T, 4]`` (reference segmenter.py:70-87).
+
+        Eval mode: the sm_100a inference kernels (no autograd graph).  Training mode: dropout active and a
+        differentiable result, the recurrences and their back-propagation through time in ``hss/model/_train.py``."""
+        if self.training:
+            from ._train import training_forward
+
+            self._check_input(x)
+            return training_forward(self, x)
         return self._run(x, True, False)[0]
 
     @torch.no_grad()

@@ -8,6 +8,7 @@
  *             band mask / abs / z-score+stack              hss/transforms/synchrosqueeze.py:56-111
  *             streaming mean / M2 recurrences              hss/moments/__init__.py:16,35-36
  *   BiLSTM    HeartSoundSegmenter.forward                  hss/model/segmenter.py:70-87
+ *   training  nn.LSTM forward/backward under autograd      main.py:67-82 (segmenter.py:80-83)
  *   metrics   multiclass confusion counts                  main.py:36-62 (torchmetrics)
  *             one-vs-rest score histograms (AUROC)         main.py:48,60
  *
@@ -137,6 +138,25 @@ int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B, int64_t T,
 int hssb_debug_trace(unsigned long long *buf, int steps);
 /* Diagnostic: co-resident 8-CTA recurrence clusters (geometry 32x3) on the current device; <0 on error. */
 int hssb_debug_max_clusters(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Training recurrences of one bidirectional LSTM layer (what autograd does for nn.LSTM in the reference's
+ * training step, main.py:67-82 over segmenter.py:80-83).  fp32.  The plain GEMMs either side (x W_ih^T + b,
+ * dG^T x, dG^T h_prev, dG W_ih) are library GEMMs issued by the caller (hss/model/_train.py).
+ * Layouts: gates [2][B*T][4H] (row b*T+t, gate order i,f,g,o), cells [2][B*T][H], out / d_out [B][T][2H],
+ * states [2][B][H]; dir 0 = forward, 1 = reverse.
+ * ------------------------------------------------------------------------------------------ */
+
+/* gates in: x W_ih^T + b_ih + b_hh per direction; out: the activated gates (kept for the backward).
+ * w_hhT_*: W_hh transposed, [H][4H].  Writes out (raw h_t, no ReLU), cells (c_t), hn, cn. */
+int hssb_lstm_train_forward(float *gates, const float *w_hhT_fwd, const float *w_hhT_rev, const float *h0, const float *c0,
+                            int64_t B, int64_t T, int H, float *out, float *cells, float *hn, float *cn, void *stream);
+
+/* gates in: activated gates from the forward; out: dG = dL/d(gate pre-activations).  w_hh_*: [4H][H] (torch layout).
+ * d_hn, d_cn nullable (zero).  Writes dh0, dc0 (gradient w.r.t. the initial state). */
+int hssb_lstm_train_backward(float *gates, const float *cells, const float *w_hh_fwd, const float *w_hh_rev, const float *c0,
+                             const float *d_out, const float *d_hn, const float *d_cn, int64_t B, int64_t T, int H,
+                             float *dh0, float *dc0, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Metric counters: replaces the torchmetrics confusion statistics of main.py:36-62.

@@ -126,3 +126,33 @@ def label_report(logp_test: torch.Tensor, logp_ref: torch.Tensor, logp_truth: to
         rep["flips_test_vs_truth"] = int((lab_t != lab_truth).sum())
         rep["flips_ref_vs_truth"] = int((lab_r != lab_truth).sum())
     return rep
+
+
+def training_reference(params: dict, h0: torch.Tensor, c0: torch.Tensor, x: torch.Tensor, y: torch.Tensor,
+                       masks: tuple[torch.Tensor, torch.Tensor] | None = None, dtype=torch.float32):
+    """One training-step forward + backward of the reference on the CPU: segmenter.py:80-87 in training mode
+    (``nn.LSTM`` under autograd), ``CrossEntropyLoss`` on the permuted output as in main.py:67-70.
+
+    Dropout (p = 0.2) cannot replay another device's RNG stream, so the two masks (already scaled by 1 / 0.8)
+    are passed in; ``None`` = no dropout.  Returns ``(loss, logp, {name: grad}, grad_x)``.
+    """
+    hidden = h0.shape[2]
+    lstm_1, lstm_2, linear = _modules(x.shape[2], hidden)
+    lstm_1.load_state_dict({k.split(".", 1)[1]: v for k, v in params.items() if k.startswith("lstm_1.")})
+    lstm_2.load_state_dict({k.split(".", 1)[1]: v for k, v in params.items() if k.startswith("lstm_2.")})
+    linear.load_state_dict({k.split(".", 1)[1]: v for k, v in params.items() if k.startswith("linear.")})
+    mods = {"lstm_1": lstm_1.to(dtype), "lstm_2": lstm_2.to(dtype), "linear": linear.to(dtype)}
+    x = x.detach().to(dtype).requires_grad_(True)
+    out, (hn, cn) = mods["lstm_1"](x, (h0.to(dtype), c0.to(dtype)))
+    out = torch.relu(out)
+    if masks is not None:
+        out = out * masks[0].to(dtype)
+    out, _ = mods["lstm_2"](out, (hn, cn))
+    out = torch.relu(out)
+    if masks is not None:
+        out = out * masks[1].to(dtype)
+    logp = torch.log_softmax(mods["linear"](out), dim=2)
+    loss = nn.functional.cross_entropy(logp.permute(0, 2, 1), y)
+    loss.backward()
+    grads = {f"{prefix}.{k}": p.grad.detach().clone() for prefix, mod in mods.items() for k, p in mod.named_parameters()}
+    return loss.detach(), logp.detach(), grads, x.grad.detach().clone()

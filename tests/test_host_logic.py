@@ -58,8 +58,10 @@ def test_segmenter_signature_state_dict_and_rng_order():
     with pytest.raises(RuntimeError, match="Expected hidden"):
         m(torch.zeros(2, 5, 44))                                      # batch mismatch raises like the reference
     m.train()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(3, 5, 44))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(3, 5, 44))                                      # training has no CPU fallback either
+    with pytest.raises(RuntimeError, match="eval"):
+        m.predict(torch.zeros(3, 5, 44))
 
 
 def test_moments_api():

@@ -1,0 +1,118 @@
+"""Training step: forward in training mode + back-propagation through time on the GPU against the
+reference's own arithmetic -- torch's CPU ``nn.LSTM`` under autograd (oracle/lstm_oracle.training_reference).
+
+Tolerance: fp32 with a different summation order (the gradients are sums over B*T terms): loss within 1e-5 relative,
+every gradient within 2e-4 of its tensor's max-abs against the fp32 reference (measured: ~1e-6).  The distance to a float64
+run of the reference is printed, not asserted: a ReLU input within rounding of zero switches sides between precisions and
+moves the gradient discontinuously (measured 9e-3 for the fp32 reference itself on the 9 x 64 case).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstm_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 2e-4
+
+
+@pytest.fixture(scope="module")
+def lib(built):
+    from hss import _lib
+
+    assert torch.cuda.is_available()
+    return _lib.lib()
+
+
+def make_model(seed, F, B, H):
+    from hss.model.segmenter import HeartSoundSegmenter
+
+    torch.manual_seed(seed)
+    return HeartSoundSegmenter(input_size=F, batch_size=B, hidden_size=H)
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("B,T,F,H", [(3, 17, 44, 240), (5, 40, 7, 32), (9, 64, 44, 240), (1, 1, 44, 240)])
+def test_training_step_gradients_match_torch_cpu(lib, B, T, F, H):
+    m = make_model(B + T, F, B, H).cuda().train()
+    m.dropout.p = 0.0                                         # dropout is covered by the next test
+    params, h0, c0 = lo.reference_params(B + T, F, B, H)
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(B, T, F, generator=g)
+    y = torch.randint(0, 4, (B, T), generator=g)
+    xg = x.cuda().requires_grad_(True)
+    logp = m(xg)
+    assert logp.requires_grad and logp.shape == (B, T, 4)
+    loss = torch.nn.functional.cross_entropy(logp.permute(0, 2, 1), y.cuda())
+    loss.backward()
+    ref_loss, ref_logp, ref_grads, ref_dx = lo.training_reference(params, h0, c0, x, y)
+    _, _, grads64, dx64 = lo.training_reference(params, h0, c0, x, y, dtype=torch.float64)
+    assert abs(float(loss.detach()) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    assert (logp.detach().cpu() - ref_logp).abs().max() < 2e-5
+    worst = worst64 = 0.0
+    for name, p in m.named_parameters():
+        e = rel_err(p.grad.cpu(), ref_grads[name])
+        worst = max(worst, e)
+        worst64 = max(worst64, rel_err(p.grad.cpu().double(), grads64[name]), rel_err(ref_grads[name].double(), grads64[name]))
+        assert e < REL_TOL, (name, e)
+    assert rel_err(xg.grad.cpu(), ref_dx) < REL_TOL
+    # eval mode on the same module = the inference kernels, same numbers as the training forward without dropout
+    m.eval()
+    with torch.no_grad():
+        assert (m(x.cuda()) - logp.detach()).abs().max() < 2e-5
+    print(f"B={B} T={T} F={F} H={H}: worst relative gradient error {worst:.2e} (fp32 reference), {worst64:.2e} (either fp32 run vs float64)")
+
+
+def test_dropout_masks_and_an_optimizer_step(lib):
+    """Dropout comes from torch's CUDA RNG (as in the reference); the masks it drew are recovered from the stream and replayed
+    on the CPU reference.  Then one Adam step with gradient-norm clipping (main.py:130-135 / trainer gradient_clip_val)."""
+    B, T, F, H = 4, 25, 44, 240
+    m = make_model(1, F, B, H).cuda().train()
+    params, h0, c0 = lo.reference_params(1, F, B, H)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, T, F, generator=g)
+    y = torch.randint(0, 4, (B, T), generator=g)
+    torch.manual_seed(123)
+    logp = m(x.cuda())
+    torch.manual_seed(123)                                     # replay: the forward draws exactly two [B,T,2H] masks, in order
+    ones = torch.ones(B, T, 2 * H, device="cuda")
+    masks = (m.dropout(ones).cpu(), m.dropout(ones).cpu())
+    assert set(np.unique(masks[0].numpy()).round(4)) <= {0.0, 1.25}
+    loss = torch.nn.functional.cross_entropy(logp.permute(0, 2, 1), y.cuda())
+    loss.backward()
+    ref_loss, _, ref_grads, _ = lo.training_reference(params, h0, c0, x, y, masks)
+    assert abs(float(loss.detach()) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    for name, p in m.named_parameters():
+        assert rel_err(p.grad.cpu(), ref_grads[name]) < REL_TOL, name
+    opt = torch.optim.Adam(m.parameters(), lr=0.01)
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    before = m.linear.weight.detach().clone()
+    opt.step()
+    assert not torch.equal(before, m.linear.weight)
+    m.eval()                                                   # the inference path repacks the updated weights
+    with torch.no_grad():
+        out = m(x.cuda())
+    new_params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    assert (out.cpu() - lo.forward_torch(new_params, h0, c0, x)).abs().max() < 2e-5
+
+
+def test_loss_decreases_over_a_few_steps(lib):
+    B, T, F = 8, 200, 44
+    m = make_model(3, F, B, 240).cuda().train()
+    g = torch.Generator().manual_seed(3)
+    y = torch.randint(0, 4, (B, 1), generator=g).expand(B, T).contiguous()
+    x = torch.randn(B, T, F, generator=g) + 2.0 * torch.nn.functional.one_hot(y, F).float()    # the label is readable from x
+    opt = torch.optim.Adam(m.parameters(), lr=0.01)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(m(x.cuda()).permute(0, 2, 1), y.cuda())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.8 * losses[0], losses
