@@ -6,6 +6,7 @@
 // Layouts (all fp32): gates [dir][B*T][4H] (row b*T + t, torch gate order i,f,g,o), cells [dir][B*T][H], out [B][T][2H]
 // (dir 0 = forward in columns 0..H-1, dir 1 = reverse in H..2H-1), states [dir][B][H].
 #include "model.cuh"
+#include <cstdlib>
 
 namespace hssb {
 
@@ -182,6 +183,14 @@ lstm_train_bwd_kernel(float *__restrict__ gates, const float *__restrict__ cells
     }
 }
 
+// HSSB_TRAIN_IMPL=stream forces the generic kernels below (weights re-read from L2 every step) where the cluster-resident
+// ones of lstm_train_cluster.cu would run: the cross-implementation test uses it.
+bool use_cluster_kernels(int H)
+{
+    const char *e = getenv("HSSB_TRAIN_IMPL");
+    return train_cluster_supported(H) && !(e && e[0] == 's');
+}
+
 int check_train_args(const char *what, int64_t B, int64_t T, int H)
 {
     if (B < 0 || T < 0 || H < 1) return fail(HSSB_E_SHAPE, "%s: B=%lld T=%lld H=%d", what, (long long)B, (long long)T, H);
@@ -209,6 +218,7 @@ extern "C" int hssb_lstm_train_forward(float *gates, const float *w_hhT_fwd, con
         HSSB_CUDA_OK(cudaMemcpyAsync(cn, c0, sizeof(float) * 2 * B * H, cudaMemcpyDeviceToDevice, st));
         return 0;
     }
+    if (use_cluster_kernels(H)) return train_fwd_cluster_launch(gates, w_hhT_fwd, w_hhT_rev, h0, c0, B, T, out, cells, hn, cn, st);
     const size_t smem = sizeof(float) * (size_t)TR * H * 6;
     HSSB_CUDA_OK(cudaFuncSetAttribute(lstm_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B + TR - 1) / TR), 2);
@@ -235,6 +245,7 @@ extern "C" int hssb_lstm_train_backward(float *gates, const float *cells, const 
         else HSSB_CUDA_OK(cudaMemsetAsync(dc0, 0, sizeof(float) * 2 * B * H, st));
         return 0;
     }
+    if (use_cluster_kernels(H)) return train_bwd_cluster_launch(gates, cells, w_hh_fwd, w_hh_rev, c0, d_out, d_hn, d_cn, B, T, dh0, dc0, st);
     const size_t smem = sizeof(float) * (size_t)TR * H * (6 + TQ);
     HSSB_CUDA_OK(cudaFuncSetAttribute(lstm_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B + TR - 1) / TR), 2);

@@ -43,4 +43,11 @@ size_t tc_workspace_bytes(const hssb_model *m, int64_t B, int64_t T);
 int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
                float *logp, int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st);
 
+// training recurrences with cluster-resident weights (lstm_train_cluster.cu); the generic ones are in lstm_train.cu
+bool train_cluster_supported(int H);
+int train_fwd_cluster_launch(float *gates, const float *w0T, const float *w1T, const float *h0, const float *c0, int64_t B, int64_t T,
+                             float *out, float *cells, float *hn, float *cn, cudaStream_t st);
+int train_bwd_cluster_launch(float *gates, const float *cells, const float *w0, const float *w1, const float *c0, const float *d_out,
+                             const float *d_hn, const float *d_cn, int64_t B, int64_t T, float *dh0, float *dc0, cudaStream_t st);
+
 }  // namespace hssb

@@ -116,3 +116,23 @@ def test_loss_decreases_over_a_few_steps(lib):
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+def test_cluster_and_streaming_kernels_agree(lib, monkeypatch):
+    """hidden_size 240 runs the cluster-resident kernels (lstm_train_cluster.cu); HSSB_TRAIN_IMPL=stream forces the generic
+    ones (lstm_train.cu).  Same step on a batch with a ragged last row group, more steps than the CPU oracle affords."""
+    B, T, F = 21, 300, 44
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, T, F, generator=g).cuda()
+    y = torch.randint(0, 4, (B, T), generator=g).cuda()
+    results = []
+    for impl in ("cluster", "stream"):
+        monkeypatch.setenv("HSSB_TRAIN_IMPL", impl)
+        m = make_model(11, F, B, 240).cuda().train()
+        m.dropout.p = 0.0
+        loss = torch.nn.functional.cross_entropy(m(x).permute(0, 2, 1), y)
+        loss.backward()
+        results.append((float(loss.detach()), {n: p.grad.clone() for n, p in m.named_parameters()}))
+    assert abs(results[0][0] - results[1][0]) < 1e-6 * abs(results[1][0])
+    for name in results[0][1]:
+        assert rel_err(results[0][1][name], results[1][1][name]) < 2e-5, name
