@@ -184,7 +184,8 @@ lstm_train_bwd_kernel(float *__restrict__ gates, const float *__restrict__ cells
 }
 
 // HSSB_TRAIN_IMPL=stream forces the generic kernels below (weights re-read from L2 every step) where the cluster-resident
-// ones of lstm_train_cluster.cu would run: the cross-implementation test uses it.
+// ones of lstm_train_cluster.cu would run, =gather the all-gather form of the cluster backward: the cross-implementation
+// test uses both.
 bool use_cluster_kernels(int H)
 {
     const char *e = getenv("HSSB_TRAIN_IMPL");
@@ -245,7 +246,10 @@ extern "C" int hssb_lstm_train_backward(float *gates, const float *cells, const 
         else HSSB_CUDA_OK(cudaMemsetAsync(dc0, 0, sizeof(float) * 2 * B * H, st));
         return 0;
     }
-    if (use_cluster_kernels(H)) return train_bwd_cluster_launch(gates, cells, w_hh_fwd, w_hh_rev, c0, d_out, d_hn, d_cn, B, T, dh0, dc0, st);
+    if (use_cluster_kernels(H)) {
+        const char *e = getenv("HSSB_TRAIN_IMPL");       // "gather": the all-gather backward (3x slower; kept as a cross-check)
+        return train_bwd_cluster_launch(gates, cells, w_hh_fwd, w_hh_rev, c0, d_out, d_hn, d_cn, B, T, dh0, dc0, e && e[0] == 'g', st);
+    }
     const size_t smem = sizeof(float) * (size_t)TR * H * (6 + TQ);
     HSSB_CUDA_OK(cudaFuncSetAttribute(lstm_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B + TR - 1) / TR), 2);

@@ -48,6 +48,7 @@ bool train_cluster_supported(int H);
 int train_fwd_cluster_launch(float *gates, const float *w0T, const float *w1T, const float *h0, const float *c0, int64_t B, int64_t T,
                              float *out, float *cells, float *hn, float *cn, cudaStream_t st);
 int train_bwd_cluster_launch(float *gates, const float *cells, const float *w0, const float *w1, const float *c0, const float *d_out,
-                             const float *d_hn, const float *d_cn, int64_t B, int64_t T, float *dh0, float *dc0, cudaStream_t st);
+                             const float *d_hn, const float *d_cn, int64_t B, int64_t T, float *dh0, float *dc0, bool all_gather,
+                             cudaStream_t st);
 
 }  // namespace hssb

@@ -126,13 +126,14 @@ def test_cluster_and_streaming_kernels_agree(lib, monkeypatch):
     x = torch.randn(B, T, F, generator=g).cuda()
     y = torch.randint(0, 4, (B, T), generator=g).cuda()
     results = []
-    for impl in ("cluster", "stream"):
+    for impl in ("cluster", "gather", "stream"):     # default (reduce-scatter backward), all-gather backward, generic kernels
         monkeypatch.setenv("HSSB_TRAIN_IMPL", impl)
         m = make_model(11, F, B, 240).cuda().train()
         m.dropout.p = 0.0
         loss = torch.nn.functional.cross_entropy(m(x).permute(0, 2, 1), y)
         loss.backward()
         results.append((float(loss.detach()), {n: p.grad.clone() for n, p in m.named_parameters()}))
-    assert abs(results[0][0] - results[1][0]) < 1e-6 * abs(results[1][0])
-    for name in results[0][1]:
-        assert rel_err(results[0][1][name], results[1][1][name]) < 2e-5, name
+    for loss, grads in results[:2]:
+        assert abs(loss - results[2][0]) < 1e-6 * abs(results[2][0])
+        for name in grads:
+            assert rel_err(grads[name], results[2][1][name]) < 2e-5, name
