@@ -47,3 +47,41 @@ def test_two_rank_confusion_allreduce(tmp_path):
     got = torch.load(out)
     assert torch.equal(got["cm"], _cpu_counts(pred, target))
     assert got["range"] == (0, 4)
+
+
+def _hist_worker(rank, world, port, logp, target, out_path):
+    sys.path.insert(0, os.path.join(ROOT, "heart-sounds-segmentation_b200"))
+    sys.path.insert(0, ROOT)
+    from hss.sharding import allreduce_counts, auroc_from_histograms, shard_range
+    from oracle import metrics_oracle as mo
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(logp.shape[0], rank, world)
+    # (on a GPU rank this histogram comes from hss.sharding.score_histograms = kernel hssb_auroc_hist)
+    hist = torch.from_numpy(mo.histograms(logp[lo:hi].numpy(), target[lo:hi].numpy(), 256))
+    hist = allreduce_counts(hist)
+    if rank == 0:
+        torch.save({"hist": hist, "auroc": auroc_from_histograms(hist)}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_auroc_histogram_allreduce(tmp_path):
+    """The AUROC state (score histograms, reference main.py:48,60) shards like the confusion counts: the all-reduced
+    histogram of two ranks equals the single-process one, and so does the AUROC computed from it."""
+    sys.path.insert(0, os.path.join(ROOT, "heart-sounds-segmentation_b200"))
+    from hss.sharding import auroc_from_histograms
+
+    from oracle import metrics_oracle as mo
+
+    g = torch.Generator().manual_seed(1)
+    target = torch.randint(0, 4, (9, 40), generator=g)
+    logits = torch.randn(9, 40, 4, generator=g) + 1.5 * torch.nn.functional.one_hot(target, 4)
+    logp = torch.log_softmax(logits, dim=2)
+    out = str(tmp_path / "hist.pt")
+    mp.spawn(_hist_worker, args=(2, _free_port(), logp, target, out), nprocs=2, join=True)
+    got = torch.load(out)
+    whole = torch.from_numpy(mo.histograms(logp.numpy(), target.numpy(), 256))
+    assert torch.equal(got["hist"], whole)
+    assert torch.equal(got["auroc"]["auroc_per_class"], auroc_from_histograms(whole)["auroc_per_class"])
+    assert abs(got["auroc"]["auroc"] - float(mo.auroc_binned(logp.numpy(), target.numpy(), 256).mean())) < 1e-12
