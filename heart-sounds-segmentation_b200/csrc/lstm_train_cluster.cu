@@ -65,15 +65,27 @@ train_fwd_cluster_kernel(float *__restrict__ gates, const float *__restrict__ w0
 
     // contraction role: thread (kq, c)
     const int kq = tid / CC, cc = tid % CC;
-    float pre[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
-        const long long t = dir ? (T - 1) : 0;
-        const float *g = gd + ((size_t)(b0 + er) * T + t) * CG4 + unit;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) pre[q] = __ldcs(g + q * CH);
-    }
+    // Global traffic stays off the barrier's critical path: a step's results are kept in registers and stored at the top of
+    // the NEXT step, its projected input is loaded there too -- both complete under the contraction, so the release of the
+    // cluster barrier only ever waits for the DSMEM stores (stores issued right before it cost ~2 us per step).
+    float res[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // i, f, g, o, c, h of the previous step
+    auto store_step = [&](long long step) {
+        const long long t = dir ? (T - 1 - step) : step;
+        const size_t row = (size_t)(b0 + er) * T + t;
+        float *g = gd + row * CG4 + unit;
+        __stcs(g, res[0]); __stcs(g + CH, res[1]); __stcs(g + 2 * CH, res[2]); __stcs(g + 3 * CH, res[3]);
+        __stcs(cd + row * CH + unit, res[4]);
+        __stcs(out + row * (2 * CH) + dir * CH + unit, res[5]);
+    };
     for (long long step = 0; step < T; ++step) {
         const long long t = dir ? (T - 1 - step) : step;
+        float pre[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            if (step > 0) store_step(step - 1);
+            const float *g = gd + ((size_t)(b0 + er) * T + t) * CG4 + unit;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pre[q] = __ldcs(g + q * CH);
+        }
         const float *hb = h_s + (step & 1) * CH * CR;
         float acc[CR];
 #pragma unroll
@@ -101,19 +113,7 @@ train_fwd_cluster_kernel(float *__restrict__ gates, const float *__restrict__ w0
             const float ig = sigmoid_f(a[0]), fg = sigmoid_f(a[1]), gg = tanhf(a[2]), og = sigmoid_f(a[3]);
             c_reg = fg * c_reg + ig * gg;
             h_reg = og * tanhf(c_reg);
-            if (live) {
-                const size_t row = (size_t)(b0 + er) * T + t;
-                float *g = gd + row * CG4 + unit;
-                __stcs(g, ig); __stcs(g + CH, fg); __stcs(g + 2 * CH, gg); __stcs(g + 3 * CH, og);
-                __stcs(cd + row * CH + unit, c_reg);
-                __stcs(out + row * (2 * CH) + dir * CH + unit, h_reg);
-                if (step + 1 < T) {                 // next step's projected input: in flight during the exchange and the contraction
-                    const long long tn = dir ? t - 1 : t + 1;
-                    const float *gn = gd + ((size_t)(b0 + er) * T + tn) * CG4 + unit;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) pre[q] = __ldcs(gn + q * CH);
-                }
-            }
+            res[0] = ig; res[1] = fg; res[2] = gg; res[3] = og; res[4] = c_reg; res[5] = h_reg;
             float *dst = h_s + ((step + 1) & 1) * CH * CR + unit * CR + er;
 #pragma unroll
             for (int p = 0; p < CCL; ++p) *cluster.map_shared_rank(dst, p) = h_reg;
@@ -121,6 +121,7 @@ train_fwd_cluster_kernel(float *__restrict__ gates, const float *__restrict__ w0
         cluster.sync();                             // h of this step is in every CTA's buffer; part_s may be overwritten
     }
     if (live) {
+        if (T > 0) store_step(T - 1);
         hn[((size_t)dir * B + b0 + er) * CH + unit] = T > 0 ? h_reg : h0[((size_t)dir * B + b0 + er) * CH + unit];
         cn[((size_t)dir * B + b0 + er) * CH + unit] = c_reg;
     }
