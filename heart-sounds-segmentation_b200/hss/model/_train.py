@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
+from torch.autograd.function import once_differentiable
 
 from .. import _lib
 
@@ -46,6 +47,7 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         return out, hn, cn
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, d_out, d_hn, d_cn):
         x, h0, c0, w_ih, w_hh, w_ih_r, w_hh_r, gates, cells, out = ctx.saved_tensors
         B, T, Fin = x.shape
