@@ -416,11 +416,13 @@ extern "C" int hssb_fsst_forward(const float *x, int64_t B, int64_t N, const flo
     return 0;
 }
 
-// Host entry point: grow-only device scratch shared by the calling process (guarded by a mutex).
+// Host entry point: grow-only device scratch shared by the calling process (guarded by a mutex), tied to the device it
+// was allocated on -- a call with another current device gets a fresh buffer.
 namespace {
 std::mutex g_host_mu;
 void *g_host_buf = nullptr;
 size_t g_host_cap = 0;
+int g_host_dev = -1;
 }  // namespace
 
 extern "C" int hssb_fsst_host(const float *x, int64_t B, int64_t N, double fs, const double *window,
@@ -442,11 +444,14 @@ extern "C" int hssb_fsst_host(const float *x, int64_t B, int64_t N, double fs, c
     const size_t total = x_bytes + win_bytes + align_up(out_bytes, 256) + ws_bytes;
 
     std::lock_guard<std::mutex> lock(g_host_mu);
-    if (total > g_host_cap) {
+    int dev = -1;
+    HSSB_CUDA_OK(cudaGetDevice(&dev));
+    if (total > g_host_cap || dev != g_host_dev) {
         if (g_host_buf) cudaFree(g_host_buf);
-        g_host_buf = nullptr; g_host_cap = 0;
+        g_host_buf = nullptr; g_host_cap = 0; g_host_dev = -1;
         HSSB_CUDA_OK(cudaMalloc(&g_host_buf, total));
         g_host_cap = total;
+        g_host_dev = dev;
     }
     char *base = static_cast<char *>(g_host_buf);
     float *dx = reinterpret_cast<float *>(base);
