@@ -178,3 +178,13 @@ extern "C" int hssb_model_forward(const hssb_model *m, const float *x, int64_t B
     if (!m->tc_ready) return simt_forward(m, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, st);
     return tc_forward(m, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, st);
 }
+
+extern "C" size_t hssb_lstm_workspace_bytes(const hssb_weights *w, int64_t B, int64_t T) { return hssb_model_workspace_bytes(w, B, T); }
+
+extern "C" int hssb_lstm_forward(const hssb_weights *w, const float *x, int64_t B, int64_t T, int F, const float *h0, const float *c0,
+                                 float *logp, int32_t *labels, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!w) return fail(HSSB_E_NULL, "hssb_lstm_forward: null weights");
+    if (F != w->F) return fail(HSSB_E_SHAPE, "hssb_lstm_forward: F=%d but the weights were packed for input_size %d", F, w->F);
+    return hssb_model_forward(w, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, 0, stream);
+}

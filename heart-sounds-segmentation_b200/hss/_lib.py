@@ -44,6 +44,8 @@ _SIGNATURES = {
     "hssb_model_destroy": (None, [c_void_p]),
     "hssb_model_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "hssb_model_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "hssb_lstm_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
+    "hssb_lstm_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hssb_debug_inproj": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hssb_debug_trace": (c_int, [c_void_p, c_int]),
     "hssb_debug_max_clusters": (c_int, []),

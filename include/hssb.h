@@ -126,6 +126,13 @@ int hssb_model_forward(const hssb_model *m, const float *x, int64_t B, int64_t T
                        const float *c0, float *logp, int32_t *labels, void *workspace,
                        size_t workspace_bytes, int impl, void *stream);
 
+/* The same two calls under the names SURVEY 8b sketches for this boundary (`hssb_weights` = the packed model handle):
+ * F must equal the model's input_size; impl = 0. */
+typedef hssb_model hssb_weights;
+size_t hssb_lstm_workspace_bytes(const hssb_weights *w, int64_t B, int64_t T);
+int hssb_lstm_forward(const hssb_weights *w, const float *x, int64_t B, int64_t T, int F, const float *h0, const float *c0,
+                      float *logp, int32_t *labels, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Diagnostic: layer-1 input projection only (kernel-level parity tests of K4).  impl 0 = tcgen05
  * kernel, 1 = SIMT kernel.  xproj [2,B*T,4H] f32 device, torch gate order.  workspace >=
  * 2*T*(B+1)*4H*4 + 2*B*T*256 bytes. */

@@ -60,6 +60,10 @@ def test_argument_errors_do_not_need_a_gpu(lib):
         _lib.check(700, "x")
     assert lib.hssb_fsst_workspace_bytes(2, 2000, 128, 4, 25, 2) >= 2 * 2 * 65 * 2000 * 8
     assert lib.hssb_fsst_stats_words(2, 2000) == 2 * 16 * 6 + 4
+    assert lib.hssb_lstm_forward(None, p, 1, 8, 44, p, p, p, None, None, 0, None) == -1      # HSSB_E_NULL (SURVEY 8b names)
+    assert lib.hssb_lstm_workspace_bytes(None, 1, 8) == 0
+    assert lib.hssb_auroc_hist(p, p, 8, 5000, p, None) == -2                                 # nbins outside [2, 4096]
+    assert lib.hssb_lstm_train_forward(None, p, p, p, p, 1, 8, 240, p, p, p, p, None) == -1
 
 
 def test_no_cuda_means_loud_failure(lib):
