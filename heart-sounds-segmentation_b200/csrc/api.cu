@@ -91,6 +91,57 @@ __global__ void confusion_kernel(const int32_t *__restrict__ pred, const int64_t
     if (threadIdx.x < 16 && local[threadIdx.x]) atomicAdd(&cm[threadIdx.x], (unsigned long long)local[threadIdx.x]);
 }
 
+// K7 complete ("confusion matrix (+ NLL sum, count) ... <= 32 scalars"): the whole metric state of one evaluation
+// step from the log-probabilities and targets -- 16 confusion counts, the summed loss and the element count -- as 18 doubles
+// (counts are exact below 2^53), so ONE all-reduce(SUM) merges ranks.  The loss term restates what the reference feeds its
+// logger (main.py:69-70,91-92,112-113): nn.CrossEntropyLoss on the permuted log-probabilities, i.e. a second log-softmax
+// over the four log-probabilities, lse(logp) - logp[target]; labels = first maximum of logp unless `pred` is given.
+__global__ void __launch_bounds__(256)
+metrics_kernel(const float4 *__restrict__ logp, const int32_t *__restrict__ pred, const int64_t *__restrict__ target, long long n,
+               double *__restrict__ state)
+{
+    __shared__ unsigned int local[16];
+    __shared__ double warp_nll[8];
+    __shared__ unsigned int warp_cnt[8];
+    if (threadIdx.x < 16) local[threadIdx.x] = 0;
+    __syncthreads();
+    double nll = 0.0;
+    unsigned int cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = target[i];
+        const float4 v = __ldcs(&logp[i]);
+        const float lp[4] = {v.x, v.y, v.z, v.w};
+        int p = 0;
+        if (pred) p = pred[i];
+        else {
+            float best = lp[0];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) if (lp[c] > best) { best = lp[c]; p = c; }
+        }
+        if (t >= 0 && t < 4) {
+            if (p >= 0 && p < 4) atomicAdd(&local[(int)t * 4 + p], 1u);
+            const float mx = fmaxf(fmaxf(lp[0], lp[1]), fmaxf(lp[2], lp[3]));
+            const float lse = mx + logf(expf(lp[0] - mx) + expf(lp[1] - mx) + expf(lp[2] - mx) + expf(lp[3] - mx));
+            nll += (double)(lse - lp[(int)t]);
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        nll += __shfl_xor_sync(0xffffffffu, nll, s);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    }
+    if ((threadIdx.x & 31) == 0) { warp_nll[threadIdx.x >> 5] = nll; warp_cnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 16 && local[threadIdx.x]) atomicAdd(&state[threadIdx.x], (double)local[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        unsigned int c = 0;
+        for (int w = 0; w < 8; ++w) { a += warp_nll[w]; c += warp_cnt[w]; }
+        if (c) { atomicAdd(&state[16], a); atomicAdd(&state[17], (double)c); }
+    }
+}
+
 // One-vs-rest score histograms for the binned multiclass AUROC (reference main.py:48,60: torchmetrics AUROC on the
 // class probabilities).  hist[c][target == c][bin(exp(logp[c]))] += 1 -- plain counters, so shards and ranks add up
 // (all-reduce) exactly like the confusion counts.  Block-private shared histograms, one warp-aggregated shared atomic
@@ -185,6 +236,22 @@ extern "C" int hssb_confusion(const int32_t *pred, const int64_t *target, int64_
     ProfScope prof("confusion", as_stream(stream));
     confusion_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pred, target, n, reinterpret_cast<unsigned long long *>(cm16));
     HSSB_LAUNCH_OK("confusion_kernel");
+    return 0;
+}
+
+extern "C" int hssb_metrics_update(const float *logp, const int32_t *pred, const int64_t *target, int64_t n, double *state18, void *stream)
+{
+    using namespace hssb;
+    if (!logp || !target || !state18) return fail(HSSB_E_NULL, "hssb_metrics_update: null pointer");
+    if (n < 0) return fail(HSSB_E_SHAPE, "hssb_metrics_update: n=%lld", (long long)n);
+    if ((reinterpret_cast<uintptr_t>(logp) & 15) != 0) return fail(HSSB_E_SHAPE, "hssb_metrics_update: logp must be 16-byte aligned");
+    if (n == 0) return 0;
+    if (int rc = require_sm100()) return rc;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ProfScope prof("metrics", as_stream(stream));
+    metrics_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(logp), pred, target, n, state18);
+    HSSB_LAUNCH_OK("metrics_kernel");
     return 0;
 }
 

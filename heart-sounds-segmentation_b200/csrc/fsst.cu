@@ -286,14 +286,12 @@ extern "C" int hssb_fsst_stft(const float *x, int64_t B, int64_t N, const float 
     ProfScope prof("stft_hop1", st);
     if (nwin == 128) {
         using C = StftCfg<8>;
-        static std::once_flag once;
-        std::call_once(once, [] { cudaFuncSetAttribute(stft_hop1_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES); });
+        HSSB_CUDA_OK(cudaFuncSetAttribute(stft_hop1_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));   // per device: set on every call
         dim3 grid((unsigned)((N + C::TT - 1) / C::TT), (unsigned)B);
         stft_hop1_kernel<8><<<grid, C::NT, C::SMEM_BYTES, st>>>(x, N, g, dg, (float2 *)Sg, (float2 *)Sdg);
     } else {
         using C = StftCfg<16>;
-        static std::once_flag once;
-        std::call_once(once, [] { cudaFuncSetAttribute(stft_hop1_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES); });
+        HSSB_CUDA_OK(cudaFuncSetAttribute(stft_hop1_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         dim3 grid((unsigned)((N + C::TT - 1) / C::TT), (unsigned)B);
         stft_hop1_kernel<16><<<grid, C::NT, C::SMEM_BYTES, st>>>(x, N, g, dg, (float2 *)Sg, (float2 *)Sdg);
     }
@@ -319,13 +317,14 @@ extern "C" int hssb_fsst_reassign(const hssb_c32 *Sg, const hssb_c32 *Sdg, int64
     if (int rc = require_sm100()) return rc;
     const int Kout = k_hi - k_lo + 1;
     const size_t smem = sizeof(float2) * (size_t)Kout * RT;
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static PerDeviceInt attr_set;                 // the opt-in shared-memory size is a per-device attribute
+    if (!attr_set.get()) {
         const int mx = (int)(sizeof(float2) * 129 * RT);
-        cudaFuncSetAttribute(if_reassign_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(if_reassign_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(if_reassign_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    });
+        HSSB_CUDA_OK(cudaFuncSetAttribute(if_reassign_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        HSSB_CUDA_OK(cudaFuncSetAttribute(if_reassign_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        HSSB_CUDA_OK(cudaFuncSetAttribute(if_reassign_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr_set.set(1);
+    }
     dim3 grid((unsigned)ntiles_reassign(N), (unsigned)B);
     const float bins_per_hz = (float)((double)nwin / (double)fs);
     const char *ru_env = getenv("HSSB_RU");
@@ -361,8 +360,7 @@ extern "C" int hssb_fsst_finish(const hssb_c32 *T, const double *stats, int64_t 
     }
     const int W = (mode == HSSB_MODE_STACK) ? 2 * Kt : Kt;
     const size_t smem = sizeof(float) * FT * (size_t)(W | 1);
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * FT * 259)); });
+    HSSB_CUDA_OK(cudaFuncSetAttribute(normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * FT * 259)));
     dim3 grid((unsigned)((N + FT - 1) / FT), (unsigned)B);
     ProfScope prof("normalise", st);
     normalise_kernel<<<grid, 256, smem, st>>>((const float2 *)T, final_stats, N, Kt, mode, out);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <atomic>
 #include "../../include/hssb.h"
 
 namespace hssb {
@@ -31,6 +32,16 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 int require_sm100();
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// One cached int per CUDA device (0 = not yet known).  Function attributes (opt-in shared memory) and occupancy figures
+// (co-resident clusters) belong to a device / context, not to the process: a second GPU used by the same process needs its own.
+constexpr int HSSB_MAX_DEVICES = 64;
+struct PerDeviceInt {
+    std::atomic<int> v[HSSB_MAX_DEVICES];
+    static int slot() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < HSSB_MAX_DEVICES) ? d : 0; }
+    int get() const { return v[slot()].load(std::memory_order_acquire); }
+    void set(int x) { v[slot()].store(x, std::memory_order_release); }
+};
 
 // Optional per-launch timing (hssb_prof_*): a pair of CUDA events recorded on the launching stream
 // around one kernel launch.  Costs nothing when disabled.

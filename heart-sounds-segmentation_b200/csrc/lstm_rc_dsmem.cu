@@ -641,7 +641,8 @@ template <int NB, int S, bool PAIR>
 static int max_resident_clusters(int *out)
 {
     using C = RcCfg<NB, S, PAIR>;
-    static int cached = 0;
+    static PerDeviceInt cache;
+    int cached = cache.get();
     if (!cached) {
         cudaError_t e = cudaFuncSetAttribute(tc_recurrent_kernel<NB, S, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_kernel)");
@@ -652,6 +653,7 @@ static int max_resident_clusters(int *out)
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         cached = n;
+        cache.set(n);
     }
     *out = cached;
     return 0;
@@ -690,7 +692,8 @@ static int launch_recurrent_pair(const RecurParams &prm_in, const __half *whh_fr
     prm.whh = whh_frag;
     prm.trace = g_trace_buf;
     prm.trace_steps = g_trace_steps;
-    static int max_clusters = 0;
+    static PerDeviceInt cached_clusters;
+    int max_clusters = cached_clusters.get();
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(C::THREADS);
@@ -709,6 +712,7 @@ static int launch_recurrent_pair(const RecurParams &prm_in, const __half *whh_fr
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_pair_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         max_clusters = n;
+        cached_clusters.set(n);
     }
     const int per = RP_NB * S;
     const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);

@@ -60,6 +60,9 @@ template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X>
 __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
 {
     using C = RmCfg<S, EW, FUSE_X>;
+    // range guard (tc_forward): the fused launch is skipped when the input left the fp16-split range, its stand-in when it did not.
+    // The flag is final before the launch, so every CTA of the grid takes the same branch (before any barrier / TMEM allocation).
+    if (p.skip_flag && ((*p.skip_flag != 0) == (p.skip_when != 0))) return;
     static_assert(EW == 1 || WARP_PUBLISH, "two warps per quadrant publish per warp");
     static_assert(!FUSE_X || WARP_PUBLISH, "the fused kernel reuses each warp's image piece as its output tile");
     extern __shared__ unsigned char smem_dyn[];
@@ -426,7 +429,8 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     prm.trace = g_trace_buf;
     prm.trace_steps = g_trace_steps;
     if (const char *e = getenv("HSSB_TRACE_LAYER")) if (atoi(e) != prm.layer) prm.trace = nullptr;
-    static int max_clusters = 0;
+    static PerDeviceInt cached_clusters;         // per device: the opt-in shared memory attribute is set where it is first used
+    int max_clusters = cached_clusters.get();
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(C::THREADS);
@@ -445,6 +449,7 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_mc_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         max_clusters = std::min(n, 16);
+        cached_clusters.set(max_clusters);
     }
     const int per = RP_NBH * S;
     const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);

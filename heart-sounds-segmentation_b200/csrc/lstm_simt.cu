@@ -217,8 +217,13 @@ int head_forward(const float *act, int64_t M, int H2, const float *lin_w, const 
     if (M == 0) return 0;
     long long blocks = (M + 15) / 16;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    const size_t smem = sizeof(float) * 4 * H2;
+    if (smem > 48 * 1024) {          // hidden sizes above 1536: opt in to the larger dynamic shared memory (per device, every call)
+        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(head_kernel)");
+    }
     ProfScope prof("head", st);
-    head_kernel<<<(unsigned)blocks, 256, sizeof(float) * 4 * H2, st>>>(act, M, H2, lin_w, lin_b, logp, labels);
+    head_kernel<<<(unsigned)blocks, 256, smem, st>>>(act, M, H2, lin_w, lin_b, logp, labels);
     HSSB_LAUNCH_OK("head_kernel");
     return 0;
 }

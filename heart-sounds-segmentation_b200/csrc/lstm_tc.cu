@@ -17,6 +17,7 @@
 // lstm_tc_common.cuh.
 #include "lstm_tc_common.cuh"
 #include <mutex>
+#include <cstring>
 
 namespace hssb {
 
@@ -59,17 +60,32 @@ static int make_tmap(CUtensorMap *m, CUtensorMapDataType dt, int rank, const voi
 // operand preparation
 // ------------------------------------------------------------------------------------------------
 // x[M,F] fp32 -> hi/lo fp16 planes [M,Kp] (zero padded columns)
+// range (nullable): {flag, bits of max|x|} -- the values are pre-scaled by 2^-range_exponent; run_flag (nullable): no-op while *run_flag == 0
 __global__ void split_planes_kernel(const float *__restrict__ x, long long M, int F, int Kp, __half *__restrict__ hi,
-                                    __half *__restrict__ lo)
+                                    __half *__restrict__ lo, const unsigned *__restrict__ range, const int *__restrict__ run_flag)
 {
+    if (run_flag && *run_flag == 0) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * Kp) return;
+    const float down = range ? pow2f(-range_exponent(range[1])) : 1.0f;
     const long long m = i / Kp;
     const int k = (int)(i % Kp);
     __half h = __float2half_rn(0.f), l = h;
-    if (k < F) split_f16(x[m * F + k], h, l);
+    if (k < F) split_f16(x[m * F + k] * down, h, l);
     hi[i] = h;
     lo[i] = l;
+}
+
+// max |x| of the model input as float bits (word 1 of `range`; non-negative floats order like unsigned integers, NaN sorts above inf)
+__global__ void input_amax_kernel(const float *__restrict__ x, long long n, unsigned *__restrict__ range, const int *__restrict__ run_flag)
+{
+    if (run_flag && *run_flag == 0) return;
+    unsigned m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(fabsf(__ldg(x + i))));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(range + 1, m);
 }
 
 // torch W_ih[960][Kin] (rows q*240 + unit) -> planes [dir*960 + g'][Kp]; bias[dir*960 + g'] = b_ih + b_hh
@@ -139,6 +155,8 @@ struct InprojParams {
     const float *bias;        // [1920]
     long long B, Bp;          // batch, and the row pitch of xproj in batch rows (see xproj_pitch)
     int debug;                // HSSB_IP_DEBUG bit 0: skip the global stores (timing experiment; results are wrong when set)
+    const unsigned *range;    // nullable: {flag, bits of max|x|} of a pre-scaled A operand -- the accumulator is scaled back by 2^e here
+    const int *run_flag;      // nullable: the launch is a no-op while *run_flag == 0 (stand-in path of the input-range guard)
     int k_real;               // true K rounded up to 16 (48 / 512)
     int T;
     int t_tiles;              // ceil(T/128)
@@ -150,6 +168,8 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
 {
     using C = IpCfg<IP_STAGES, EPI_WARPS>;
     constexpr int IP_OUT_BYTES = C::OUT_BYTES;
+    if (p.run_flag && *p.run_flag == 0) return;        // uniform over the grid; before any barrier / TMEM allocation
+    const float up = p.range ? pow2f(range_exponent(p.range[1])) : 1.0f;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char *stage_base = smem;
@@ -281,10 +301,10 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
                     for (int j = 0; j < 8; ++j) {
                         const float4 bj = bias[j];                 // shared-memory broadcast
                         float4 o;
-                        o.x = __uint_as_float(v[i][4 * j + 0]) + bj.x;
-                        o.y = __uint_as_float(v[i][4 * j + 1]) + bj.y;
-                        o.z = __uint_as_float(v[i][4 * j + 2]) + bj.z;
-                        o.w = __uint_as_float(v[i][4 * j + 3]) + bj.w;
+                        o.x = fmaf(__uint_as_float(v[i][4 * j + 0]), up, bj.x);      // up = 1 unless the A operand was pre-scaled
+                        o.y = fmaf(__uint_as_float(v[i][4 * j + 1]), up, bj.y);
+                        o.z = fmaf(__uint_as_float(v[i][4 * j + 2]), up, bj.z);
+                        o.w = fmaf(__uint_as_float(v[i][4 * j + 3]), up, bj.w);
                         *reinterpret_cast<float4 *>(ob + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;   // 128B xor swizzle: conflict free both ways
                     }
                     __syncwarp();
@@ -352,8 +372,11 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
     // the raw torch tensors may be host pointers: stage them through a temporary device buffer
     float *tmp = nullptr;
     const size_t tmp_floats = (size_t)TC_G * (2 * TC_H) + 2 * TC_G;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&tmp), sizeof(float) * tmp_floats, st);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&tmp), sizeof(float) * (tmp_floats + 2), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tc_pack)");
+    // max |w| over the LSTM weights (word 1): outside the fp16-split range the model keeps to the generic fp32 kernels
+    unsigned *w_range = reinterpret_cast<unsigned *>(tmp + tmp_floats);
+    if ((e = cudaMemsetAsync(w_range, 0, 8, st)) != cudaSuccess) { cudaFreeAsync(tmp, st); return cuda_fail(e, "cudaMemsetAsync(tc_pack)"); }
     int rc = 0;
     m->tc_wih0_frag = reinterpret_cast<__half *>(base + off);
     off += align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 64, 256);
@@ -378,6 +401,7 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
                 rc = cuda_fail(e, "cudaMemcpyAsync(tc_pack)");
                 break;
             }
+            input_amax_kernel<<<64, 256, 0, st>>>(w, (long long)TC_G * kin[l], w_range, nullptr);
             pack_wih_kernel<<<TC_G, 128, 0, st>>>(w, bi, bh, kin[l], Kp, d, l, hi, lo, m->tc_bias[l]);
             if (l == 0) pack_wih0_frag_kernel<<<8 * 128, 64, 0, st>>>(w, bi, bh, kin[0], d, m->tc_wih0_frag, m->tc_bias0_frag);
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "pack_wih_kernel"); break; }
@@ -385,6 +409,7 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
                 rc = cuda_fail(e, "cudaMemcpyAsync(tc_pack w_hh)");
                 break;
             }
+            input_amax_kernel<<<64, 256, 0, st>>>(w, (long long)TC_G * TC_H, w_range, nullptr);
             pack_whh_kernel<<<8 * 128, 128, 0, st>>>(w, d, 0, m->tc_whh[l]);
             pack_whh_kernel<<<8 * 128, 128, 0, st>>>(w, d, 1, m->tc_whh_frag[l]);
             if ((e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e, "pack_whh_kernel");
@@ -400,9 +425,14 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
             if ((e2 = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e2, "pack_linw_kernel");
         }
     }
+    unsigned w_bits[2] = {0, 0};
+    if (!rc && ((e = cudaMemcpyAsync(w_bits, w_range, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess))
+        rc = cuda_fail(e, "tc_pack: weight range");
     cudaFreeAsync(tmp, st);
     if (rc) return rc;
-    m->tc_ready = true;
+    float w_max;
+    memcpy(&w_max, &w_bits[1], 4);
+    m->tc_ready = (w_max <= TC_SPLIT_SAFE);      // false for larger / non-finite weights: hssb_model_forward then runs the fp32 SIMT kernels
     return 0;
 }
 
@@ -419,7 +449,8 @@ static int launch_inproj(const InprojParams &prm, int n_items, const char *name,
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static int max_clusters = 0;
+    static PerDeviceInt cached_clusters;
+    int max_clusters = cached_clusters.get();
     if (!max_clusters) {
         cudaError_t e = cudaFuncSetAttribute(tc_inproj_kernel<STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_inproj_kernel)");
@@ -429,6 +460,7 @@ static int launch_inproj(const InprojParams &prm, int n_items, const char *name,
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_inproj_kernel)");
         if (n < 1) return fail(HSSB_E_DEVICE, "device cannot host an input-projection cluster");
         max_clusters = n;
+        cached_clusters.set(n);
     }
     cfg.gridDim = dim3((unsigned)(IP_CL * std::min(max_clusters, n_items)));
     ProfScope prof(name, st);
@@ -439,9 +471,11 @@ static int launch_inproj(const InprojParams &prm, int n_items, const char *name,
 
 // One layer's input projection on the tensor cores.  a_hi/a_lo: [B*T][pitch] fp16 planes.
 int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *a_lo, int pitch_elems, int64_t B, int64_t T,
-              float *xproj /*[2][T][B][960]*/, cudaStream_t st)
+              float *xproj /*[2][T][B][960]*/, cudaStream_t st, const unsigned *range = nullptr, const int *run_flag = nullptr)
 {
     InprojParams prm;
+    prm.range = range;
+    prm.run_flag = run_flag;
     const int Kp = kp_of_layer(layer, m->F);
     const int kreal = kreal_of_layer(layer, m->F);
     {
@@ -521,8 +555,10 @@ __global__ void pack_wih0_frag_kernel(const float *__restrict__ w, const float *
 
 // x[B][T][F] fp32 -> hi/lo fp16 planes [t][32-column tile][chunk 8][32 cols][8 features] (zero padded features and columns): the
 // K-major operand of the fused projection for one (step, sub-tile) is then one contiguous run, fetched by a single bulk copy
+// *range_flag (nullable) is raised when some |x| > TC_SPLIT_SAFE or x is not finite: the fused recurrence then stands down for the
+// pre-scaled projection path (tc_forward)
 __global__ void split_planes_tiled_kernel(const float *__restrict__ x, long long B, long long T, int F, __half *__restrict__ hi,
-                                          __half *__restrict__ lo)
+                                          __half *__restrict__ lo, int *__restrict__ range_flag)
 {
     const long long tiles = (B + RP_NBH - 1) / RP_NBH;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((t * tiles + tile) * 8 + chunk) * 32 + col
@@ -531,14 +567,20 @@ __global__ void split_planes_tiled_kernel(const float *__restrict__ x, long long
     const long long tile = (i / (8 * RP_NBH)) % tiles, t = i / (8 * RP_NBH * tiles);
     const long long b = tile * RP_NBH + col;
     __half h[8], l[8];
+    bool out_of_range = false;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = 8 * c + e;
         h[e] = l[e] = __float2half_rn(0.f);
-        if (k < F && b < B) split_f16(__ldg(x + (b * T + t) * F + k), h[e], l[e]);
+        if (k < F && b < B) {
+            const float v = __ldg(x + (b * T + t) * F + k);
+            out_of_range |= !(fabsf(v) <= TC_SPLIT_SAFE);
+            split_f16(v, h[e], l[e]);
+        }
     }
     *reinterpret_cast<uint4 *>(hi + i * 8) = *reinterpret_cast<const uint4 *>(h);
     *reinterpret_cast<uint4 *>(lo + i * 8) = *reinterpret_cast<const uint4 *>(l);
+    if (out_of_range && range_flag) *range_flag = 1;          // benign race: every writer stores the same value
 }
 
 // linear.weight[4][480] -> slot layout [4][512]
@@ -554,13 +596,15 @@ int g_trace_steps = 0;
 // One layer's recurrence for batch columns [0, B): picks the sub-tile geometry from B.
 static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const float *h0, const float *c0, float *hn, float *cn,
                         __half *out_hi, __half *out_lo, float *out_f32, unsigned char *gather, int64_t B, int64_t T, cudaStream_t st,
-                        const __half *x_hi = nullptr, const __half *x_lo = nullptr)
+                        const __half *x_hi = nullptr, const __half *x_lo = nullptr, const int *skip_flag = nullptr, int skip_when = 0)
 {
     // x_hi / x_lo != nullptr: layer 1 with the input projection fused into the recurrence (tile-major x planes, no xproj)
     const bool fused = x_hi != nullptr;
     RecurParams prm = {};
     prm.gather = gather;
     prm.layer = layer;
+    prm.skip_flag = skip_flag;
+    prm.skip_when = skip_when;
     if (fused) {
         prm.x_hi = x_hi;
         prm.x_lo = x_lo;
@@ -608,6 +652,7 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         else if (per_group <= 64) { nb = 32; s = 2; pair = 4; }
         else { nb = 32; s = 3; pair = 3; }
         if (fused && force_nb) return fail(HSSB_E_MODE, "HSSB_RC_GEOM cannot be combined with the fused projection");
+        if (skip_flag && !(nb == 32 && pair >= 2)) return fail(HSSB_E_MODE, "the input-range guard needs the multicast recurrence");
         // pair: 0 = DSMEM all-gather (K5), 1 = its cta_group::2 mode or, with nb = 64, the CTA-pair kernel (K5p); 2..4 = K5m variants
         int rc, done = 0;
         if (nb == 32 && pair >= 2) rc = rc_mc_launch(s, pair, fused, prm, m->tc_whh_frag[layer], rem, &done, xproj, st);
@@ -620,7 +665,7 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
 }
 
 namespace {
-struct TcWs { size_t xhi, xlo, xproj, o1hi, o1lo, out2, hn, cn, gather, total; };
+struct TcWs { size_t xhi, xlo, xproj, o1hi, o1lo, out2, hn, cn, gather, range, total; };
 TcWs tc_ws_layout(int64_t B, int64_t T)
 {
     const size_t M = (size_t)B * T;
@@ -636,6 +681,7 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
     w.hn = off;    off += align_up(sizeof(float) * 2 * B * TC_H, 1024);
     w.cn = off;    off += align_up(sizeof(float) * 2 * B * TC_H, 1024);
     w.gather = off; off += TC_GATHER_BYTES;
+    w.range = off; off += 256;                                     // input-range guard: {flag, bits of max|x|}
     w.total = off;
     return w;
 }
@@ -661,23 +707,32 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     // HSSB_FUSE_X=0 or a forced recurrence geometry selects the separate projection kernel instead.
     const char *fx = getenv("HSSB_FUSE_X");
     const bool fused = m->F <= 16 * RX_KSTEPS && !getenv("HSSB_RC_GEOM") && !(fx && fx[0] == '0');
+    // Input-range guard.  The fp16 hi/lo split is exact (22 bits) for |x| <= 65504; beyond that hi would be inf where the reference
+    // (plain fp32, segmenter.py:80) is finite.  The separate-projection path therefore pre-scales x by 2^-e (e from the tensor's
+    // max-abs, 0 while |x| < 2^15) and K4 scales the fp32 accumulator back by 2^e: exact for every finite input.  The fused
+    // recurrence cannot scale one operand of its mixed accumulator, so its split kernel only raises a flag when an input leaves
+    // the safe range; the fused launch is then a no-op and the pre-scaled path, launched behind it (a no-op otherwise), runs.
+    int *range_flag = reinterpret_cast<int *>(base + w.range);
+    unsigned *range = reinterpret_cast<unsigned *>(range_flag);
+    HSSB_CUDA_OK(cudaMemsetAsync(range_flag, 0, 8, st));
+    const int *standin = fused ? range_flag : nullptr;             // stand-in kernels run only when the flag was raised
     if (fused) {
         {
             ProfScope prof("split_planes", st);
             const long long n = T * ((B + RP_NBH - 1) / RP_NBH) * 8 * RP_NBH;
-            split_planes_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, B, T, m->F, xhi, xlo);
+            split_planes_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, B, T, m->F, xhi, xlo, range_flag);
             HSSB_LAUNCH_OK("split_planes_tiled_kernel");
         }
-        if (int rc = tc_recurrent(m, 0, nullptr, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, xhi, xlo)) return rc;
-    } else {
-        {
-            ProfScope prof("split_planes", st);
-            split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo);
-            HSSB_LAUNCH_OK("split_planes_kernel");
-        }
-        if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st)) return rc;
-        if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st)) return rc;
+        if (int rc = tc_recurrent(m, 0, nullptr, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, xhi, xlo, range_flag, 1)) return rc;
     }
+    {
+        ProfScope prof(fused ? "range_standin" : "split_planes", st);
+        input_amax_kernel<<<148 * 4, 256, 0, st>>>(x, M * m->F, range, standin);
+        split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo, range, standin);
+        HSSB_LAUNCH_OK("split_planes_kernel");
+    }
+    if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st, range, standin)) return rc;
+    if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, nullptr, nullptr, standin, 0)) return rc;
     if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st)) return rc;
     if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, st)) return rc;
     return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st);
@@ -725,7 +780,7 @@ extern "C" int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B,
     if (!workspace || workspace_bytes < need) return fail(HSSB_E_WORKSPACE, "hssb_debug_inproj: workspace %zu < %zu", workspace_bytes, need);
     float *raw = static_cast<float *>(workspace);
     __half *hi = reinterpret_cast<__half *>(raw + raw_floats), *lo = hi + M * 64;
-    split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, hi, lo);
+    split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, hi, lo, nullptr, nullptr);
     HSSB_LAUNCH_OK("split_planes_kernel");
     if (int rc = tc_inproj(m, 0, hi, lo, 64, B, T, raw, st)) return rc;
     unpermute_xproj_kernel<<<(unsigned)((2 * M * TC_G + 255) / 256), 256, 0, st>>>(raw, B, xproj_pitch(B), T, xproj);

@@ -31,6 +31,20 @@ __device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo)
     lo = __float2half_rn(v - __half2float(hi));
 }
 
+// Range of the split: hi = fp16(v) is finite for |v| <= 65504.  Hidden states are in (-1, 1) and weights are checked when they are
+// packed, so only the model INPUT can leave that range (un-normalised features): inputs whose magnitude exceeds TC_SPLIT_SAFE are
+// pre-scaled by a power of two taken from the tensor's max-abs (exact in fp32) and the projection result is scaled back in the
+// fp32 epilogue of K4 -- see tc_forward.  range word 0: "some |x| > TC_SPLIT_SAFE (or non-finite)", word 1: bits of max |x|.
+constexpr float TC_SPLIT_SAFE = 32768.0f;
+// exponent e >= 0 such that max|x| * 2^-e < 2^15 (0 while the input is in range); 2^-e and 2^e as floats
+__device__ __forceinline__ int range_exponent(unsigned amax_bits)
+{
+    const int ex = (int)((amax_bits >> 23) & 255u) - 127;       // floor(log2(max|x|)); 128 for inf / nan
+    const int e = ex - 14;
+    return e < 0 ? 0 : (e > 110 ? 110 : e);
+}
+__device__ __forceinline__ float pow2f(int e) { return __uint_as_float((unsigned)(127 + e) << 23); }
+
 
 // recurrence geometry shared by all variants: 8 CTAs per cluster, 30 hidden units (120 gate rows) per CTA
 constexpr int RC_CL = 8;            // CTAs per cluster
@@ -65,6 +79,9 @@ struct RecurParams {
     unsigned char *gather;      // multicast kernel: L2 scratch [cluster][rank][S][2][4 KB] of the all-gather
     int debug;                  // HSSB_RC_DEBUG knock-out switches for timing experiments (results are wrong when set)
     int layer;
+    // input-range guard of the fused layer-1 path: the launch is a no-op when (*skip_flag != 0) == skip_when (nullptr: always runs)
+    const int *skip_flag;
+    int skip_when;
 };
 
 // trace events (per step, per sub-tile): see scripts/trace_recurrent.py

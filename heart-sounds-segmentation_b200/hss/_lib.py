@@ -52,6 +52,7 @@ _SIGNATURES = {
     "hssb_lstm_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hssb_lstm_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "hssb_confusion": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "hssb_metrics_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hssb_auroc_hist": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "hssb_prof_enable": (c_int, [c_int]),
     "hssb_prof_read": (c_int, [c_char_p, c_size_t]),
@@ -102,6 +103,27 @@ def stream_ptr() -> int:
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+def cached_workspace(cache: dict, dev, need: int):
+    """Grow-only scratch tensor for ``(device, current stream)``.
+
+    Keyed by stream because the kernels of two concurrent calls on different CUDA streams (or threads) must not share
+    scratch; an outgrown buffer is handed back to the caching allocator with ``record_stream`` so that it is not reused
+    while work queued on this stream may still touch it."""
+    import torch
+
+    stream = torch.cuda.current_stream(dev)
+    key = (dev.index, stream.cuda_stream)
+    ws = cache.get(key)
+    if ws is None or ws.numel() < need:
+        if ws is not None:
+            ws.record_stream(stream)
+        cache.pop(key, None)
+        ws = None
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        cache[key] = ws
+    return ws
 
 
 def prof_enable(on: bool) -> None:

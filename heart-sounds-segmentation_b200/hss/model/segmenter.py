@@ -53,7 +53,7 @@ class HeartSoundSegmenter(nn.Module):
         self._handle = None           # hssb_model* (ctypes.c_void_p)
         self._handle_key = None
         self._state_dev: dict = {}
-        self._workspace: dict[int, torch.Tensor] = {}
+        self._workspace: dict = {}
 
     # ------------------------------------------------------------------------------------------
     def _params_in_abi_order(self):
@@ -74,6 +74,18 @@ class HeartSoundSegmenter(nn.Module):
             self._release()
         except Exception:
             pass
+
+    # The packed-weights handle, the device copies of h0 / c0 and the workspaces belong to this object and this process:
+    # copies and pickles (copy.deepcopy, torch.save(model), spawn-based strategies) start without them and repack lazily,
+    # like the plain reference module, which can be copied and pickled freely.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handle"], state["_handle_key"], state["_state_dev"], state["_workspace"] = None, None, {}, {}
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._handle, self._handle_key, self._state_dev, self._workspace = None, None, {}, {}
 
     def _packed(self, dev: torch.device):
         """(Re)pack the parameters into HBM operands when they changed (load_state_dict, optimiser step)."""
@@ -148,12 +160,7 @@ class HeartSoundSegmenter(nn.Module):
             labels = torch.empty((B, T), dtype=torch.int32, device=dev) if want_labels else None
             if B and T:
                 need = lib.hssb_model_workspace_bytes(handle, B, T)
-                ws = self._workspace.get(dev.index)
-                if ws is None or ws.numel() < need:
-                    ws = None
-                    self._workspace.pop(dev.index, None)
-                    ws = torch.empty(need, dtype=torch.uint8, device=dev)
-                    self._workspace[dev.index] = ws
+                ws = _lib.cached_workspace(self._workspace, dev, need)
                 rc = lib.hssb_model_forward(
                     handle, xd.data_ptr(), B, T, h0.data_ptr(), c0.data_ptr(),
                     logp.data_ptr() if want_logp else None, labels.data_ptr() if want_labels else None,

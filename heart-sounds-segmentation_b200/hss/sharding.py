@@ -44,11 +44,54 @@ def allreduce_counts(cm: torch.Tensor) -> torch.Tensor:
     return cm
 
 
+def metric_state(logp: torch.Tensor, target: torch.Tensor, labels: torch.Tensor | None = None,
+                 state: torch.Tensor | None = None) -> torch.Tensor:
+    """The whole metric state of an evaluation step as 18 float64 scalars (CUDA kernel ``hssb_metrics_update``):
+    ``state[:16]`` = confusion counts ``cm[target, pred]``, ``state[16]`` = summed loss terms, ``state[17]`` = elements.
+
+    The loss is what the reference logs as ``train_loss`` / ``val_loss`` / ``test_loss`` (main.py:69-70,91-92,112-117):
+    ``nn.CrossEntropyLoss`` on the permuted log-probabilities.  Pass ``state`` to accumulate over several steps on the
+    device; ``allreduce_counts`` merges ranks with one all-reduce; ``metrics_from_state`` finalises.
+    """
+    if not logp.is_cuda:
+        raise RuntimeError("metric_state runs on the GPU (no CPU fallback)")
+    if logp.shape[-1] != 4:
+        raise ValueError(f"expected [..., 4] log-probabilities, got {tuple(logp.shape)}")
+    logp = logp.to(torch.float32).contiguous().reshape(-1, 4)
+    target = target.to(device=logp.device, dtype=torch.int64).contiguous().reshape(-1)
+    if logp.shape[0] != target.numel():
+        raise ValueError("logp / target size mismatch")
+    if labels is not None:
+        labels = labels.to(device=logp.device, dtype=torch.int32).contiguous().reshape(-1)
+        if labels.numel() != target.numel():
+            raise ValueError("labels / target size mismatch")
+    if state is None:
+        state = torch.zeros(18, dtype=torch.float64, device=logp.device)
+    elif state.shape != (18,) or state.dtype != torch.float64 or state.device != logp.device or not state.is_contiguous():
+        raise ValueError("state must be a contiguous float64 [18] tensor on the device of logp")
+    with torch.cuda.device(logp.device):
+        rc = _lib.lib().hssb_metrics_update(logp.data_ptr(), labels.data_ptr() if labels is not None else None, target.data_ptr(),
+                                            target.numel(), state.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "hssb_metrics_update")
+    return state
+
+
+def metrics_from_state(state: torch.Tensor) -> dict:
+    """Metrics of ``metrics_from_counts`` plus ``loss`` (mean cross-entropy) from an (all-reduced) 18-scalar state."""
+    st = state.detach().to(torch.float64).cpu()
+    out = metrics_from_counts(st[:16].round().to(torch.int64).reshape(4, 4))
+    out["loss"] = float(st[16] / st[17]) if float(st[17]) > 0 else float("nan")
+    out["count"] = int(st[17].round())
+    return out
+
+
 def metrics_from_counts(cm: torch.Tensor) -> dict:
     """Per-class and macro accuracy(=recall) / precision / F1 from ``cm[target, pred]``.
 
     Same definitions as the torchmetrics multiclass collection of reference main.py:36-62
-    (``Accuracy(average=None)`` is per-class recall; zero-division -> 0).
+    (``Accuracy(average=None)`` is per-class recall; zero-division -> 0).  ``average="macro"`` follows torchmetrics'
+    ``_adjust_weights_safe_divide``: a class that occurs neither in the targets nor in the predictions
+    (tp + fp + fn == 0) gets weight 0, so the macro figures are means over the classes that are present.
     """
     cm = cm.to(torch.float64).cpu()
     tp = cm.diag()
@@ -58,10 +101,16 @@ def metrics_from_counts(cm: torch.Tensor) -> dict:
     precision = torch.where(predicted > 0, tp / predicted.clamp(min=1), torch.zeros_like(tp))
     denom = precision + recall
     f1 = torch.where(denom > 0, 2 * precision * recall / denom.clamp(min=1e-300), torch.zeros_like(tp))
+    present = ((support + predicted) > 0).to(torch.float64)
+    n_present = present.sum().clamp(min=1)
+
+    def macro(v):
+        return float((v * present).sum() / n_present)
+
     return {
         "accuracy_per_class": recall, "recall_per_class": recall, "precision_per_class": precision, "f1_per_class": f1,
-        "accuracy": float(recall.mean()), "recall": float(recall.mean()), "precision": float(precision.mean()),
-        "f1": float(f1.mean()), "micro_accuracy": float(tp.sum() / cm.sum().clamp(min=1)),
+        "accuracy": macro(recall), "recall": macro(recall), "precision": macro(precision),
+        "f1": macro(f1), "micro_accuracy": float(tp.sum() / cm.sum().clamp(min=1)),
     }
 
 

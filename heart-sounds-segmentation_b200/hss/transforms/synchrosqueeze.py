@@ -49,7 +49,7 @@ class FSST:
         dw = derivative_window(w, fs)
         self._host_windows = torch.from_numpy(np.concatenate([w, dw]).astype(np.float32))
         self._dev_windows: dict[int, torch.Tensor] = {}
-        self._workspace: dict[int, torch.Tensor] = {}
+        self._workspace: dict = {}
         if truncate_freq:
             self._k_lo, self._k_hi = band_rows(fs, self._nwin, truncate_freq)
         else:
@@ -109,12 +109,7 @@ class FSST:
                 win = self._host_windows.to(dev)
                 self._dev_windows[dev.index] = win
             need = lib.hssb_fsst_workspace_bytes(B, N, self._nwin, self._k_lo, self._k_hi, self._mode)
-            ws = self._workspace.get(dev.index)
-            if ws is None or ws.numel() < need:
-                ws = None
-                self._workspace.pop(dev.index, None)
-                ws = torch.empty(need, dtype=torch.uint8, device=dev)
-                self._workspace[dev.index] = ws
+            ws = _lib.cached_workspace(self._workspace, dev, need)
             rc = lib.hssb_fsst_forward(
                 xd.data_ptr(), B, N, win.data_ptr(), win.data_ptr() + 4 * self._nwin, self._nwin,
                 float(self.fs), self._k_lo, self._k_hi, self._mode, out.data_ptr(),

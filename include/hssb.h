@@ -171,6 +171,14 @@ int hssb_lstm_train_backward(float *gates, const float *cells, const float *w_hh
  * ------------------------------------------------------------------------------------------ */
 int hssb_confusion(const int32_t *pred, const int64_t *target, int64_t n, int64_t *cm16, void *stream);
 
+/* The complete metric state of one evaluation step (main.py:36-62 counters + the loss logged at main.py:69-70,91-92,
+ * 112-117) in <= 32 scalars: state18 [18] float64 device = 16 confusion counts cm[target][pred] (exact integers), the summed
+ * nn.CrossEntropyLoss terms of the permuted log-probabilities (lse(logp) - logp[target]) and the number of elements.
+ * Accumulates (caller zeroes); one all-reduce(SUM) of the 18 doubles merges ranks; mean loss = state[16] / state[17].
+ * logp [n,4] f32 device, 16-byte aligned; pred [n] int32 device or NULL (labels = first maximum of logp); rows with a target
+ * outside 0..3 are skipped. */
+int hssb_metrics_update(const float *logp, const int32_t *pred, const int64_t *target, int64_t n, double *state18, void *stream);
+
 /* One-vs-rest score histograms for the binned AUROC of main.py:48,60 (torchmetrics multiclass AUROC on the class
  * probabilities).  logp [n,4] f32 device (log-probabilities, 16-byte aligned), target [n] int64 device (rows with a
  * target outside 0..3 are skipped); hist [4][2][nbins] int64 device,

@@ -65,6 +65,17 @@ static void dft_any(const cplx *in, cplx *out, int n, const cplx *tw_full)
 
 static double round_half_away(double v) { return v < 0.0 ? -floor(-v + 0.5) : floor(v + 0.5); }
 
+/* Thread count of the OpenMP loops over windows; n <= 0 leaves it alone.  (Under torchrun the environment carries
+ * OMP_NUM_THREADS=1: the bench sets the count explicitly instead of inheriting it.) */
+void hsso_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int hsso_num_threads(void)
 {
 #ifdef _OPENMP

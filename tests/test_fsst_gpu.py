@@ -212,8 +212,12 @@ def test_frames_of_a_recording_equal_per_frame_calls(lib):
     out = f.frames(x.cuda(), 1000, 2000)
     frames, _ = frame_signal(x, torch.zeros(x.shape[0], dtype=torch.int64), 1000, 2000)
     assert out.shape == (len(frames), 2000, 44) and len(frames) == 7
+    w = fo.reference_window()
     for i, fr in enumerate(frames):
-        assert torch.equal(out[i].cpu(), f(fr))          # CPU-in -> CPU-out per-item path, same kernels
+        # against the ORACLE on every frame (each frame zero-padded and z-scored on its own, heart_sounds.py:160-169) ...
+        ref = fo.fsst_features(fr[:, 0].numpy(), 1000, w, stack=True, truncate_freq=(25, 200))
+        assert np.abs(out[i].cpu().numpy() - ref).max() < 2e-4
+        assert torch.equal(out[i].cpu(), f(fr))          # ... and the CPU-in -> CPU-out per-item path gives the same bits
 
 
 def test_config5_long_windows_at_2khz(lib):
@@ -243,7 +247,66 @@ def test_recording_to_frames_equals_the_dataset_loop(lib):
     feats, labels = recording_to_frames(x, y, f)
     frames, lab = frame_signal(x, y - 1, 1000, 2000)
     assert feats.shape == (len(frames), 2000, 44) and labels.shape == (len(frames), 2000) and feats.is_cuda
+    w = fo.reference_window()
     for i, (fr, lb) in enumerate(zip(frames, lab)):
+        ref = fo.fsst_features(fr[:, 0].numpy(), 1000, w, stack=True, truncate_freq=(25, 200))      # the oracle, per frame
+        assert np.abs(feats[i].cpu().numpy() - ref).max() < 2e-4
         assert torch.equal(feats[i].cpu(), f(fr)) and torch.equal(labels[i].cpu(), lb[:, 0])
     short = recording_to_frames(x[:1500], y[:1500], f)
     assert short[0].shape[0] == 0 and short[1].shape[0] == 0
+
+
+def test_config1_single_csv_recording_as_written(lib):
+    """BASELINE config 1 as SURVEY 8d writes it: tests/data/0001.csv (35 000 rows, seed 68) -> 33 frames of 2000 at stride 1000
+    (reference test/test_dataset.py:37,67-69) through (a) load_recording_csv -> recording_to_frames, one device call, and
+    (b) the reference dataset's own loop -- _load_file, frame_signal(x, y - 1), per-frame transform on CPU tensors
+    (heart_sounds.py:155-169,193-201).  Every frame is checked against the float64 oracle; (a) and (b) give the same bits."""
+    import pandas as pd
+
+    from hss.transforms import FSST
+    from hss.utils import frame_signal, load_recording_csv, recording_to_frames
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "0001.csv")
+    x, y = load_recording_csv(path)
+    df = pd.read_csv(path, skiprows=1, names=["Signals", "Labels"])                    # heart_sounds.py:193-197
+    assert torch.equal(x, torch.tensor(df.loc[:, "Signals"].to_numpy(), dtype=torch.float32))
+    assert torch.equal(y, torch.tensor(df.loc[:, "Labels"].to_numpy(), dtype=torch.int64))
+    assert x.shape == (35_000,) and int(y.min()) == 1 and int(y.max()) == 4
+
+    w = fo.reference_window()
+    f = FSST(1000, window=w, truncate_freq=(25, 200), stack=True)
+    feats, labels = recording_to_frames(x, y, f)
+    assert feats.shape == (33, 2000, 44) and labels.shape == (33, 2000) and labels.dtype == torch.int64
+    frames, labs = frame_signal(x, y - 1, 1000, 2000)
+    assert len(frames) == 33
+    worst = 0.0
+    for i, (fr, lb) in enumerate(zip(frames, labs)):
+        item = f(fr)                                                                    # CPU tensor [2000, 1] in, CPU [2000, 44] out
+        assert item.shape == (2000, 44) and not item.is_cuda and lb.squeeze(1).shape == (2000,)
+        ref = fo.fsst_features(fr[:, 0].numpy(), 1000, w, stack=True, truncate_freq=(25, 200))
+        worst = max(worst, float(np.abs(item.numpy() - ref).max()))
+        assert torch.equal(feats[i].cpu(), item) and torch.equal(labels[i].cpu(), lb.squeeze(1))
+    assert worst < 2e-4, worst
+    print("config 1: 33 frames, max |feature - oracle| =", worst)
+
+
+def test_second_device_after_first(lib):
+    """Function attributes (opt-in shared memory) and cluster occupancy are per device: FSST (nwin 128 and 256) and the model
+    on cuda:1 after cuda:0 in one process give the same results."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from hss.model.segmenter import HeartSoundSegmenter
+    from hss.transforms import FSST
+
+    x = torch.from_numpy(fo.synth_pcg_batch(3, 2000, seed=3))
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(dev):
+            f128 = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True)
+            f256 = FSST(1000, window=np.kaiser(256, 10.0))
+            torch.manual_seed(1)
+            m = HeartSoundSegmenter(input_size=44, batch_size=3).eval()
+            feats = f128.batch(x.to(dev))
+            outs.append((feats.cpu(), f256.batch(x.to(dev)).cpu(), m(feats).cpu()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

@@ -101,6 +101,27 @@ def test_metrics_from_counts():
     assert metrics_from_counts(torch.zeros(4, 4))["f1"] == 0.0
 
 
+def test_macro_average_skips_absent_classes():
+    """torchmetrics average="macro" (reference main.py:49-56) gives weight 0 to a class with tp + fp + fn == 0: a shard in which
+    class 3 occurs neither in the targets nor in the predictions averages over the three classes that are present."""
+    from hss.sharding import metrics_from_counts, metrics_from_state
+
+    cm = torch.tensor([[8, 2, 0, 0], [1, 9, 0, 0], [0, 5, 5, 0], [0, 0, 0, 0]])
+    m = metrics_from_counts(cm)
+    rec = [0.8, 0.9, 0.5]
+    prec = [8 / 9, 9 / 16, 1.0]
+    f1 = [2 * p * r / (p + r) for p, r in zip(prec, rec)]
+    assert abs(m["recall"] - sum(rec) / 3) < 1e-12 and abs(m["accuracy"] - sum(rec) / 3) < 1e-12
+    assert abs(m["precision"] - sum(prec) / 3) < 1e-12 and abs(m["f1"] - sum(f1) / 3) < 1e-12
+    # a class that is predicted but never a target IS present (fp > 0) and counts with recall 0
+    cm2 = torch.tensor([[8, 2, 0, 1], [1, 9, 0, 0], [0, 5, 5, 0], [0, 0, 0, 0]])
+    assert abs(metrics_from_counts(cm2)["recall"] - (8 / 11 + 0.9 + 0.5 + 0.0) / 4) < 1e-12
+    # the 18-scalar state: counts + loss sum + count
+    st = torch.cat([cm.reshape(-1).double(), torch.tensor([15.0, 30.0], dtype=torch.float64)])
+    out = metrics_from_state(st)
+    assert out["loss"] == 0.5 and out["count"] == 30 and abs(out["f1"] - m["f1"]) < 1e-15
+
+
 def test_frame_signal_matches_reference_contract():
     """hss.utils.preprocess: L = floor((T - n) / stride) frames, truncated single frame otherwise (reference preprocess.py:39-56)."""
     import math

@@ -62,6 +62,23 @@ def test_golden_reference_outputs(lib, golden_dir, name, impl, monkeypatch):
     assert torch.equal(m.predict(x), labels)
 
 
+def test_config3_full_size_vs_torch_cpu(lib):
+    """BASELINE config 3 AS NAMED: FSST + BiLSTM end to end, batch 50, T = 2000 (the reference's frame length), against the
+    torch-CPU restatement of segmenter.py on the same features; label report printed."""
+    from hss.transforms import FSST
+
+    B, T = 50, 2000
+    x = torch.from_numpy(fo.synth_pcg_batch(B, T, seed=68))
+    feats = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True).batch(x.cuda())
+    m = make_model(68, 44, B, 240)
+    logp, labels = m.forward_with_labels(feats)
+    params, h0, c0 = lo.reference_params(68, 44, B, 240)
+    ref = lo.forward_torch(params, h0, c0, feats.cpu())
+    rep = check(logp.cpu(), labels.cpu(), ref)
+    assert rep["labels"] == B * T
+    print("config 3 (50 x 2000) label report:", rep)
+
+
 @pytest.mark.parametrize("impl", ["auto", "simt"])
 def test_config3_shape_vs_torch_cpu(lib, impl, monkeypatch):
     """BASELINE config 3 geometry (batch 50, 44 features, H 240) on FSST features, shorter T for the CPU oracle."""
@@ -154,6 +171,74 @@ def test_config4_shard_size_cross_kernel_agreement(lib, monkeypatch):
     print("config 4 shard: max |dlogp| between the two kernel families", d, "label flips", flips, "of", la.numel())
 
 
+def test_config4_shard_full_size_rows_vs_torch_cpu(lib):
+    """BASELINE config 4's per-GPU shard at FULL size (512 windows x 2000 samples) through the DEFAULT path, checked against the
+    reference arithmetic itself: batch rows are independent (h0 / c0 are per row, segmenter.py:38-41), so torch-CPU on a subset
+    of rows with the matching h0 / c0 slices is the reference's result for those rows.  16 rows: first / last column of
+    several 32-column sub-tiles and of both halves of the batch."""
+    B, T = 512, 2000
+    m = make_model(68, 44, B, 240)
+    x = torch.randn(B, T, 44, generator=torch.Generator().manual_seed(68))
+    logp, labels = m.forward_with_labels(x.cuda())
+    rows = [0, 1, 31, 32, 63, 95, 96, 255, 256, 287, 288, 300, 415, 479, 480, 511]
+    params, h0, c0 = lo.reference_params(68, 44, B, 240)
+    ref = lo.forward_torch(params, h0[:, rows].contiguous(), c0[:, rows].contiguous(), x[rows])
+    rep = check(logp[rows].cpu(), labels[rows].cpu(), ref)
+    print("config 4 shard, 16 of 512 rows vs torch-CPU:", rep)
+
+
+@pytest.mark.parametrize("scale", [1e-4, 1.0, 1e3, 1e5, 3e7])
+def test_input_range_of_the_fp16_split(lib, scale):
+    """The gate contractions split every operand into fp16 hi + lo planes; fp16 overflows at 65504 where the reference is plain
+    fp32 (segmenter.py:80).  Inputs up to 2^15 ride the fused path; at 1e5 / 3e7 the range guard pre-scales x by a power of two
+    and scales the projection back (exact), so nothing is inf / nan.  Large inputs amplify the fp32 rounding noise of the
+    reference itself (|W x| ~ scale), so the yardstick is the float64 evaluation of the same network: the CUDA path must be as
+    close to it as torch-CPU's own fp32 arithmetic is (within 4x, never worse than the usual tolerance needs)."""
+    B, T = 40, 60
+    m = make_model(21, 44, B, 240)
+    x = torch.randn(B, T, 44, generator=torch.Generator().manual_seed(5)) * scale
+    params, h0, c0 = lo.reference_params(21, 44, B, 240)
+    logp, labels = m.forward_with_labels(x.cuda())
+    logp, labels = logp.cpu(), labels.cpu()
+    assert torch.isfinite(logp).all()
+    ref = lo.forward_torch(params, h0, c0, x)
+    truth = lo.forward_manual(params, h0, c0, x, torch.float64)
+    err_ref = float((ref.double() - truth).abs().max())
+    err_ours = float((logp.double() - truth).abs().max())
+    rep = lo.label_report(logp, ref, truth)
+    print(f"scale {scale:g}: |ours - f64| {err_ours:.3g}, |torch-CPU - f64| {err_ref:.3g}", rep)
+    assert err_ours <= max(LOGP_TOL, 4 * err_ref), (err_ours, err_ref)
+    assert rep["flips"] == 0 or rep["max_margin_flipped"] < max(MARGIN_TOL, 4 * err_ref), rep
+    assert torch.equal(labels.long(), logp.argmax(-1))
+    if scale <= 1.0:
+        check(logp, labels, ref)
+
+
+def test_weights_outside_the_split_range_use_the_fp32_kernels(lib):
+    m = make_model(4, 44, 3, 240)
+    with torch.no_grad():
+        m.lstm_1.weight_ih_l0[5, 7] = 1.0e5
+    x = torch.randn(3, 25, 44, generator=torch.Generator().manual_seed(6))
+    logp, labels = m.forward_with_labels(x.cuda())
+    assert torch.isfinite(logp).all()
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    check(logp.cpu(), labels.cpu(), lo.forward_torch(params, m.h0, m.c0, x))
+
+
+def test_copies_and_pickles_repack_lazily(lib):
+    import copy
+    import pickle
+
+    m = make_model(8, 44, 2, 240)
+    x = torch.randn(2, 30, 44)
+    a = m(x)
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone._handle is None
+        assert torch.equal(clone(x), a)
+    del clone
+    assert torch.equal(m(x), a)                 # the original handle is still alive
+
+
 def test_state_dict_reload_repacks_weights(lib):
     m = make_model(3, 44, 2, 240)
     x = torch.randn(2, 20, 44)
@@ -177,6 +262,30 @@ def test_confusion_kernel_and_metrics(lib):
     ref.index_put_((target.reshape(-1), pred.reshape(-1).long()), torch.ones(pred.numel(), dtype=torch.int64), accumulate=True)
     assert torch.equal(cm, ref)
     assert abs(metrics_from_counts(cm)["micro_accuracy"] - float((pred == target).double().mean())) < 1e-9
+
+
+def test_metric_state_kernel_confusion_and_loss(lib):
+    """hssb_metrics_update (K7 complete): 16 confusion counts + summed loss + count in 18 doubles.  The loss is what the
+    reference logs (main.py:69-70,112-117): nn.CrossEntropyLoss on the permuted log-probabilities."""
+    from hss.sharding import metric_state, metrics_from_counts, metrics_from_state
+
+    g = torch.Generator().manual_seed(3)
+    B, T = 50, 2000
+    logp = torch.log_softmax(torch.randn(B, T, 4, generator=g) * 2, dim=2)
+    target = torch.randint(0, 4, (B, T), generator=g)
+    st = metric_state(logp.cuda(), target.cuda())
+    ref_loss = torch.nn.CrossEntropyLoss()(logp.permute(0, 2, 1).double(), target)
+    cm = torch.zeros(4, 4, dtype=torch.int64)
+    cm.index_put_((target.reshape(-1), logp.argmax(-1).reshape(-1)), torch.ones(B * T, dtype=torch.int64), accumulate=True)
+    out = metrics_from_state(st)
+    assert torch.equal(st[:16].cpu().round().long().reshape(4, 4), cm) and out["count"] == B * T
+    assert abs(out["loss"] - float(ref_loss)) < 1e-6 * max(1.0, abs(float(ref_loss)))
+    assert out["f1"] == metrics_from_counts(cm)["f1"]
+    # accumulation over steps on the device + explicit labels + skipped targets
+    target2 = target.clone()
+    target2[0, :100] = -1
+    st2 = metric_state(logp.cuda(), target2.cuda(), labels=logp.argmax(-1).int().cuda(), state=st.clone())
+    assert int(st2[17].item()) == 2 * B * T - 100
 
 
 def test_auroc_histogram_kernel(lib):
