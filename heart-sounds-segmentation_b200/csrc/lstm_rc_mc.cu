@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     cluster_sync();                          // every CTA's barriers are initialised before any multicast can target them
+    if (p.resident && threadIdx.x == 0) atomicAdd(p.resident, 1u);      // this CTA holds its SM: the gated projection launch may start
 
     if (warp < S) {
         // ================= MMA issuer of sub-tile s = warp (one elected thread) =================
@@ -237,9 +238,25 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
             const long long xstep = (dir ? -1 : 1) * p.Bp * TC_G;
             float4 xnext[NI];
             float c_state[NI];
+            int x_t = dir ? (int)T - 1 : 0, x_tile = -1;        // time index of the next xproj load and the time tile already waited for
             // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
             // wait of the warp (TMA issue, spill reloads, ...) would otherwise sit behind these HBM loads.
             auto load_x = [&]() {
+                if (!FUSE_X && p.chunk_done && (x_t >> 7) != x_tile) {
+                    // the projection GEMM runs concurrently: wait until this direction's chunk of the time tile is in memory
+                    x_tile = x_t >> 7;
+                    if (lane == 0) {
+                        const unsigned *flag = p.chunk_done + (dir ? 2 * (p.t_tiles - 1 - x_tile) + 1 : 2 * x_tile);
+                        unsigned long long t_start = 0;
+                        while (ld_acquire_u32(flag) < p.chunk_need) {
+                            __nanosleep(256);
+                            if (!t_start) t_start = globaltimer_ns();
+                            else if (globaltimer_ns() - t_start > POLL_TIMEOUT_NS) { *p.timeout_flag = 1; break; }
+                        }
+                    }
+                    __syncwarp();
+                }
+                x_t += dir ? -1 : 1;
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
                     const int c = col_of(i);
@@ -398,6 +415,17 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                     if (!p.out_f32) tma_store_3d(&om[1], out_tile + LO_OFF, out_c0, t_idx, (int)b0 + cbase);
                     tma_store_commit();
                 }
+                if (p.tile_done && ((dir ? (t_idx & (TC_TT - 1)) == 0 : (t_idx & (TC_TT - 1)) == TC_TT - 1) || t + 1 == Ti)) {
+                    // this warp's relu(h) of a whole time tile is on its way: once the bulk stores have completed, tell the
+                    // projection GEMM of the next layer (generic-proxy release behind the async-proxy writes)
+                    if (elect_one()) {
+                        tma_store_wait<0>();
+                        fence_proxy_async_all();
+                        __threadfence();
+                        atomicAdd(p.tile_done + dir * p.t_tiles + (t_idx >> 7), 1u);
+                    }
+                    __syncwarp();
+                }
                 t_idx += dir ? -1 : 1;
                 if (t + 1 < Ti) {
                     load_x();
@@ -421,7 +449,8 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
 }
 
 template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X = false>
-static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st)
+static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st,
+                               RecurLaunchInfo *info)
 {
     using C = RmCfg<S, EW, FUSE_X>;
     RecurParams prm = prm_in;
@@ -462,6 +491,13 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     if (const char *e = getenv("HSSB_RC_DEBUG")) prm.debug = atoi(e);
 #endif
     cfg.gridDim = dim3((unsigned)(2 * groups * RC_CL));
+    if (info) {
+        info->ctas = 2 * groups * RC_CL;
+        unsigned live = 0;                          // sub-tiles of one direction that hold batch columns
+        for (int g = 0; g < groups; ++g)
+            for (int i = 0; i < S; ++i) live += (prm.b_base + ((long long)g * S + i) * RP_NBH < prm.B) ? 1u : 0u;
+        info->signals_per_dir = live * RC_CL * 4 * EW;
+    }
     ProfScope prof("tc_recurrent", st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
@@ -470,23 +506,23 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
 
 
 int rc_mc_launch(int s, int variant, bool fused, const RecurParams &prm, const __half *whh_frag, int64_t rem, int *done,
-                 const float *xproj, cudaStream_t st)
+                 const float *xproj, cudaStream_t st, RecurLaunchInfo *info)
 {
     if (fused) {        // the default variants only: two epilogue warps per quadrant up to 64 columns per cluster, one beyond
-        if (s == 1) return launch_recurrent_mc<1, true, 2, true>(prm, whh_frag, rem, done, xproj, st);
-        if (s == 2) return launch_recurrent_mc<2, true, 2, true>(prm, whh_frag, rem, done, xproj, st);
-        if (s == 3) return launch_recurrent_mc<3, true, 1, true>(prm, whh_frag, rem, done, xproj, st);
+        if (s == 1) return launch_recurrent_mc<1, true, 2, true>(prm, whh_frag, rem, done, xproj, st, info);
+        if (s == 2) return launch_recurrent_mc<2, true, 2, true>(prm, whh_frag, rem, done, xproj, st, info);
+        if (s == 3) return launch_recurrent_mc<3, true, 1, true>(prm, whh_frag, rem, done, xproj, st, info);
     }
     switch (s * 10 + variant) {
-    case 12: return launch_recurrent_mc<1, false, 1>(prm, whh_frag, rem, done, xproj, st);
-    case 22: return launch_recurrent_mc<2, false, 1>(prm, whh_frag, rem, done, xproj, st);
-    case 32: return launch_recurrent_mc<3, false, 1>(prm, whh_frag, rem, done, xproj, st);
-    case 13: return launch_recurrent_mc<1, true, 1>(prm, whh_frag, rem, done, xproj, st);
-    case 23: return launch_recurrent_mc<2, true, 1>(prm, whh_frag, rem, done, xproj, st);
-    case 33: return launch_recurrent_mc<3, true, 1>(prm, whh_frag, rem, done, xproj, st);
-    case 14: return launch_recurrent_mc<1, true, 2>(prm, whh_frag, rem, done, xproj, st);
-    case 24: return launch_recurrent_mc<2, true, 2>(prm, whh_frag, rem, done, xproj, st);
-    case 34: return launch_recurrent_mc<3, true, 2>(prm, whh_frag, rem, done, xproj, st);
+    case 12: return launch_recurrent_mc<1, false, 1>(prm, whh_frag, rem, done, xproj, st, info);
+    case 22: return launch_recurrent_mc<2, false, 1>(prm, whh_frag, rem, done, xproj, st, info);
+    case 32: return launch_recurrent_mc<3, false, 1>(prm, whh_frag, rem, done, xproj, st, info);
+    case 13: return launch_recurrent_mc<1, true, 1>(prm, whh_frag, rem, done, xproj, st, info);
+    case 23: return launch_recurrent_mc<2, true, 1>(prm, whh_frag, rem, done, xproj, st, info);
+    case 33: return launch_recurrent_mc<3, true, 1>(prm, whh_frag, rem, done, xproj, st, info);
+    case 14: return launch_recurrent_mc<1, true, 2>(prm, whh_frag, rem, done, xproj, st, info);
+    case 24: return launch_recurrent_mc<2, true, 2>(prm, whh_frag, rem, done, xproj, st, info);
+    case 34: return launch_recurrent_mc<3, true, 2>(prm, whh_frag, rem, done, xproj, st, info);
     default: return fail(HSSB_E_MODE, "multicast recurrence: %d sub-tiles, variant %d unsupported", s, variant);
     }
 }

@@ -152,9 +152,12 @@ int simt_recurrent(const float *xproj, const float *const w_hhT[2], const float 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 head_kernel(const float *__restrict__ act, long long M, int H2, const float *__restrict__ lin_w,
-            const float *__restrict__ lin_b, float *__restrict__ logp, int32_t *__restrict__ labels)
+            const float *__restrict__ lin_b, float *__restrict__ logp, int32_t *__restrict__ labels, const int *__restrict__ poison)
 {
     extern __shared__ float w_s[];   // [4][H2]
+    // `poison` (nullable): a producer / consumer wait upstream gave up (see POLL_TIMEOUT_NS) -- the activations are not the
+    // forward's result, so the outputs are NaN / -1 rather than plausible numbers
+    const bool bad = poison && *poison != 0;
     for (int i = threadIdx.x; i < 4 * H2; i += blockDim.x) w_s[i] = lin_w[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -205,14 +208,15 @@ head_kernel(const float *__restrict__ act, long long M, int H2, const float *__r
             float best = o[0];
 #pragma unroll
             for (int c = 1; c < 4; ++c) if (o[c] > best) { best = o[c]; arg = c; }
-            if (logp) *reinterpret_cast<float4 *>(logp + (size_t)row * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            if (labels) labels[row] = arg;
+            const float nan = __int_as_float(0x7fc00000);
+            if (logp) *reinterpret_cast<float4 *>(logp + (size_t)row * 4) = bad ? make_float4(nan, nan, nan, nan) : make_float4(o[0], o[1], o[2], o[3]);
+            if (labels) labels[row] = bad ? -1 : arg;
         }
     }
 }
 
 int head_forward(const float *act, int64_t M, int H2, const float *lin_w, const float *lin_b, float *logp,
-                 int32_t *labels, cudaStream_t st)
+                 int32_t *labels, cudaStream_t st, const int *poison)
 {
     if (M == 0) return 0;
     long long blocks = (M + 15) / 16;
@@ -223,7 +227,7 @@ int head_forward(const float *act, int64_t M, int H2, const float *lin_w, const 
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(head_kernel)");
     }
     ProfScope prof("head", st);
-    head_kernel<<<(unsigned)blocks, 256, smem, st>>>(act, M, H2, lin_w, lin_b, logp, labels);
+    head_kernel<<<(unsigned)blocks, 256, smem, st>>>(act, M, H2, lin_w, lin_b, logp, labels, poison);
     HSSB_LAUNCH_OK("head_kernel");
     return 0;
 }

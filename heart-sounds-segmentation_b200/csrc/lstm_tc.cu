@@ -109,48 +109,64 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: input projection GEMM, persistent + warp specialised, clusters of 8 CTAs (4 along M x 2 along N).
+// K4: input projection GEMM, persistent + warp specialised, clusters of CM (along M) x CN (along N) CTAs.
 //
-//   xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']          M = B*T, N = 1920, K = 48 / 480
+//   xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']          M = B*T, N = 1920, K = 48 / 512
 //
-// Per CTA one 128(t) x 192(g') output tile at a time; three fp16 MMAs per product (hi*hi, lo*hi, hi*lo).
-// The operands come out of L2, whose bandwidth (~7 TB/s, the same order as HBM) is what bounded the first
-// version of this kernel: a lone CTA re-reads (128 + 192) x K x 4 bytes per tile.  Here the eight CTAs of a
-// cluster work on 4 consecutive m-tiles x 2 consecutive n-tiles and share their loads by TMA multicast:
-// the A stage (128 rows) is fetched in two halves by the two CTAs of a column and multicast to both, the
-// W stage (192 rows) in four quarters by the four CTAs of a row -> (128/2 + 192/4) rows per CTA and stage.
-//   warp 0   : TMA producer (4-stage ring of 40 KB stages, BK = 32, SW64: the refill of a stage waits for the
-//              slowest of the 5 CTAs that read it, so depth matters more than stage size)
-//   warp 1   : tcgen05.mma issuer; accumulators double-buffered in TMEM (2 x 192 columns) so that the
-//              epilogue of tile i overlaps the main loop of tile i+1; smem stages are released to all
-//              CTAs that write into this one with a multicast tcgen05.commit
-//   warps 2-5: epilogue TMEM -> registers (+bias) -> swizzled smem -> TMA store
+// Per CTA one 128(t) x 160(g') output tile at a time; three fp16 MMAs per product (hi*hi, lo*hi, hi*lo).
+// The operands come out of L2, whose bandwidth is what bounds a lone CTA (it re-reads (128 + 160) x K x 4 bytes per tile).
+// The CTAs of a cluster work on CM consecutive batch rows x CN consecutive n-tiles of one time tile and share their loads by
+// TMA multicast: the A stage (128 rows) is fetched in CN parts by the CTAs of a cluster column and multicast to all of them,
+// the W stage (160 rows) in CM parts by the CTAs of a cluster row.
+//
+// Work order ("chunks").  The consumer of layer 2's projection is the layer-2 recurrence, whose forward direction walks
+// t = 0.. and whose reverse direction walks t = T-1..; the producer of its A operand is the layer-1 recurrence, which
+// finishes the MIDDLE time steps first.  So the unit of scheduling is a chunk q = (direction, time tile of 128 steps) in
+// outside-in order -- q = 2k: (forward, tile k), q = 2k + 1: (reverse, tile t_tiles - 1 - k) -- and one launch covers a
+// range [chunk_lo, chunk_hi) of that sequence, front to back or (`reverse`) back to front.  Every finished tile bumps
+// chunk_done[q]; the recurrence polls it before it reads a chunk's xproj (lstm_rc_mc.cu), which is what lets the tail of
+// this GEMM run on the SMs the latency-bound recurrence leaves idle (tc_forward).
+// Items (CM batch rows x CN n-tiles of one chunk) are handed out by an atomic counter, not by blockIdx: a launch that shares
+// the GPU with the recurrence has fewer clusters resident than launched, and a statically assigned item of a cluster that is
+// not resident would never be produced while the recurrence waits for it.
+//   warp 0          : TMA producer (ring of STAGES stages, BK = 32, SW64)
+//   warp 1          : tcgen05.mma issuer; accumulators double-buffered in TMEM (columns 0.. and 256..) so that the
+//                     epilogue of tile i overlaps the main loop of tile i+1; smem stages are released to all CTAs
+//                     that write into this one with a multicast tcgen05.commit
+//   warps 2..       : epilogue TMEM -> registers (+bias) -> swizzled smem tile -> coalesced 16-byte global stores
+//   last warp       : item scheduler (cluster rank 0 fetches the next item and posts it into every CTA's item ring)
 // ------------------------------------------------------------------------------------------------
-constexpr int IP_BM = 128, IP_BN = 192, IP_BK = 32;   // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
-constexpr int IP_CM = 4, IP_CN = 2, IP_CL = IP_CM * IP_CN;   // cluster shape
+constexpr int IP_BM = 128, IP_BN = 160, IP_BK = 32;      // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
+constexpr int IP_NT_DIR = TC_G / IP_BN;                  // n-tiles per direction (6)
+static_assert(IP_BM == TC_TT, "the M tile of the projection is the time tile of the producer / consumer flags");
+static_assert(TC_G % IP_BN == 0 && IP_BN % 32 == 0, "n-tiles must not straddle the two directions");
 constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (8 KB)
-constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the B stage (12 KB)
-constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 40 KB
+constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the W stage (10 KB)
+constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 36 KB
 constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue transposition tile of one warp: 32 rows x 32 fp32 (4 KB)
-constexpr int IP_OUT_RING = 1;                           // tiles per warp
 constexpr int IP_BIAS_BYTES = TC_NG * 4;                 // all 1920 folded biases, staged once per CTA
+constexpr int IP_RING = 4;                               // item ring depth
+constexpr int IP_NCHUNK = IP_BN / 32;                    // 32-column chunks of the accumulator (5)
 // STAGES / EPI_WARPS: layer 2's projection (K = 512) is main-loop bound: 5 smem stages, 4 epilogue warps.  Layer 1's (K = 48)
 // is epilogue bound -- one warp per SMSP cannot hide the TMEM-load / shared-memory latencies of the drain: 3 stages, 8 warps.
-template <int STAGES, int EPI_WARPS>
+template <int STAGES, int EPI_WARPS, int CM, int CN>
 struct IpCfg {
-    static constexpr int OUT_BYTES = EPI_WARPS * IP_OUT_RING * IP_OUT_TILE;
-    static constexpr int SMEM_BYTES = STAGES * IP_STAGE_BYTES + OUT_BYTES + IP_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int CL = CM * CN;
+    static constexpr int OUT_BYTES = EPI_WARPS * IP_OUT_TILE;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int SMEM_BYTES = STAGES * IP_STAGE_BYTES + OUT_BYTES + IP_BIAS_BYTES + 1024 /*align*/ + BAR_BYTES;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;
+    static constexpr int CONSUMERS = 2 + EPI_WARPS;      // roles of one CTA that read an item slot
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two warps per TMEM lane quadrant");
+    static_assert(IP_NT_DIR % CN == 0 && IP_BM % CN == 0 && (IP_BN / CM) % 8 == 0, "cluster shape must split the tiles");
+    static_assert((2 * STAGES + 4 + 2 * IP_RING) * 8 + 4 + 4 * IP_RING <= BAR_BYTES, "barrier area too small");
 };
-constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 192 columns (at 0 and 256)
-constexpr int IP_N_TILES = TC_NG / IP_BN;                // 10
-static_assert(IP_N_TILES % IP_CN == 0, "n-tiles must split over the cluster");
+constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 160 columns (at 0 and 256)
 
 struct InprojParams {
-    CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (32, 64, 1), SW64   (half of the A stage)
-    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 48), SW64  (quarter of the W stage)
+    CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (32, 128 / CN, 1), SW64   (my part of the A stage)
+    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 160 / CM), SW64  (my part of the W stage)
     float *out;               // xproj [dir][t][Bp][960] fp32
     const float *bias;        // [1920]
     long long B, Bp;          // batch, and the row pitch of xproj in batch rows (see xproj_pitch)
@@ -160,14 +176,22 @@ struct InprojParams {
     int k_real;               // true K rounded up to 16 (48 / 512)
     int T;
     int t_tiles;              // ceil(T/128)
-    int m_groups;             // ceil(B * t_tiles / 4)
+    int b_groups;             // ceil(B / CM)
+    int chunk_lo, chunk_hi;   // chunks [lo, hi) of the outside-in sequence belong to this launch
+    int reverse;              // walk them back to front (middle-out)
+    unsigned *next_item;      // item counter of this launch (zeroed by the host)
+    unsigned *chunk_done;     // nullable: [2 * t_tiles] finished (tile, epilogue warp) pairs per chunk
+    const unsigned *src_done; // nullable: [2][t_tiles] counters of the layer-1 recurrence (its relu(h1) tile is in memory) ...
+    unsigned src_need;        // ... a time tile may be loaded once both directions reached this count
+    int *timeout_flag;        // raised instead of hanging when src_done never arrives
 };
 
-template <int IP_STAGES, int EPI_WARPS>
-__global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_inproj_kernel(const __grid_constant__ InprojParams p)
+template <int IP_STAGES, int EPI_WARPS, int CM, int CN>
+__global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 1) tc_inproj_kernel(const __grid_constant__ InprojParams p)
 {
-    using C = IpCfg<IP_STAGES, EPI_WARPS>;
+    using C = IpCfg<IP_STAGES, EPI_WARPS, CM, CN>;
     constexpr int IP_OUT_BYTES = C::OUT_BYTES;
+    constexpr int CL = C::CL;
     if (p.run_flag && *p.run_flag == 0) return;        // uniform over the grid; before any barrier / TMEM allocation
     const float up = p.range ? pow2f(range_exponent(p.range[1])) : 1.0f;
     extern __shared__ unsigned char smem_dyn[];
@@ -177,21 +201,42 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
     float *bias_s = reinterpret_cast<float *>(out_base + IP_OUT_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + IP_OUT_BYTES + IP_BIAS_BYTES);
     uint64_t *full = bars, *empty = bars + IP_STAGES, *tmem_full = bars + 2 * IP_STAGES, *tmem_empty = bars + 2 * IP_STAGES + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * IP_STAGES + 4);
+    uint64_t *item_full = bars + 2 * IP_STAGES + 4, *item_empty = item_full + IP_RING;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(item_empty + IP_RING);
+    int *item_ring = reinterpret_cast<int *>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int cx = rank % IP_CM, cy = rank / IP_CM;                // position in the cluster: m / n
-    const uint16_t mask_a = (uint16_t)((1u << cx) | (1u << (cx + IP_CM)));          // CTAs sharing my A tile
-    const uint16_t mask_w = (uint16_t)(((1u << IP_CM) - 1u) << (IP_CM * cy));       // CTAs sharing my W tile
+    const int cx = rank % CM, cy = rank / CM;                      // position in the cluster: m / n
+    uint16_t mask_a = 0, mask_w = 0;
+#pragma unroll
+    for (int j = 0; j < CN; ++j) mask_a |= (uint16_t)(1u << (cx + CM * j));        // CTAs sharing my A tile (same batch row)
+#pragma unroll
+    for (int i = 0; i < CM; ++i) mask_w |= (uint16_t)(1u << (i + CM * cy));        // CTAs sharing my W tile (same n-tile)
     const int kblocks = (p.k_real + IP_BK - 1) / IP_BK;
-    const int cluster_id = blockIdx.x / IP_CL, n_clusters = gridDim.x / IP_CL;
-    const int n_items = p.m_groups * (IP_N_TILES / IP_CN);
+    constexpr int N_PAIRS = IP_NT_DIR / CN;
+    const int items_per_chunk = p.b_groups * N_PAIRS;
+    const int n_items = (p.chunk_hi - p.chunk_lo) * items_per_chunk;
+
+    // item -> tile coordinates of this CTA
+    struct Tile { int q, dir, t0, b, n0; };
+    auto tile_of = [&](int item) {
+        Tile t;
+        const int ci = item / items_per_chunk, r = item % items_per_chunk;
+        t.q = p.reverse ? p.chunk_hi - 1 - ci : p.chunk_lo + ci;
+        t.dir = t.q & 1;
+        const int k = t.q >> 1;
+        t.t0 = (t.dir ? p.t_tiles - 1 - k : k) * IP_BM;
+        t.b = (r / N_PAIRS) * CM + cx;
+        t.n0 = t.dir * TC_G + ((r % N_PAIRS) * CN + cy) * IP_BN;
+        return t;
+    };
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.a_hi); prefetch_tmap(&p.a_lo); prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
-        for (int s = 0; s < IP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], IP_CM + IP_CN - 1); }
+        for (int s = 0; s < IP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CM + CN - 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
+        for (int i = 0; i < IP_RING; ++i) { mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], CL * C::CONSUMERS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<IP_TMEM_COLS>(tmem_slot);
@@ -200,27 +245,59 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    cluster_sync();     // barriers of every CTA exist before any multicast can target them
+    cluster_sync();     // barriers of every CTA exist before any multicast / remote arrive can target them
+
+    // every consumer role (the producer thread, the MMA thread, each epilogue warp) reads the ring in order and hands a slot back
+    // to the scheduler with ONE arrival as soon as the value is in its registers; an item >= n_items is the end marker
+    uint32_t ring_it = 0;
+    auto next_item = [&]() {                   // called by a single thread
+        const int slot = ring_it % IP_RING;
+        mbar_wait_cluster(&item_full[slot], (ring_it / IP_RING) & 1);
+        const int item = *reinterpret_cast<volatile int *>(&item_ring[slot]);
+        mbar_arrive_remote(&item_empty[slot], 0);
+        ++ring_it;
+        return item;
+    };
+    auto next_item_warp = [&]() {              // called by a converged warp
+        const int slot = ring_it % IP_RING;
+        mbar_wait_cluster(&item_full[slot], (ring_it / IP_RING) & 1);
+        const int item = *reinterpret_cast<volatile int *>(&item_ring[slot]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&item_empty[slot], 0);
+        ++ring_it;
+        return item;
+    };
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
             uint32_t it = 0;
-            for (int item = cluster_id; item < n_items; item += n_clusters) {
-                const int m_tile = (item / (IP_N_TILES / IP_CN)) * IP_CM + cx;
-                const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * IP_BM;
-                const int n0 = ((item % (IP_N_TILES / IP_CN)) * IP_CN + cy) * IP_BN;
+            unsigned long long t_start = 0;
+            for (int item = next_item(); item < n_items; item = next_item()) {
+                const Tile tl = tile_of(item);
+                if (p.src_done) {
+                    // layer 1 still running: both of its directions must have stored this time tile (generic-proxy flag, then a
+                    // proxy fence so that the TMA reads below are ordered behind it)
+                    const int tt = tl.t0 / IP_BM;
+                    while (ld_acquire_u32(p.src_done + tt) < p.src_need || ld_acquire_u32(p.src_done + p.t_tiles + tt) < p.src_need) {
+                        __nanosleep(500);
+                        if (!t_start) t_start = globaltimer_ns();
+                        else if (globaltimer_ns() - t_start > POLL_TIMEOUT_NS) { *p.timeout_flag = 1; break; }
+                    }
+                    t_start = 0;
+                    fence_proxy_async_all();
+                }
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % IP_STAGES;
                     mbar_wait_cluster(&empty[s], ((it / IP_STAGES) & 1) ^ 1);
                     unsigned char *st = stage_base + s * IP_STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[s], IP_STAGE_BYTES);
-                    // my half of the A tile (rows cy*64 ..) -> both CTAs of my cluster column
-                    tma_load_3d_mc(st + cy * (IP_A_BYTES / 2), &p.a_hi, &full[s], kb * IP_BK, t0 + cy * (IP_BM / 2), b, mask_a);
-                    tma_load_3d_mc(st + IP_A_BYTES + cy * (IP_A_BYTES / 2), &p.a_lo, &full[s], kb * IP_BK, t0 + cy * (IP_BM / 2), b, mask_a);
-                    // my quarter of the W tile (rows cx*48 ..) -> the four CTAs of my cluster row
-                    tma_load_2d_mc(st + 2 * IP_A_BYTES + cx * (IP_B_BYTES / 4), &p.w_hi, &full[s], kb * IP_BK, n0 + cx * (IP_BN / 4), mask_w);
-                    tma_load_2d_mc(st + 2 * IP_A_BYTES + IP_B_BYTES + cx * (IP_B_BYTES / 4), &p.w_lo, &full[s], kb * IP_BK, n0 + cx * (IP_BN / 4), mask_w);
+                    // my part of the A tile (rows cy * 128/CN ..) -> the CTAs of my cluster column
+                    tma_load_3d_mc(st + cy * (IP_A_BYTES / CN), &p.a_hi, &full[s], kb * IP_BK, tl.t0 + cy * (IP_BM / CN), tl.b, mask_a);
+                    tma_load_3d_mc(st + IP_A_BYTES + cy * (IP_A_BYTES / CN), &p.a_lo, &full[s], kb * IP_BK, tl.t0 + cy * (IP_BM / CN), tl.b, mask_a);
+                    // my part of the W tile (rows cx * 160/CM ..) -> the CTAs of my cluster row
+                    tma_load_2d_mc(st + 2 * IP_A_BYTES + cx * (IP_B_BYTES / CM), &p.w_hi, &full[s], kb * IP_BK, tl.n0 + cx * (IP_BN / CM), mask_w);
+                    tma_load_2d_mc(st + 2 * IP_A_BYTES + IP_B_BYTES + cx * (IP_B_BYTES / CM), &p.w_lo, &full[s], kb * IP_BK, tl.n0 + cx * (IP_BN / CM), mask_w);
                 }
             }
         }
@@ -230,7 +307,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
             constexpr uint32_t idesc = make_idesc_f16(IP_BM, IP_BN);
             const uint16_t mask_rel = mask_a | mask_w;     // every CTA that writes into my stages
             uint32_t it = 0, tile = 0;
-            for (int item = cluster_id; item < n_items; item += n_clusters, ++tile) {
+            for (int item = next_item(); item < n_items; item = next_item(), ++tile) {
                 const uint32_t acc = tile & 1;
                 mbar_wait(&tmem_empty[acc], ((tile >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -259,44 +336,40 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
                 mma_commit(&tmem_full[acc]);               // accumulator complete
             }
         }
-    } else {
-        // ===== epilogue: warps 2.., TMEM lane quadrant = warp % 4; with 8 warps the two warps of a quadrant take alternate chunks =====
-        // A warp first pulls ALL of its 32-column chunks of the accumulator into registers and hands the accumulator back to the
-        // MMA warp at once (the stores below are slow -- 1.5 ms of layer 2's projection -- and must not hold TMEM), then per chunk:
+    } else if (warp < 2 + EPI_WARPS) {
+        // ===== epilogue: TMEM lane quadrant = warp % 4; with 8 warps the two warps of a quadrant take alternate 32-column chunks =====
+        // A warp first pulls ALL of its chunks of the accumulator into registers (three at a time) and hands the accumulator back to the
+        // MMA warp as soon as the last one is loaded (the stores below are slow and must not hold TMEM), then per chunk:
         // registers (one row of 32 columns per thread, + bias) -> xor-swizzled smem tile -> 16-byte global stores in which 8
         // consecutive lanes cover one 128-byte row segment (every store instruction writes four full lines).
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int CSTEP = EPI_WARPS / 4;
-        constexpr int NCH = (IP_BN / 32) / CSTEP;           // chunks per warp: 6 (4 warps) or 3 (8 warps)
-        constexpr int NPASS = (NCH > 3) ? 2 : 1;            // registers hold 3 chunks at a time
-        constexpr int PCH = NCH / NPASS;
         unsigned char *ob = out_base + (warp - 2) * IP_OUT_TILE;
         uint32_t tile = 0;
-        for (int item = cluster_id; item < n_items; item += n_clusters, ++tile) {
-            const int m_tile = (item / (IP_N_TILES / IP_CN)) * IP_CM + cx;
-            const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * IP_BM;
-            const int n0 = ((item % (IP_N_TILES / IP_CN)) * IP_CN + cy) * IP_BN;
-            const int dir = n0 / TC_G, nl0 = n0 % TC_G;
+        for (int item = next_item_warp(); item < n_items; item = next_item_warp(), ++tile) {
+            const Tile tl = tile_of(item);
+            const int nl0 = tl.n0 - tl.dir * TC_G;
             const uint32_t acc = tile & 1;
             mbar_wait(&tmem_full[acc], (tile >> 1) & 1);
             tc_fence_after();
+            for (int c0 = half; c0 < IP_NCHUNK; c0 += 3 * CSTEP) {
+                uint32_t v[3][32];
 #pragma unroll
-            for (int pass = 0; pass < NPASS; ++pass) {
-                uint32_t v[PCH][32];
-#pragma unroll
-                for (int i = 0; i < PCH; ++i)
-                    tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (half + (pass * PCH + i) * CSTEP) * 32, v[i]);
+                for (int i = 0; i < 3; ++i)
+                    if (c0 + i * CSTEP < IP_NCHUNK)
+                        tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + (c0 + i * CSTEP) * 32, v[i]);
                 tmem_ld_wait();
-                if (pass == NPASS - 1) {                    // my part of the accumulator is in registers: hand it back to the MMA warp
+                if (c0 + 3 * CSTEP >= IP_NCHUNK) {          // my part of the accumulator is in registers: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
 #pragma unroll
-                for (int i = 0; i < PCH; ++i) {
-                    const int c = half + (pass * PCH + i) * CSTEP;
-                    const float4 *bias = reinterpret_cast<const float4 *>(bias_s + n0 + c * 32);
+                for (int i = 0; i < 3; ++i) {
+                    const int c = c0 + i * CSTEP;
+                    if (c >= IP_NCHUNK) break;
+                    const float4 *bias = reinterpret_cast<const float4 *>(bias_s + tl.n0 + c * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 bj = bias[j];                 // shared-memory broadcast
@@ -309,16 +382,41 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS>::THREADS, 1) tc_in
                     }
                     __syncwarp();
                     const int rsub = lane >> 3, c16 = lane & 7;
-                    float *gout = p.out + (((size_t)dir * p.T + t0 + q * 32) * p.Bp + b) * TC_G + nl0 + c * 32 + c16 * 4;
+                    float *gout = p.out + (((size_t)tl.dir * p.T + tl.t0 + q * 32) * p.Bp + tl.b) * TC_G + nl0 + c * 32 + c16 * 4;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int row = 4 * j + rsub;
                         const float4 o = *reinterpret_cast<const float4 *>(ob + row * 128 + ((c16 ^ (row & 7)) << 4));
-                        if (b < p.B && t0 + q * 32 + row < p.T && !(p.debug & 1))                    // (b >= B: padding tiles of the last m-group)
+                        if (tl.b < p.B && tl.t0 + q * 32 + row < p.T && !(p.debug & 1))              // (b >= B: padding tiles of the last batch group)
                             __stcs(reinterpret_cast<float4 *>(gout + (size_t)row * p.Bp * TC_G), o);
                     }
                     __syncwarp();
                 }
+            }
+            if (p.chunk_done && tl.b < p.B) {
+                // this warp's part of the tile is stored: publish it (the recurrence counts real tiles x epilogue warps per chunk)
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(p.chunk_done + tl.q, 1u);
+                }
+            }
+        }
+    } else {
+        // ===== item scheduler (cluster rank 0): the next item of the launch -> every CTA's ring =====
+        if (rank == 0 && elect_one()) {
+            uint32_t it = 0;
+            for (;; ++it) {
+                const int slot = it % IP_RING;
+                mbar_wait_cluster(&item_empty[slot], ((it / IP_RING) & 1) ^ 1);
+                const int item = (int)atomicAdd(p.next_item, 1u);
+                const uint32_t ring_addr = smem_u32(&item_ring[slot]);
+#pragma unroll
+                for (int r = 0; r < CL; ++r) {
+                    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa(ring_addr, r)), "r"(item) : "memory");
+                    mbar_arrive_remote(&item_full[slot], r);       // release.cluster: the store above is visible to the waiter
+                }
+                if (item >= n_items) break;
             }
         }
     }
@@ -436,14 +534,27 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
     return 0;
 }
 
-template <int STAGES, int EPI_WARPS>
+// What one launch of K4 covers and how it is synchronised with the recurrences either side of it (see tc_forward).
+struct InprojJob {
+    int chunk_lo = 0, chunk_hi = -1;      // chunks [lo, hi) of the outside-in sequence; hi < 0 = all 2 * t_tiles
+    int reverse = 0;                      // back to front (middle-out)
+    int shape = 0;                        // cluster shape CM x CN: 0 = 4x2, 1 = 2x2, 2 = 2x1, 3 = 1x1
+    unsigned *next_item = nullptr;        // zeroed device word: the item counter of this launch (required)
+    unsigned *chunk_done = nullptr;       // [2 * t_tiles] zeroed device counters bumped per finished (tile, epilogue warp)
+    const unsigned *src_done = nullptr;   // [2][t_tiles] progress of the layer-1 recurrence (middle-out launch only)
+    unsigned src_need = 0;
+    int *timeout_flag = nullptr;
+    const char *name = nullptr;
+};
+
+template <int STAGES, int EPI_WARPS, int CM, int CN>
 static int launch_inproj(const InprojParams &prm, int n_items, const char *name, cudaStream_t st)
 {
-    using C = IpCfg<STAGES, EPI_WARPS>;
+    using C = IpCfg<STAGES, EPI_WARPS, CM, CN>;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = IP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
@@ -452,27 +563,31 @@ static int launch_inproj(const InprojParams &prm, int n_items, const char *name,
     static PerDeviceInt cached_clusters;
     int max_clusters = cached_clusters.get();
     if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(tc_inproj_kernel<STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_inproj_kernel<STAGES, EPI_WARPS, CM, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_inproj_kernel)");
-        cfg.gridDim = dim3(IP_CL * 16);
+        cfg.gridDim = dim3(C::CL * 16);
         int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_inproj_kernel<STAGES, EPI_WARPS>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, tc_inproj_kernel<STAGES, EPI_WARPS, CM, CN>, &cfg);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_inproj_kernel)");
         if (n < 1) return fail(HSSB_E_DEVICE, "device cannot host an input-projection cluster");
         max_clusters = n;
         cached_clusters.set(n);
     }
-    cfg.gridDim = dim3((unsigned)(IP_CL * std::min(max_clusters, n_items)));
+    cfg.gridDim = dim3((unsigned)(C::CL * std::max(1, std::min(max_clusters, n_items))));
     ProfScope prof(name, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_inproj_kernel<STAGES, EPI_WARPS>, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_inproj_kernel<STAGES, EPI_WARPS, CM, CN>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_inproj_kernel)");
     return 0;
 }
 
 // One layer's input projection on the tensor cores.  a_hi/a_lo: [B*T][pitch] fp16 planes.
 int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *a_lo, int pitch_elems, int64_t B, int64_t T,
-              float *xproj /*[2][T][B][960]*/, cudaStream_t st, const unsigned *range = nullptr, const int *run_flag = nullptr)
+              float *xproj /*[2][T][B][960]*/, cudaStream_t st, const InprojJob &job, const unsigned *range = nullptr,
+              const int *run_flag = nullptr)
 {
+    static const int SHAPES[4][2] = {{4, 2}, {2, 2}, {2, 1}, {1, 1}};
+    if (job.shape < 0 || job.shape > 3 || !job.next_item) return fail(HSSB_E_MODE, "tc_inproj: bad job");
+    const int CM = SHAPES[job.shape][0], CN = SHAPES[job.shape][1];
     InprojParams prm;
     prm.range = range;
     prm.run_flag = run_flag;
@@ -481,14 +596,14 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     {
         const uint64_t dims[3] = {(uint64_t)(layer == 0 ? Kp : kreal), (uint64_t)T, (uint64_t)B};
         const uint64_t strides[2] = {(uint64_t)pitch_elems * 2, (uint64_t)T * pitch_elems * 2};
-        const uint32_t box[3] = {IP_BK, IP_BM / IP_CN, 1};
+        const uint32_t box[3] = {IP_BK, (uint32_t)(IP_BM / CN), 1};
         if (int rc = make_tmap(&prm.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
         if (int rc = make_tmap(&prm.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
     {
         const uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)TC_NG};
         const uint64_t strides[1] = {(uint64_t)Kp * 2};
-        const uint32_t box[2] = {IP_BK, IP_BN / IP_CM};
+        const uint32_t box[2] = {IP_BK, (uint32_t)(IP_BN / CM)};
         const __half *hi = m->tc_wih[layer], *lo = hi + (size_t)TC_NG * Kp;
         if (int rc = make_tmap(&prm.w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
         if (int rc = make_tmap(&prm.w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
@@ -504,15 +619,33 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     prm.k_real = kreal;
     prm.T = (int)T;
     prm.t_tiles = (int)((T + IP_BM - 1) / IP_BM);
-    prm.m_groups = (int)((B * prm.t_tiles + IP_CM - 1) / IP_CM);
+    prm.b_groups = (int)((B + CM - 1) / CM);
+    prm.chunk_lo = job.chunk_lo;
+    prm.chunk_hi = job.chunk_hi < 0 ? 2 * prm.t_tiles : job.chunk_hi;
+    prm.reverse = job.reverse;
+    prm.next_item = job.next_item;
+    prm.chunk_done = job.chunk_done;
+    prm.src_done = job.src_done;
+    prm.src_need = job.src_need;
+    prm.timeout_flag = job.timeout_flag;
+    if (prm.chunk_lo < 0 || prm.chunk_hi > 2 * prm.t_tiles || prm.chunk_hi < prm.chunk_lo) return fail(HSSB_E_SHAPE, "tc_inproj: bad chunk range");
+    if (prm.chunk_hi == prm.chunk_lo) return 0;
+    if (prm.src_done && !prm.timeout_flag) return fail(HSSB_E_NULL, "tc_inproj: src_done needs a timeout flag");
 
-    const int n_items = prm.m_groups * (IP_N_TILES / IP_CN);
-    if (layer == 0) return launch_inproj<3, 8>(prm, n_items, "tc_inproj_l0", st);
-    if (const char *e = getenv("HSSB_IP_L1")) {
-        if (atoi(e) == 48) return launch_inproj<4, 8>(prm, n_items, "tc_inproj_l1", st);
-        if (atoi(e) == 44) return launch_inproj<4, 4>(prm, n_items, "tc_inproj_l1", st);
+    const long long items = (long long)(prm.chunk_hi - prm.chunk_lo) * prm.b_groups * (IP_NT_DIR / CN);
+    if (items > 0x7fffff00ll) return fail(HSSB_E_SHAPE, "tc_inproj: %lld work items do not fit the item counter", items);
+    const int n_items = (int)items;
+    const char *name = job.name ? job.name : (layer == 0 ? "tc_inproj_l0" : "tc_inproj_l1");
+    if (layer == 0) {                      // K = 48: epilogue bound -> 3 stages, 8 epilogue warps
+        if (job.shape != 0) return fail(HSSB_E_MODE, "tc_inproj: layer 1 runs on 4x2 clusters");
+        return launch_inproj<3, 8, 4, 2>(prm, n_items, name, st);
     }
-    return launch_inproj<5, 4>(prm, n_items, "tc_inproj_l1", st);
+    switch (job.shape) {
+    case 0: return launch_inproj<5, 4, 4, 2>(prm, n_items, name, st);
+    case 1: return launch_inproj<5, 4, 2, 2>(prm, n_items, name, st);
+    case 2: return launch_inproj<5, 4, 2, 1>(prm, n_items, name, st);
+    default: return launch_inproj<5, 4, 1, 1>(prm, n_items, name, st);
+    }
 }
 
 // torch W_hh[960][240] -> planes [dir][rank][plane][128 rows][256 k' = 32 r' + u'];  row (TMEM lane) order:
@@ -593,18 +726,43 @@ __global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict_
 unsigned long long *g_trace_buf = nullptr;
 int g_trace_steps = 0;
 
+// Optional hooks of a recurrence (input-range guard, flags of the overlapped projection) and what its launches looked like.
+struct RecurSync {
+    const int *skip_flag = nullptr;       // the launches are no-ops when (*skip_flag != 0) == skip_when
+    int skip_when = 0;
+    const unsigned *chunk_done = nullptr; // consumer side: wait for the projection chunk before reading its xproj
+    unsigned chunk_need = 0;
+    unsigned *tile_done = nullptr;        // producer side: relu(h) of a time tile is in memory
+    unsigned *resident = nullptr;         // bumped by every CTA once it holds its SM
+    int *timeout_flag = nullptr;
+    // out
+    int launches = 0, ctas_first = 0;
+    unsigned signals_per_dir = 0;
+    bool multicast = true;                // every launch was a K5m launch (the only kernel that implements the hooks)
+};
+
 // One layer's recurrence for batch columns [0, B): picks the sub-tile geometry from B.
 static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const float *h0, const float *c0, float *hn, float *cn,
                         __half *out_hi, __half *out_lo, float *out_f32, unsigned char *gather, int64_t B, int64_t T, cudaStream_t st,
-                        const __half *x_hi = nullptr, const __half *x_lo = nullptr, const int *skip_flag = nullptr, int skip_when = 0)
+                        const __half *x_hi = nullptr, const __half *x_lo = nullptr, RecurSync *sync = nullptr)
 {
     // x_hi / x_lo != nullptr: layer 1 with the input projection fused into the recurrence (tile-major x planes, no xproj)
     const bool fused = x_hi != nullptr;
+    RecurSync no_sync;
+    if (!sync) sync = &no_sync;
+    const int *skip_flag = sync->skip_flag;
     RecurParams prm = {};
     prm.gather = gather;
     prm.layer = layer;
-    prm.skip_flag = skip_flag;
-    prm.skip_when = skip_when;
+    prm.skip_flag = sync->skip_flag;
+    prm.skip_when = sync->skip_when;
+    prm.chunk_done = sync->chunk_done;
+    prm.chunk_need = sync->chunk_need;
+    prm.tile_done = sync->tile_done;
+    prm.resident = sync->resident;
+    prm.timeout_flag = sync->timeout_flag;
+    prm.t_tiles = (int)((T + TC_TT - 1) / TC_TT);
+    sync->launches = 0; sync->ctas_first = 0; sync->signals_per_dir = 0; sync->multicast = true;
     if (fused) {
         prm.x_hi = x_hi;
         prm.x_lo = x_lo;
@@ -655,17 +813,27 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         if (skip_flag && !(nb == 32 && pair >= 2)) return fail(HSSB_E_MODE, "the input-range guard needs the multicast recurrence");
         // pair: 0 = DSMEM all-gather (K5), 1 = its cta_group::2 mode or, with nb = 64, the CTA-pair kernel (K5p); 2..4 = K5m variants
         int rc, done = 0;
-        if (nb == 32 && pair >= 2) rc = rc_mc_launch(s, pair, fused, prm, m->tc_whh_frag[layer], rem, &done, xproj, st);
-        else if (nb == 64) rc = rc_pair_launch(s, prm, m->tc_whh_frag[layer], rem, &done, xproj, st);
-        else rc = rc_dsmem_launch(nb, s, pair, prm, rem, &done, xproj, st);
+        RecurLaunchInfo info = {0, 0};
+        if (nb == 32 && pair >= 2) rc = rc_mc_launch(s, pair, fused, prm, m->tc_whh_frag[layer], rem, &done, xproj, st, &info);
+        else {
+            sync->multicast = false;
+            if (sync->chunk_done || sync->tile_done) return fail(HSSB_E_MODE, "the overlapped projection needs the multicast recurrence");
+            if (nb == 64) rc = rc_pair_launch(s, prm, m->tc_whh_frag[layer], rem, &done, xproj, st);
+            else rc = rc_dsmem_launch(nb, s, pair, prm, rem, &done, xproj, st);
+        }
         if (rc) return rc;
+        if (sync->launches++ == 0) sync->ctas_first = info.ctas;
+        sync->signals_per_dir += info.signals_per_dir;
         base += done;
     }
     return 0;
 }
 
 namespace {
-struct TcWs { size_t xhi, xlo, xproj, o1hi, o1lo, out2, hn, cn, gather, range, total; };
+constexpr int SYNC_MAX_CHUNKS = 8192;                                   // chunk / tile counters of the overlapped projection
+constexpr size_t SYNC_HEAD = 256;                                        // next_item[8], timeout flag, resident counter
+constexpr size_t SYNC_BYTES = SYNC_HEAD + 2 * sizeof(unsigned) * SYNC_MAX_CHUNKS;
+struct TcWs { size_t xhi, xlo, xproj, o1hi, o1lo, out2, hn, cn, gather, range, sync, total; };
 TcWs tc_ws_layout(int64_t B, int64_t T)
 {
     const size_t M = (size_t)B * T;
@@ -682,6 +850,7 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
     w.cn = off;    off += align_up(sizeof(float) * 2 * B * TC_H, 1024);
     w.gather = off; off += TC_GATHER_BYTES;
     w.range = off; off += 256;                                     // input-range guard: {flag, bits of max|x|}
+    w.sync = off; off += align_up(SYNC_BYTES, 256);                // flags of the overlapped layer-2 projection
     w.total = off;
     return w;
 }
@@ -716,6 +885,43 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     unsigned *range = reinterpret_cast<unsigned *>(range_flag);
     HSSB_CUDA_OK(cudaMemsetAsync(range_flag, 0, 8, st));
     const int *standin = fused ? range_flag : nullptr;             // stand-in kernels run only when the flag was raised
+
+    // ---- flags of the overlapped layer-2 projection ----------------------------------------------------------------------
+    // Layer 2's projection GEMM (K4, throughput bound, 4.8 ms alone at 512 x 2000) sits between two latency-bound recurrences
+    // that leave ~50 of the 148 SMs idle.  It runs as up to three launches over the outside-in chunk sequence (see K4):
+    //   M  the middle chunks, back to front, on small clusters on the side stream UNDER the layer-1 recurrence, each time tile as
+    //      soon as both layer-1 directions have stored it (tile_done) -- gated until every layer-1 CTA is resident;
+    //   A  the outer chunks on all SMs, alone, until the recurrence has enough of a head start;
+    //   B  the rest on small clusters UNDER the layer-2 recurrence, which polls chunk_done before it reads a chunk.
+    // The layer-2 recurrence runs on a high-priority internal stream so that its clusters are placed before B's CTAs.
+    unsigned char *sync_base = reinterpret_cast<unsigned char *>(base + w.sync);
+    unsigned *next_item = reinterpret_cast<unsigned *>(sync_base);                   // [8]
+    int *timeout_flag = reinterpret_cast<int *>(sync_base + 32);
+    unsigned *resident = reinterpret_cast<unsigned *>(sync_base + 36);
+    unsigned *chunk_done = reinterpret_cast<unsigned *>(sync_base + SYNC_HEAD);
+    unsigned *tile_done = chunk_done + SYNC_MAX_CHUNKS;
+    const int t_tiles = (int)((T + TC_TT - 1) / TC_TT), Q = 2 * t_tiles;
+    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    const bool overlap = env_int("HSSB_OVERLAP", 1) != 0 && Q <= SYNC_MAX_CHUNKS && t_tiles >= 8 && !getenv("HSSB_RC_GEOM") &&
+                         m->sm_count >= 128 && m->hi_stream && m->side_stream;
+    const int shape_small = std::min(3, std::max(1, env_int("HSSB_K4_SHAPE", 2)));
+    int qA = Q, qM = 0;
+    if (overlap) {
+        qM = (Q * std::min(40, std::max(0, env_int("HSSB_K4_MID", 0))) / 100) & ~1;
+        qA = std::min(Q - qM, std::max(2, Q * std::min(100, std::max(5, env_int("HSSB_K4_SPLIT", 65))) / 100));
+        HSSB_CUDA_OK(cudaMemsetAsync(sync_base, 0, SYNC_HEAD + sizeof(unsigned) * Q, st));
+        if (qM) HSSB_CUDA_OK(cudaMemsetAsync(tile_done, 0, sizeof(unsigned) * Q, st));
+    } else {
+        HSSB_CUDA_OK(cudaMemsetAsync(sync_base, 0, SYNC_HEAD, st));
+    }
+
+    // ---- layer 1 -----------------------------------------------------------------------------------------------------------
+    RecurSync l1;
+    l1.timeout_flag = timeout_flag;
+    if (qM) { l1.tile_done = tile_done; l1.resident = resident; }
+    int l1_ctas = 0;
+    unsigned l1_signals = 0;
+    bool l1_single = true;
     if (fused) {
         {
             ProfScope prof("split_planes", st);
@@ -723,7 +929,9 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
             split_planes_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, B, T, m->F, xhi, xlo, range_flag);
             HSSB_LAUNCH_OK("split_planes_tiled_kernel");
         }
-        if (int rc = tc_recurrent(m, 0, nullptr, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, xhi, xlo, range_flag, 1)) return rc;
+        l1.skip_flag = range_flag; l1.skip_when = 1;
+        if (int rc = tc_recurrent(m, 0, nullptr, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, xhi, xlo, &l1)) return rc;
+        l1_ctas = l1.ctas_first; l1_signals = l1.signals_per_dir; l1_single = l1.launches == 1;
     }
     {
         ProfScope prof(fused ? "range_standin" : "split_planes", st);
@@ -731,11 +939,46 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo, range, standin);
         HSSB_LAUNCH_OK("split_planes_kernel");
     }
-    if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st, range, standin)) return rc;
-    if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, nullptr, nullptr, standin, 0)) return rc;
-    if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st)) return rc;
-    if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, st)) return rc;
-    return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st);
+    {
+        InprojJob job;
+        job.next_item = next_item + 0;
+        if (fused) job.name = "range_standin";
+        if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st, job, range, standin)) return rc;
+    }
+    l1.skip_flag = standin; l1.skip_when = 0;
+    if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, nullptr, nullptr, &l1)) return rc;
+    if (!fused) { l1_ctas = l1.ctas_first; l1_signals = l1.signals_per_dir; l1_single = l1.launches == 1; }
+    else if (l1.ctas_first != l1_ctas || l1.signals_per_dir != l1_signals) l1_single = false;    // (the stand-in must look like the launch it replaces)
+
+    // ---- layer 2 -----------------------------------------------------------------------------------------------------------
+    const unsigned chunk_need = (unsigned)(B * IP_NT_DIR * 4);        // finished (tile, epilogue warp) pairs of a chunk: 4 epilogue warps
+    if (!overlap) {
+        InprojJob job;
+        job.next_item = next_item + 1;
+        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, job)) return rc;
+        if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, st)) return rc;
+    } else {
+        // NOTE: the middle launch was enqueued on the side stream right after layer 1's launch below would be too late -- it is
+        // issued here, behind the host-side launch of layer 1 (its kernels wait on device flags, not on the host)
+        if (qM && l1_single && l1.multicast) {
+            HSSB_CUDA_OK(cudaEventRecord(m->ev[0], st));            // (host order only: everything above is already enqueued)
+        }
+        InprojJob a;
+        a.chunk_lo = 0; a.chunk_hi = qA; a.shape = 0; a.next_item = next_item + 1; a.chunk_done = chunk_done;
+        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, a)) return rc;
+        HSSB_CUDA_OK(cudaEventRecord(m->ev[1], st));
+        HSSB_CUDA_OK(cudaStreamWaitEvent(m->hi_stream, m->ev[1], 0));
+        RecurSync l2;
+        l2.chunk_done = chunk_done; l2.chunk_need = chunk_need; l2.timeout_flag = timeout_flag;
+        if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, m->hi_stream, nullptr, nullptr, &l2)) return rc;
+        HSSB_CUDA_OK(cudaEventRecord(m->ev[2], m->hi_stream));
+        InprojJob b;
+        b.chunk_lo = qA; b.chunk_hi = Q - qM; b.shape = shape_small; b.next_item = next_item + 2; b.chunk_done = chunk_done;
+        b.name = "tc_inproj_l1_tail";
+        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, b)) return rc;
+        HSSB_CUDA_OK(cudaStreamWaitEvent(st, m->ev[2], 0));
+    }
+    return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st, timeout_flag);
 }
 
 }  // namespace hssb
@@ -776,13 +1019,16 @@ extern "C" int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B,
     }
     if (m->H != TC_H || m->F > 64 || !m->tc_wih[0]) return fail(HSSB_E_MODEL, "tcgen05 kernels need hidden_size 240");
     const size_t raw_floats = (size_t)2 * T * xproj_pitch(B) * TC_G;
-    const size_t need = sizeof(float) * raw_floats + sizeof(__half) * 2 * M * 64;
+    const size_t need = sizeof(float) * raw_floats + sizeof(__half) * 2 * M * 64 + 256;
     if (!workspace || workspace_bytes < need) return fail(HSSB_E_WORKSPACE, "hssb_debug_inproj: workspace %zu < %zu", workspace_bytes, need);
     float *raw = static_cast<float *>(workspace);
     __half *hi = reinterpret_cast<__half *>(raw + raw_floats), *lo = hi + M * 64;
     split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, hi, lo, nullptr, nullptr);
     HSSB_LAUNCH_OK("split_planes_kernel");
-    if (int rc = tc_inproj(m, 0, hi, lo, 64, B, T, raw, st)) return rc;
+    InprojJob job;
+    job.next_item = reinterpret_cast<unsigned *>(hi + 2 * M * 64);
+    HSSB_CUDA_OK(cudaMemsetAsync(job.next_item, 0, 256, st));
+    if (int rc = tc_inproj(m, 0, hi, lo, 64, B, T, raw, st, job)) return rc;
     unpermute_xproj_kernel<<<(unsigned)((2 * M * TC_G + 255) / 256), 256, 0, st>>>(raw, B, xproj_pitch(B), T, xproj);
     HSSB_LAUNCH_OK("unpermute_xproj_kernel");
     return 0;

@@ -46,6 +46,22 @@ __device__ __forceinline__ int range_exponent(unsigned amax_bits)
 __device__ __forceinline__ float pow2f(int e) { return __uint_as_float((unsigned)(127 + e) << 23); }
 
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long POLL_TIMEOUT_NS = 4000000000ull;     // 4 s: a producer that never shows up must not hang the GPU
+
+constexpr int TC_TT = 128;          // time tile: the projection GEMM's M tile, and the granularity of the producer / consumer flags
+
 // recurrence geometry shared by all variants: 8 CTAs per cluster, 30 hidden units (120 gate rows) per CTA
 constexpr int RC_CL = 8;            // CTAs per cluster
 constexpr int RC_U = 30;            // real units per CTA
@@ -82,6 +98,16 @@ struct RecurParams {
     // input-range guard of the fused layer-1 path: the launch is a no-op when (*skip_flag != 0) == skip_when (nullptr: always runs)
     const int *skip_flag;
     int skip_when;
+    // producer / consumer flags of the overlapped layer-2 projection (tc_forward).  chunk_done (nullable): the xproj of time tile tt
+    // and this direction may be read once chunk_done[q] reached chunk_need (q = 2 tt forward, 2 (t_tiles - 1 - tt) + 1 reverse);
+    // tile_done (nullable): bumped per epilogue warp when its relu(h) stores of a time tile are complete, [dir][t_tiles];
+    // resident (nullable): bumped once per CTA when the launch is on the machine; timeout_flag: raised instead of hanging
+    const unsigned *chunk_done;
+    unsigned chunk_need;
+    unsigned *tile_done;
+    unsigned *resident;
+    int *timeout_flag;
+    int t_tiles;
 };
 
 // trace events (per step, per sub-tile): see scripts/trace_recurrent.py
@@ -176,7 +202,9 @@ int rc_dsmem_launch(int nb, int s, int pair, const RecurParams &prm, int64_t rem
 int rc_dsmem_max_clusters(int *out);                 // co-resident 8-CTA clusters of the 32 x 3 DSMEM geometry
 int rc_pair_launch(int s, const RecurParams &prm, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st);
 // variant 2: one publisher per sub-tile, 3: per-warp publishing, 4: per-warp + two epilogue warps per TMEM quadrant
+// info (nullable): CTAs of the launch and the number of epilogue warps per direction that run the step loop (tile_done signals)
+struct RecurLaunchInfo { int ctas; unsigned signals_per_dir; };
 int rc_mc_launch(int s, int variant, bool fused, const RecurParams &prm, const __half *whh_frag, int64_t rem, int *cols_done,
-                 const float *xproj, cudaStream_t st);
+                 const float *xproj, cudaStream_t st, RecurLaunchInfo *info = nullptr);
 
 }  // namespace hssb

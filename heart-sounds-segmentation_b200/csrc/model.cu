@@ -101,8 +101,17 @@ extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, v
     std::memset(m, 0, sizeof(*m));
     m->F = F; m->H = H;
     cudaGetDevice(&m->device);
+    cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
+    {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaError_t es = cudaStreamCreateWithPriority(&m->hi_stream, cudaStreamNonBlocking, greatest);
+        if (es == cudaSuccess) es = cudaStreamCreateWithPriority(&m->side_stream, cudaStreamNonBlocking, least);
+        for (int i = 0; i < 6 && es == cudaSuccess; ++i) es = cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming);
+        if (es != cudaSuccess) { hssb_model_destroy(m); return cuda_fail(es, "hssb_model_create: internal streams"); }
+    }
     cudaError_t e = cudaMalloc(&m->all, off);
-    if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaMalloc(model)"); }
+    if (e != cudaSuccess) { m->all = nullptr; hssb_model_destroy(m); return cuda_fail(e, "cudaMalloc(model)"); }
     m->all_bytes = off;
     char *base = static_cast<char *>(m->all);
     float *stage = reinterpret_cast<float *>(base + o_stage);
@@ -136,7 +145,7 @@ extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, v
     }
     if (!rc && tc_pack_bytes(F, H) > 0) rc = tc_pack(m, p, base + o_tc, st);
     if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(model create)");
-    if (rc) { cudaFree(m->all); delete m; return rc; }
+    if (rc) { hssb_model_destroy(m); return rc; }
     *out = m;
     return 0;
 }
@@ -145,6 +154,9 @@ extern "C" void hssb_model_destroy(hssb_model *m)
 {
     if (!m) return;
     if (m->all) cudaFree(m->all);
+    if (m->hi_stream) cudaStreamDestroy(m->hi_stream);
+    if (m->side_stream) cudaStreamDestroy(m->side_stream);
+    for (int i = 0; i < 6; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m;
 }
 

@@ -25,6 +25,12 @@ struct hssb_model {
     float *tc_bias0_frag;     // their folded biases [dir][rank][128]
     void *all;                // single allocation backing everything above
     size_t all_bytes;
+    // overlapped layer-2 projection (tc_forward): the layer-2 recurrence runs on a high-priority internal stream while the tail of
+    // the projection GEMM keeps the SMs it leaves idle busy; a second internal stream hosts the middle-out part of the GEMM that
+    // runs under the layer-1 recurrence.  Everything is joined back into the caller's stream before tc_forward's last kernel.
+    cudaStream_t hi_stream, side_stream;
+    cudaEvent_t ev[6];
+    int sm_count;
 };
 
 namespace hssb {
@@ -34,7 +40,7 @@ int simt_inproj(const float *A, int64_t M, int K, const float *Wt, const float *
 int simt_recurrent(const float *xproj /*[2][B*T][4H]*/, const float *const w_hhT[2], const float *h0, const float *c0,
                    int64_t B, int64_t T, int H, float *out /*[B,T,2H] relu'd*/, float *hn, float *cn, cudaStream_t st);
 int head_forward(const float *act /*[M,2H] already relu'd*/, int64_t M, int H2, const float *lin_w, const float *lin_b,
-                 float *logp, int32_t *labels, cudaStream_t st);
+                 float *logp, int32_t *labels, cudaStream_t st, const int *poison = nullptr);
 
 // tcgen05 path (lstm_tc.cu)
 size_t tc_pack_bytes(int F, int H);
