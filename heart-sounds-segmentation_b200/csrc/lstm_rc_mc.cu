@@ -448,28 +448,24 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
 #undef RM_TRACE
 }
 
-template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X = false>
-static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st,
-                               RecurLaunchInfo *info)
+// Per device, once: opt in to the kernel's shared memory and find out how many of its clusters are co-resident.  Also called for
+// every default variant when a model is created (rc_mc_prepare): the first use of a kernel loads its code, which may synchronise
+// the device -- that must not happen while a recurrence is polling for a projection launch that the host has not issued yet.
+template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X>
+static int prepare_recurrent_mc(int *max_clusters_out)
 {
     using C = RmCfg<S, EW, FUSE_X>;
-    RecurParams prm = prm_in;
-    prm.whh = whh_frag;
-    prm.trace = g_trace_buf;
-    prm.trace_steps = g_trace_steps;
-    if (const char *e = getenv("HSSB_TRACE_LAYER")) if (atoi(e) != prm.layer) prm.trace = nullptr;
-    static PerDeviceInt cached_clusters;         // per device: the opt-in shared memory attribute is set where it is first used
+    static PerDeviceInt cached_clusters;
     int max_clusters = cached_clusters.get();
-    cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(C::THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     if (!max_clusters) {
+        cudaLaunchAttribute attr[1];
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(C::THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
         cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_mc_kernel)");
         cfg.gridDim = dim3(16 * RC_CL);
@@ -480,6 +476,42 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
         max_clusters = std::min(n, 16);
         cached_clusters.set(max_clusters);
     }
+    *max_clusters_out = max_clusters;
+    return 0;
+}
+
+int rc_mc_prepare()
+{
+    int n = 0;
+    if (int rc = prepare_recurrent_mc<1, true, 2, true>(&n)) return rc;
+    if (int rc = prepare_recurrent_mc<2, true, 2, true>(&n)) return rc;
+    if (int rc = prepare_recurrent_mc<3, true, 1, true>(&n)) return rc;
+    if (int rc = prepare_recurrent_mc<1, true, 2, false>(&n)) return rc;
+    if (int rc = prepare_recurrent_mc<2, true, 2, false>(&n)) return rc;
+    return prepare_recurrent_mc<3, true, 1, false>(&n);
+}
+
+template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X = false>
+static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st,
+                               RecurLaunchInfo *info)
+{
+    using C = RmCfg<S, EW, FUSE_X>;
+    RecurParams prm = prm_in;
+    prm.whh = whh_frag;
+    prm.trace = g_trace_buf;
+    prm.trace_steps = g_trace_steps;
+    if (const char *e = getenv("HSSB_TRACE_LAYER")) if (atoi(e) != prm.layer) prm.trace = nullptr;
+    int max_clusters = 0;
+    if (int rc = prepare_recurrent_mc<S, WARP_PUBLISH, EW, FUSE_X>(&max_clusters)) return rc;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     const int per = RP_NBH * S;
     const int groups = (int)std::min<int64_t>(max_clusters / 2, (rem + per - 1) / per);
     *cols_done = groups * per;

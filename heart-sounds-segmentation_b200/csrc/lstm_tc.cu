@@ -119,13 +119,15 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 // TMA multicast: the A stage (128 rows) is fetched in CN parts by the CTAs of a cluster column and multicast to all of them,
 // the W stage (160 rows) in CM parts by the CTAs of a cluster row.
 //
-// Work order ("chunks").  The consumer of layer 2's projection is the layer-2 recurrence, whose forward direction walks
-// t = 0.. and whose reverse direction walks t = T-1..; the producer of its A operand is the layer-1 recurrence, which
-// finishes the MIDDLE time steps first.  So the unit of scheduling is a chunk q = (direction, time tile of 128 steps) in
-// outside-in order -- q = 2k: (forward, tile k), q = 2k + 1: (reverse, tile t_tiles - 1 - k) -- and one launch covers a
-// range [chunk_lo, chunk_hi) of that sequence, front to back or (`reverse`) back to front.  Every finished tile bumps
-// chunk_done[q]; the recurrence polls it before it reads a chunk's xproj (lstm_rc_mc.cu), which is what lets the tail of
-// this GEMM run on the SMs the latency-bound recurrence leaves idle (tc_forward).
+// Work order.  The consumer of layer 2's projection is the layer-2 recurrence, whose forward direction walks t = 0.. and whose
+// reverse direction walks t = T-1..; the producer of its A operand is the layer-1 recurrence, which finishes the MIDDLE time
+// steps first.  Work is therefore scheduled in units of one time tile (128 steps), in one of three orders per launch:
+//   mode 0  whole tiles (the n-tiles of both directions: the A tile is fetched once), outside-in: 0, last, 1, last-1, ...
+//   mode 1  whole tiles, middle-out
+//   mode 2  one direction of a tile ("chunk" q = 2k: (forward, tile k), q = 2k + 1: (reverse, tile t_tiles - 1 - k)) in the
+//           order in which the recurrence needs them, over one or two ranges of q
+// Every finished tile bumps chunk_done[q]; the recurrence polls it before it reads a chunk's xproj (lstm_rc_mc.cu), which is
+// what lets parts of this GEMM run on the SMs the latency-bound recurrences leave idle (tc_forward).
 // Items (CM batch rows x CN n-tiles of one chunk) are handed out by an atomic counter, not by blockIdx: a launch that shares
 // the GPU with the recurrence has fewer clusters resident than launched, and a statically assigned item of a cluster that is
 // not resident would never be produced while the recurrence waits for it.
@@ -177,8 +179,9 @@ struct InprojParams {
     int T;
     int t_tiles;              // ceil(T/128)
     int b_groups;             // ceil(B / CM)
-    int chunk_lo, chunk_hi;   // chunks [lo, hi) of the outside-in sequence belong to this launch
-    int reverse;              // walk them back to front (middle-out)
+    int unit_mode;            // 0 whole tiles outside-in, 1 whole tiles middle-out, 2 single-direction chunks (see above)
+    int u_lo, n_units;        // modes 0 / 1: units [u_lo, u_lo + n_units) of the order; mode 2: n_units chunks ...
+    int q_lo1, len1, q_lo2;   // ... q_lo1 + u for u < len1, q_lo2 + (u - len1) beyond
     unsigned *next_item;      // item counter of this launch (zeroed by the host)
     unsigned *chunk_done;     // nullable: [2 * t_tiles] finished (tile, epilogue warp) pairs per chunk
     const unsigned *src_done; // nullable: [2][t_tiles] counters of the layer-1 recurrence (its relu(h1) tile is in memory) ...
@@ -214,21 +217,33 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
 #pragma unroll
     for (int i = 0; i < CM; ++i) mask_w |= (uint16_t)(1u << (i + CM * cy));        // CTAs sharing my W tile (same n-tile)
     const int kblocks = (p.k_real + IP_BK - 1) / IP_BK;
-    constexpr int N_PAIRS = IP_NT_DIR / CN;
-    const int items_per_chunk = p.b_groups * N_PAIRS;
-    const int n_items = (p.chunk_hi - p.chunk_lo) * items_per_chunk;
+    const int n_pairs = (p.unit_mode == 2 ? IP_NT_DIR : 2 * IP_NT_DIR) / CN;      // cluster columns per unit
+    const int items_per_unit = p.b_groups * n_pairs;
+    const int n_items = p.n_units * items_per_unit;
 
     // item -> tile coordinates of this CTA
     struct Tile { int q, dir, t0, b, n0; };
     auto tile_of = [&](int item) {
         Tile t;
-        const int ci = item / items_per_chunk, r = item % items_per_chunk;
-        t.q = p.reverse ? p.chunk_hi - 1 - ci : p.chunk_lo + ci;
-        t.dir = t.q & 1;
-        const int k = t.q >> 1;
-        t.t0 = (t.dir ? p.t_tiles - 1 - k : k) * IP_BM;
-        t.b = (r / N_PAIRS) * CM + cx;
-        t.n0 = t.dir * TC_G + ((r % N_PAIRS) * CN + cy) * IP_BN;
+        const int u = item / items_per_unit, r = item % items_per_unit;
+        int tt, ntile;
+        if (p.unit_mode == 2) {
+            const int q = u < p.len1 ? p.q_lo1 + u : p.q_lo2 + (u - p.len1);
+            const int dir = q & 1, k = q >> 1;
+            tt = dir ? p.t_tiles - 1 - k : k;
+            ntile = dir * IP_NT_DIR + (r % n_pairs) * CN + cy;
+        } else {
+            const int j = p.u_lo + u;
+            if (p.unit_mode == 0) tt = (j & 1) ? p.t_tiles - 1 - (j >> 1) : (j >> 1);
+            else if (p.t_tiles & 1) tt = (j & 1) ? (p.t_tiles - 1) / 2 - ((j + 1) >> 1) : (p.t_tiles - 1) / 2 + (j >> 1);
+            else tt = (j & 1) ? p.t_tiles / 2 + (j >> 1) : p.t_tiles / 2 - 1 - (j >> 1);
+            ntile = (r % n_pairs) * CN + cy;
+        }
+        t.dir = ntile / IP_NT_DIR;
+        t.q = t.dir ? 2 * (p.t_tiles - 1 - tt) + 1 : 2 * tt;
+        t.t0 = tt * IP_BM;
+        t.b = (r / n_pairs) * CM + cx;
+        t.n0 = ntile * IP_BN;
         return t;
     };
 
@@ -445,6 +460,8 @@ __global__ void unpermute_xproj_kernel(const float *__restrict__ src, long long 
 static int kp_of_layer(int layer, int F) { return layer == 0 ? 64 : 512; }
 static int kreal_of_layer(int layer, int F) { return layer == 0 ? ((F + 15) / 16) * 16 : TC_OP; }
 
+static int tc_prepare();
+
 size_t tc_pack_bytes(int F, int H)
 {
     if (H != TC_H || F > 64) return 0;
@@ -531,13 +548,15 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
     float w_max;
     memcpy(&w_max, &w_bits[1], 4);
     m->tc_ready = (w_max <= TC_SPLIT_SAFE);      // false for larger / non-finite weights: hssb_model_forward then runs the fp32 SIMT kernels
+    if (m->tc_ready) return tc_prepare();
     return 0;
 }
 
 // What one launch of K4 covers and how it is synchronised with the recurrences either side of it (see tc_forward).
 struct InprojJob {
-    int chunk_lo = 0, chunk_hi = -1;      // chunks [lo, hi) of the outside-in sequence; hi < 0 = all 2 * t_tiles
-    int reverse = 0;                      // back to front (middle-out)
+    int unit_mode = 0;                    // 0 whole tiles outside-in, 1 whole tiles middle-out, 2 single-direction chunks
+    int u_lo = 0, n_units = -1;           // modes 0 / 1: units of the order (n_units < 0: all t_tiles tiles)
+    int q_lo1 = 0, len1 = 0, q_lo2 = 0;   // mode 2: chunks q_lo1 .. (len1 of them), then q_lo2 .. up to n_units in total
     int shape = 0;                        // cluster shape CM x CN: 0 = 4x2, 1 = 2x2, 2 = 2x1, 3 = 1x1
     unsigned *next_item = nullptr;        // zeroed device word: the item counter of this launch (required)
     unsigned *chunk_done = nullptr;       // [2 * t_tiles] zeroed device counters bumped per finished (tile, epilogue warp)
@@ -547,22 +566,23 @@ struct InprojJob {
     const char *name = nullptr;
 };
 
+// Per device, once: opt in to the kernel's shared memory and find its co-resident clusters (see prepare_recurrent_mc for why this
+// also runs when a model is created).
 template <int STAGES, int EPI_WARPS, int CM, int CN>
-static int launch_inproj(const InprojParams &prm, int n_items, const char *name, cudaStream_t st)
+static int prepare_inproj(int *max_clusters_out)
 {
     using C = IpCfg<STAGES, EPI_WARPS, CM, CN>;
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(C::THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     static PerDeviceInt cached_clusters;
     int max_clusters = cached_clusters.get();
     if (!max_clusters) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(C::THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
         cudaError_t e = cudaFuncSetAttribute(tc_inproj_kernel<STAGES, EPI_WARPS, CM, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_inproj_kernel)");
         cfg.gridDim = dim3(C::CL * 16);
@@ -573,11 +593,47 @@ static int launch_inproj(const InprojParams &prm, int n_items, const char *name,
         max_clusters = n;
         cached_clusters.set(n);
     }
+    *max_clusters_out = max_clusters;
+    return 0;
+}
+
+template <int STAGES, int EPI_WARPS, int CM, int CN>
+static int launch_inproj(const InprojParams &prm, int n_items, const char *name, cudaStream_t st)
+{
+    using C = IpCfg<STAGES, EPI_WARPS, CM, CN>;
+    int max_clusters = 0;
+    if (int rc = prepare_inproj<STAGES, EPI_WARPS, CM, CN>(&max_clusters)) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     cfg.gridDim = dim3((unsigned)(C::CL * std::max(1, std::min(max_clusters, n_items))));
     ProfScope prof(name, st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_inproj_kernel<STAGES, EPI_WARPS, CM, CN>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_inproj_kernel)");
     return 0;
+}
+
+__global__ void resident_gate_kernel(const unsigned *__restrict__ resident, unsigned expected, int *__restrict__ timeout_flag);
+
+// Loads and configures every kernel that may be launched while another one is polling for it (see prepare_recurrent_mc).
+static int tc_prepare()
+{
+    int n = 0;
+    if (int rc = prepare_inproj<3, 8, 4, 2>(&n)) return rc;
+    if (int rc = prepare_inproj<5, 4, 4, 2>(&n)) return rc;
+    if (int rc = prepare_inproj<5, 4, 2, 2>(&n)) return rc;
+    if (int rc = prepare_inproj<5, 4, 2, 1>(&n)) return rc;
+    if (int rc = prepare_inproj<5, 4, 1, 1>(&n)) return rc;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, resident_gate_kernel);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(resident_gate_kernel)");
+    return rc_mc_prepare();
 }
 
 // One layer's input projection on the tensor cores.  a_hi/a_lo: [B*T][pitch] fp16 planes.
@@ -620,19 +676,26 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     prm.T = (int)T;
     prm.t_tiles = (int)((T + IP_BM - 1) / IP_BM);
     prm.b_groups = (int)((B + CM - 1) / CM);
-    prm.chunk_lo = job.chunk_lo;
-    prm.chunk_hi = job.chunk_hi < 0 ? 2 * prm.t_tiles : job.chunk_hi;
-    prm.reverse = job.reverse;
+    prm.unit_mode = job.unit_mode;
+    prm.u_lo = job.u_lo;
+    prm.n_units = job.n_units < 0 ? prm.t_tiles : job.n_units;
+    prm.q_lo1 = job.q_lo1; prm.len1 = job.len1; prm.q_lo2 = job.q_lo2;
     prm.next_item = job.next_item;
     prm.chunk_done = job.chunk_done;
     prm.src_done = job.src_done;
     prm.src_need = job.src_need;
     prm.timeout_flag = job.timeout_flag;
-    if (prm.chunk_lo < 0 || prm.chunk_hi > 2 * prm.t_tiles || prm.chunk_hi < prm.chunk_lo) return fail(HSSB_E_SHAPE, "tc_inproj: bad chunk range");
-    if (prm.chunk_hi == prm.chunk_lo) return 0;
+    const int nt_unit = (job.unit_mode == 2 ? IP_NT_DIR : 2 * IP_NT_DIR);
+    if (job.unit_mode < 0 || job.unit_mode > 2 || nt_unit % CN != 0) return fail(HSSB_E_MODE, "tc_inproj: cluster shape %dx%d does not fit unit mode %d", CM, CN, job.unit_mode);
+    if (job.unit_mode == 2) {
+        if (prm.len1 < 0 || prm.len1 > prm.n_units || prm.q_lo1 < 0 || prm.q_lo1 + prm.len1 > 2 * prm.t_tiles ||
+            (prm.n_units > prm.len1 && (prm.q_lo2 < 0 || prm.q_lo2 + prm.n_units - prm.len1 > 2 * prm.t_tiles)))
+            return fail(HSSB_E_SHAPE, "tc_inproj: bad chunk ranges");
+    } else if (prm.u_lo < 0 || prm.u_lo + prm.n_units > prm.t_tiles) return fail(HSSB_E_SHAPE, "tc_inproj: bad tile range");
+    if (prm.n_units == 0) return 0;
     if (prm.src_done && !prm.timeout_flag) return fail(HSSB_E_NULL, "tc_inproj: src_done needs a timeout flag");
 
-    const long long items = (long long)(prm.chunk_hi - prm.chunk_lo) * prm.b_groups * (IP_NT_DIR / CN);
+    const long long items = (long long)prm.n_units * prm.b_groups * (nt_unit / CN);
     if (items > 0x7fffff00ll) return fail(HSSB_E_SHAPE, "tc_inproj: %lld work items do not fit the item counter", items);
     const int n_items = (int)items;
     const char *name = job.name ? job.name : (layer == 0 ? "tc_inproj_l0" : "tc_inproj_l1");
@@ -721,6 +784,18 @@ __global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict_
 {
     const int c = blockIdx.x, k = threadIdx.x, slot = k & 31;
     dst[c * TC_OP + k] = slot < 30 ? w[c * 2 * TC_H + (k >> 8) * TC_H + ((k >> 5) & 7) * 30 + slot] : 0.f;
+}
+
+// Holds the side stream back until every CTA of the layer-1 recurrence is on the machine: the middle-out projection launch behind it
+// waits on that recurrence's progress flags, so its persistent CTAs must never occupy an SM the recurrence still needs.
+__global__ void resident_gate_kernel(const unsigned *__restrict__ resident, unsigned expected, int *__restrict__ timeout_flag)
+{
+    if (threadIdx.x != 0) return;
+    const unsigned long long t_start = globaltimer_ns();
+    while (ld_acquire_u32(resident) < expected) {
+        __nanosleep(1000);
+        if (globaltimer_ns() - t_start > POLL_TIMEOUT_NS) { *timeout_flag = 1; break; }
+    }
 }
 
 unsigned long long *g_trace_buf = nullptr;
@@ -888,16 +963,18 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
 
     // ---- flags of the overlapped layer-2 projection ----------------------------------------------------------------------
     // Layer 2's projection GEMM (K4, throughput bound, 4.8 ms alone at 512 x 2000) sits between two latency-bound recurrences
-    // that leave ~50 of the 148 SMs idle.  It runs as up to three launches over the outside-in chunk sequence (see K4):
-    //   M  the middle chunks, back to front, on small clusters on the side stream UNDER the layer-1 recurrence, each time tile as
-    //      soon as both layer-1 directions have stored it (tile_done) -- gated until every layer-1 CTA is resident;
-    //   A  the outer chunks on all SMs, alone, until the recurrence has enough of a head start;
-    //   B  the rest on small clusters UNDER the layer-2 recurrence, which polls chunk_done before it reads a chunk.
-    // The layer-2 recurrence runs on a high-priority internal stream so that its clusters are placed before B's CTAs.
+    // that leave ~50 of the 148 SMs idle.  It runs as up to three launches (work orders: see K4):
+    //   M  the middle time tiles, middle-out, on small clusters on the side stream UNDER the layer-1 recurrence, each tile as soon
+    //      as both layer-1 directions have stored it (tile_done) -- gated until every layer-1 CTA is resident;
+    //   A  the outer time tiles (both directions of a tile together: its A operand is read once) on all SMs, alone, until the
+    //      layer-2 recurrence has enough of a head start;
+    //   B  the tiles in between, one direction at a time in the order the layer-2 recurrence needs them, on small clusters UNDER
+    //      that recurrence, which polls chunk_done before it reads a chunk -- gated until its clusters are on the machine.
+    // The layer-2 recurrence runs on a high-priority internal stream; everything is joined into the caller's stream before the head.
     unsigned char *sync_base = reinterpret_cast<unsigned char *>(base + w.sync);
     unsigned *next_item = reinterpret_cast<unsigned *>(sync_base);                   // [8]
     int *timeout_flag = reinterpret_cast<int *>(sync_base + 32);
-    unsigned *resident = reinterpret_cast<unsigned *>(sync_base + 36);
+    unsigned *resident = reinterpret_cast<unsigned *>(sync_base + 36);               // [2]: CTAs of the layer-1 / layer-2 recurrence on the machine
     unsigned *chunk_done = reinterpret_cast<unsigned *>(sync_base + SYNC_HEAD);
     unsigned *tile_done = chunk_done + SYNC_MAX_CHUNKS;
     const int t_tiles = (int)((T + TC_TT - 1) / TC_TT), Q = 2 * t_tiles;
@@ -905,12 +982,18 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     const bool overlap = env_int("HSSB_OVERLAP", 1) != 0 && Q <= SYNC_MAX_CHUNKS && t_tiles >= 8 && !getenv("HSSB_RC_GEOM") &&
                          m->sm_count >= 128 && m->hi_stream && m->side_stream;
     const int shape_small = std::min(3, std::max(1, env_int("HSSB_K4_SHAPE", 2)));
-    int qA = Q, qM = 0;
+    // tiles [0, kA) and [t_tiles - kA, t_tiles): launch A (whole tiles, all SMs, alone); the tM middle tiles: launch M (whole tiles,
+    // under layer 1); what lies between: launch B (single-direction chunks in the order the layer-2 recurrence needs them, under it)
+    int kA = t_tiles / 2, tM = 0;
     if (overlap) {
-        qM = (Q * std::min(40, std::max(0, env_int("HSSB_K4_MID", 0))) / 100) & ~1;
-        qA = std::min(Q - qM, std::max(2, Q * std::min(100, std::max(5, env_int("HSSB_K4_SPLIT", 65))) / 100));
+        tM = t_tiles * std::min(40, std::max(0, env_int("HSSB_K4_MID", 0))) / 100;
+        if (tM && ((tM ^ t_tiles) & 1)) --tM;                        // the middle tiles must be symmetric about the centre
+        kA = std::min((t_tiles - tM) / 2, std::max(1, (t_tiles * std::min(100, std::max(5, env_int("HSSB_K4_SPLIT", 65))) / 100 + 1) / 2));
         HSSB_CUDA_OK(cudaMemsetAsync(sync_base, 0, SYNC_HEAD + sizeof(unsigned) * Q, st));
-        if (qM) HSSB_CUDA_OK(cudaMemsetAsync(tile_done, 0, sizeof(unsigned) * Q, st));
+        if (tM) {
+            HSSB_CUDA_OK(cudaMemsetAsync(tile_done, 0, sizeof(unsigned) * Q, st));
+            HSSB_CUDA_OK(cudaEventRecord(m->ev[0], st));           // the side stream starts behind the cleared flags (and behind the previous forward)
+        }
     } else {
         HSSB_CUDA_OK(cudaMemsetAsync(sync_base, 0, SYNC_HEAD, st));
     }
@@ -918,7 +1001,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     // ---- layer 1 -----------------------------------------------------------------------------------------------------------
     RecurSync l1;
     l1.timeout_flag = timeout_flag;
-    if (qM) { l1.tile_done = tile_done; l1.resident = resident; }
+    if (tM) { l1.tile_done = tile_done; l1.resident = resident; }
     int l1_ctas = 0;
     unsigned l1_signals = 0;
     bool l1_single = true;
@@ -958,25 +1041,47 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, job)) return rc;
         if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, st)) return rc;
     } else {
-        // NOTE: the middle launch was enqueued on the side stream right after layer 1's launch below would be too late -- it is
-        // issued here, behind the host-side launch of layer 1 (its kernels wait on device flags, not on the host)
-        if (qM && l1_single && l1.multicast) {
-            HSSB_CUDA_OK(cudaEventRecord(m->ev[0], st));            // (host order only: everything above is already enqueued)
+        bool mid_running = false;
+        if (tM && l1_single && l1.multicast && l1_ctas > 0 && m->sm_count - l1_ctas >= 16) {
+            // launch M: behind the gate on the side stream, concurrent with the layer-1 launches enqueued above
+            HSSB_CUDA_OK(cudaStreamWaitEvent(m->side_stream, m->ev[0], 0));
+            resident_gate_kernel<<<1, 32, 0, m->side_stream>>>(resident, (unsigned)l1_ctas, timeout_flag);
+            HSSB_LAUNCH_OK("resident_gate_kernel");
+            InprojJob mid;
+            mid.unit_mode = 1; mid.u_lo = 0; mid.n_units = tM; mid.shape = shape_small;
+            mid.next_item = next_item + 3; mid.chunk_done = chunk_done;
+            mid.src_done = tile_done; mid.src_need = l1_signals; mid.timeout_flag = timeout_flag;
+            mid.name = "tc_inproj_l1_mid";
+            if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, m->side_stream, mid)) return rc;
+            HSSB_CUDA_OK(cudaEventRecord(m->ev[3], m->side_stream));
+            mid_running = true;
+        } else {
+            tM = 0;
         }
+        const int m_lo = (t_tiles - tM) / 2, m_hi = m_lo + tM - 1;      // middle tiles [m_lo, m_hi] (empty when tM == 0)
         InprojJob a;
-        a.chunk_lo = 0; a.chunk_hi = qA; a.shape = 0; a.next_item = next_item + 1; a.chunk_done = chunk_done;
+        a.unit_mode = 0; a.u_lo = 0; a.n_units = 2 * kA; a.shape = 0; a.next_item = next_item + 1; a.chunk_done = chunk_done;
         if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, a)) return rc;
         HSSB_CUDA_OK(cudaEventRecord(m->ev[1], st));
         HSSB_CUDA_OK(cudaStreamWaitEvent(m->hi_stream, m->ev[1], 0));
         RecurSync l2;
-        l2.chunk_done = chunk_done; l2.chunk_need = chunk_need; l2.timeout_flag = timeout_flag;
+        l2.chunk_done = chunk_done; l2.chunk_need = chunk_need; l2.timeout_flag = timeout_flag; l2.resident = resident + 1;
         if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, m->hi_stream, nullptr, nullptr, &l2)) return rc;
         HSSB_CUDA_OK(cudaEventRecord(m->ev[2], m->hi_stream));
+        // launch B: chunks k in [kA, m_lo) and (m_hi, t_tiles - kA) of both directions, i.e. q in [2 kA, 2 m_lo) and [2 m_hi + 2, Q - 2 kA),
+        // held back until the recurrence's clusters are on the machine (they are placed first, B takes what is left)
         InprojJob b;
-        b.chunk_lo = qA; b.chunk_hi = Q - qM; b.shape = shape_small; b.next_item = next_item + 2; b.chunk_done = chunk_done;
+        b.unit_mode = 2; b.shape = shape_small; b.next_item = next_item + 2; b.chunk_done = chunk_done;
+        b.q_lo1 = 2 * kA; b.len1 = tM ? 2 * (m_lo - kA) : Q - 4 * kA;
+        b.q_lo2 = 2 * m_hi + 2; b.n_units = tM ? b.len1 + (Q - 2 * kA) - (2 * m_hi + 2) : b.len1;
         b.name = "tc_inproj_l1_tail";
-        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, b)) return rc;
+        if (b.n_units > 0) {
+            resident_gate_kernel<<<1, 32, 0, st>>>(resident + 1, (unsigned)l2.ctas_first, timeout_flag);
+            HSSB_LAUNCH_OK("resident_gate_kernel");
+            if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, b)) return rc;
+        }
         HSSB_CUDA_OK(cudaStreamWaitEvent(st, m->ev[2], 0));
+        if (mid_running) HSSB_CUDA_OK(cudaStreamWaitEvent(st, m->ev[3], 0));
     }
     return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st, timeout_flag);
 }
@@ -990,6 +1095,14 @@ extern "C" int hssb_debug_max_clusters(void)
     int n = 0;
     if (hssb::rc_dsmem_max_clusters(&n)) return -1;
     return n;
+}
+
+// Diagnostic: byte offset of the producer / consumer flag area inside the model workspace ({next_item[8], timeout flag, resident
+// counter} in the first 256 bytes, then chunk_done[8192] and tile_done[8192]); read by scripts/dump_sync.py.
+extern "C" long long hssb_debug_sync_offset(long long B, long long T)
+{
+    if (B <= 0 || T <= 0) return -1;
+    return (long long)hssb::tc_ws_layout(B, T).sync;
 }
 
 extern "C" int hssb_debug_trace(unsigned long long *buf, int steps)

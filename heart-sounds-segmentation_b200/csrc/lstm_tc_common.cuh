@@ -202,6 +202,7 @@ int rc_dsmem_launch(int nb, int s, int pair, const RecurParams &prm, int64_t rem
 int rc_dsmem_max_clusters(int *out);                 // co-resident 8-CTA clusters of the 32 x 3 DSMEM geometry
 int rc_pair_launch(int s, const RecurParams &prm, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st);
 // variant 2: one publisher per sub-tile, 3: per-warp publishing, 4: per-warp + two epilogue warps per TMEM quadrant
+int rc_mc_prepare();                                  // load / configure every default K5m variant on the current device
 // info (nullable): CTAs of the launch and the number of epilogue warps per direction that run the step loop (tile_done signals)
 struct RecurLaunchInfo { int ctas; unsigned signals_per_dir; };
 int rc_mc_launch(int s, int variant, bool fused, const RecurParams &prm, const __half *whh_frag, int64_t rem, int *cols_done,

@@ -49,11 +49,14 @@ _SIGNATURES = {
     "hssb_debug_inproj": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hssb_debug_trace": (c_int, [c_void_p, c_int]),
     "hssb_debug_max_clusters": (c_int, []),
+    "hssb_debug_sync_offset": (ctypes.c_longlong, [ctypes.c_longlong, ctypes.c_longlong]),
     "hssb_lstm_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hssb_lstm_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "hssb_confusion": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hssb_metrics_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hssb_auroc_hist": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "hssb_csv_scan": (c_int, [POINTER(c_char_p), c_int, c_int, c_void_p]),
+    "hssb_csv_parse": (c_int, [POINTER(c_char_p), c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hssb_prof_enable": (c_int, [c_int]),
     "hssb_prof_read": (c_int, [c_char_p, c_size_t]),
 }

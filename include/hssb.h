@@ -44,7 +44,8 @@ enum {
     HSSB_E_MODE = -5,      /* unknown output mode */
     HSSB_E_WORKSPACE = -6, /* workspace too small / misaligned */
     HSSB_E_MODEL = -7,     /* unsupported model geometry */
-    HSSB_E_DEVICE = -8     /* no sm_100 device / wrong architecture */
+    HSSB_E_DEVICE = -8,    /* no sm_100 device / wrong architecture */
+    HSSB_E_IO = -9         /* file cannot be read / malformed recording file */
 };
 
 /* output modes of the FSST wrapper (branch precedence of synchrosqueeze.py:56-65) */
@@ -143,6 +144,9 @@ int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B, int64_t T,
  * `steps` steps of every following recurrence launch.  buf: steps*4*16 uint64 on the device; NULL
  * disables.  Read by scripts/trace_recurrent.py. */
 int hssb_debug_trace(unsigned long long *buf, int steps);
+/* Diagnostic: byte offset of the flag area of the overlapped layer-2 projection inside the model workspace
+ * (next_item[8], timeout flag, resident counter | chunk_done[8192] | tile_done[8192], all 32-bit). */
+long long hssb_debug_sync_offset(long long B, long long T);
 /* Diagnostic: co-resident 8-CTA recurrence clusters (geometry 32x3) on the current device; <0 on error. */
 int hssb_debug_max_clusters(void);
 
@@ -185,6 +189,18 @@ int hssb_metrics_update(const float *logp, const int32_t *pred, const int64_t *t
  *   hist[c][target == c][min(nbins-1, floor(exp(logp[c]) * nbins))] += 1   (accumulates; caller zeroes; 2 <= nbins <= 4096).
  * Counters add across shards / ranks, so the job-wide AUROC comes from the all-reduced histogram. */
 int hssb_auroc_hist(const float *logp, const int64_t *target, int64_t n, int nbins, int64_t *hist, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Recording ingest: replaces the per-file pandas.read_csv of hss/datasets/heart_sounds.py:193-197 (_load_file) for a
+ * batch of files.  On-disk format: two-column CSV, first row a header (skipped), column 0 the PCG signal (decimal float),
+ * column 1 the state label (integer 1..4).  HOST entry points (no CUDA): files are parsed by `threads` host threads
+ * (<= 0: all cores) into caller-owned buffers -- pinned staging memory, from which the caller issues the async H2D copies.
+ *   hssb_csv_scan : rows_out[i] = data rows of paths[i]
+ *   hssb_csv_parse: file i -> signal / labels [offsets[i], offsets[i+1])  (offsets = prefix sums of the scanned rows;
+ *                   decimal -> float64 correctly rounded, narrowed to float32 as the reference's torch.tensor(..., dtype) does)
+ * ------------------------------------------------------------------------------------------ */
+int hssb_csv_scan(const char *const *paths, int n_files, int threads, int64_t *rows_out);
+int hssb_csv_parse(const char *const *paths, int n_files, int threads, const int64_t *offsets, float *signal, int64_t *labels);
 
 /* ------------------------------------------------------------------------------------------
  * Per-launch timing for bench.py: when enabled, every kernel launch is bracketed by CUDA events on

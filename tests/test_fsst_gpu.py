@@ -310,3 +310,35 @@ def test_second_device_after_first(lib):
             outs.append((feats.cpu(), f256.batch(x.to(dev)).cpu(), m(feats).cpu()))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_stream_recordings_pipeline_equals_per_recording_path(lib, tmp_path):
+    """hss.utils.ingest.stream_recordings: native multi-file parse -> pinned staging -> async H2D on a copy stream
+    -> FSST, pipelined over groups of files, gives the same tensors as load_recording_csv + recording_to_frames per file;
+    recordings shorter than one frame are skipped (heart_sounds.py:160-161)."""
+    from hss.transforms import FSST
+    from hss.utils import load_recording_csv, recording_to_frames, stream_recordings
+    from workloads import synth_pcg, synthetic_targets
+
+    lens = [4100, 2000, 1500, 9000, 3050, 2500, 7777]
+    paths = []
+    for i, n in enumerate(lens):
+        x = synth_pcg(n, 1000.0, 100 + i)
+        y = synthetic_targets(1, n)[0] + 1
+        path = tmp_path / f"{i:04d}.csv"
+        with open(path, "w") as f:
+            f.write("Signals,Labels\n")
+            for a, b in zip(x, y):
+                f.write(f"{float(a):.9g},{int(b)}\n")
+        paths.append(str(path))
+    f = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True)
+    streamed = list(stream_recordings(paths, f, group=3, threads=2))
+    expected = []
+    for p in paths:
+        x, y = load_recording_csv(p)
+        feats, labels = recording_to_frames(x, y, f)
+        if feats.shape[0]:
+            expected.append((feats, labels))
+    assert len(streamed) == len(expected) == 6                    # only the 1500-sample recording is shorter than one frame
+    for (a, la), (b, lb) in zip(streamed, expected):
+        assert a.shape == b.shape and torch.equal(a, b) and torch.equal(la, lb)

