@@ -113,11 +113,13 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 //
 //   xproj[dir][t][b][g'] = A[b,t,:] . W_ih[g',:] + (b_ih + b_hh)[g']          M = B*T, N = 1920, K = 48 / 512
 //
-// Per CTA one 128(t) x 160(g') output tile at a time; three fp16 MMAs per product (hi*hi, lo*hi, hi*lo).
-// The operands come out of L2, whose bandwidth is what bounds a lone CTA (it re-reads (128 + 160) x K x 4 bytes per tile).
+// Per CTA one 128(t) x 240(g') output tile at a time; three fp16 MMAs per product (hi*hi, hi*lo with the A operand kept in the
+// collector, lo*hi).  SS-mode MMAs are bound by shared-memory bandwidth -- every instruction reads its A (4 KB) and B (N x 32 B)
+// operands -- so N is as wide as a direction's 960 gate rows allow (4 n-tiles) and the hi*lo product reuses the A read.
+// The operands come out of L2, whose bandwidth is what bounds a lone CTA (it re-reads (128 + 240) x K x 4 bytes per tile).
 // The CTAs of a cluster work on CM consecutive batch rows x CN consecutive n-tiles of one time tile and share their loads by
 // TMA multicast: the A stage (128 rows) is fetched in CN parts by the CTAs of a cluster column and multicast to all of them,
-// the W stage (160 rows) in CM parts by the CTAs of a cluster row.
+// the W stage (240 rows) in CM parts by the CTAs of a cluster row.
 //
 // Work order.  The consumer of layer 2's projection is the layer-2 recurrence, whose forward direction walks t = 0.. and whose
 // reverse direction walks t = T-1..; the producer of its A operand is the layer-1 recurrence, which finishes the MIDDLE time
@@ -138,18 +140,18 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 //   warps 2..       : epilogue TMEM -> registers (+bias) -> swizzled smem tile -> coalesced 16-byte global stores
 //   last warp       : item scheduler (cluster rank 0 fetches the next item and posts it into every CTA's item ring)
 // ------------------------------------------------------------------------------------------------
-constexpr int IP_BM = 128, IP_BN = 160, IP_BK = 32;      // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
-constexpr int IP_NT_DIR = TC_G / IP_BN;                  // n-tiles per direction (6)
+constexpr int IP_BM = 128, IP_BN = 240, IP_BK = 32;      // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
+constexpr int IP_NT_DIR = TC_G / IP_BN;                  // n-tiles per direction (4)
 static_assert(IP_BM == TC_TT, "the M tile of the projection is the time tile of the producer / consumer flags");
-static_assert(TC_G % IP_BN == 0 && IP_BN % 32 == 0, "n-tiles must not straddle the two directions");
+static_assert(TC_G % IP_BN == 0 && IP_BN % 16 == 0 && IP_BN <= 256, "n-tiles must not straddle the two directions");
 constexpr int IP_A_BYTES = IP_BM * IP_BK * 2;            // one fp16 plane of the A stage (8 KB)
-constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the W stage (10 KB)
-constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 36 KB
+constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of the W stage (15 KB)
+constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 46 KB
 constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue transposition tile of one warp: 32 rows x 32 fp32 (4 KB)
-constexpr int IP_BIAS_BYTES = TC_NG * 4;                 // all 1920 folded biases, staged once per CTA
+constexpr int IP_BIAS_BYTES = (TC_NG + 32) * 4;          // all 1920 folded biases, staged once per CTA (+ slack for the last half chunk)
 constexpr int IP_RING = 4;                               // item ring depth
-constexpr int IP_NCHUNK = IP_BN / 32;                    // 32-column chunks of the accumulator (5)
-// STAGES / EPI_WARPS: layer 2's projection (K = 512) is main-loop bound: 5 smem stages, 4 epilogue warps.  Layer 1's (K = 48)
+constexpr int IP_NCHUNK = (IP_BN + 31) / 32;             // 32-column chunks of the accumulator (7 + one half chunk)
+// STAGES / EPI_WARPS: layer 2's projection (K = 512) is main-loop bound: 4 smem stages, 4 epilogue warps.  Layer 1's (K = 48)
 // is epilogue bound -- one warp per SMSP cannot hide the TMEM-load / shared-memory latencies of the drain: 3 stages, 8 warps.
 template <int STAGES, int EPI_WARPS, int CM, int CN>
 struct IpCfg {
@@ -161,14 +163,14 @@ struct IpCfg {
     static constexpr int CONSUMERS = 2 + EPI_WARPS;      // roles of one CTA that read an item slot
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two warps per TMEM lane quadrant");
-    static_assert(IP_NT_DIR % CN == 0 && IP_BM % CN == 0 && (IP_BN / CM) % 8 == 0, "cluster shape must split the tiles");
+    static_assert(IP_NT_DIR % CN == 0 && IP_BM % CN == 0 && IP_BN % CM == 0 && (IP_BN / CM) % 8 == 0, "cluster shape must split the tiles");
     static_assert((2 * STAGES + 4 + 2 * IP_RING) * 8 + 4 + 4 * IP_RING <= BAR_BYTES, "barrier area too small");
 };
-constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 160 columns (at 0 and 256)
+constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 240 columns (at 0 and 256)
 
 struct InprojParams {
     CUtensorMap a_hi, a_lo;   // [k, t, b] fp16, box (32, 128 / CN, 1), SW64   (my part of the A stage)
-    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 160 / CM), SW64  (my part of the W stage)
+    CUtensorMap w_hi, w_lo;   // [k, g'(1920)] fp16, box (32, 240 / CM), SW64  (my part of the W stage)
     float *out;               // xproj [dir][t][Bp][960] fp32
     const float *bias;        // [1920]
     long long B, Bp;          // batch, and the row pitch of xproj in batch rows (see xproj_pitch)
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<IP_TMEM_COLS>(tmem_slot);
-    for (int i = threadIdx.x; i < TC_NG; i += C::THREADS) bias_s[i] = __ldg(p.bias + i);
+    for (int i = threadIdx.x; i < TC_NG + 32; i += C::THREADS) bias_s[i] = i < TC_NG ? __ldg(p.bias + i) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
                     // my part of the A tile (rows cy * 128/CN ..) -> the CTAs of my cluster column
                     tma_load_3d_mc(st + cy * (IP_A_BYTES / CN), &p.a_hi, &full[s], kb * IP_BK, tl.t0 + cy * (IP_BM / CN), tl.b, mask_a);
                     tma_load_3d_mc(st + IP_A_BYTES + cy * (IP_A_BYTES / CN), &p.a_lo, &full[s], kb * IP_BK, tl.t0 + cy * (IP_BM / CN), tl.b, mask_a);
-                    // my part of the W tile (rows cx * 160/CM ..) -> the CTAs of my cluster row
+                    // my part of the W tile (rows cx * 240/CM ..) -> the CTAs of my cluster row
                     tma_load_2d_mc(st + 2 * IP_A_BYTES + cx * (IP_B_BYTES / CM), &p.w_hi, &full[s], kb * IP_BK, tl.n0 + cx * (IP_BN / CM), mask_w);
                     tma_load_2d_mc(st + 2 * IP_A_BYTES + IP_B_BYTES + cx * (IP_B_BYTES / CM), &p.w_lo, &full[s], kb * IP_BK, tl.n0 + cx * (IP_BN / CM), mask_w);
                 }
@@ -342,9 +344,9 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
                         const uint64_t da_lo = make_smem_desc(a_lo + off, 16, 512, LAYOUT_SW64);
                         const uint64_t db_hi = make_smem_desc(b_hi + off, 16, 512, LAYOUT_SW64);
                         const uint64_t db_lo = make_smem_desc(b_lo + off, 16, 512, LAYOUT_SW64);
-                        mma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
+                        mma_f16_ss_keep_a(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);      // a_hi stays in the collector ...
+                        mma_f16_ss_reuse_a(d_tmem, da_hi, db_lo, idesc, 1);                  // ... for the hi * lo product
                         mma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1);
-                        mma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1);
                     }
                     mma_commit_mc(&empty[s], mask_rel);    // frees this stage in every CTA that fills it
                 }
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
                     for (int j = 0; j < 8; ++j) {
                         const int row = 4 * j + rsub;
                         const float4 o = *reinterpret_cast<const float4 *>(ob + row * 128 + ((c16 ^ (row & 7)) << 4));
-                        if (tl.b < p.B && tl.t0 + q * 32 + row < p.T && !(p.debug & 1))              // (b >= B: padding tiles of the last batch group)
+                        if (tl.b < p.B && tl.t0 + q * 32 + row < p.T && c * 32 + c16 * 4 < IP_BN && !(p.debug & 1))   // (b >= B: padding tiles of the last batch group)
                             __stcs(reinterpret_cast<float4 *>(gout + (size_t)row * p.Bp * TC_G), o);
                     }
                     __syncwarp();
@@ -557,7 +559,7 @@ struct InprojJob {
     int unit_mode = 0;                    // 0 whole tiles outside-in, 1 whole tiles middle-out, 2 single-direction chunks
     int u_lo = 0, n_units = -1;           // modes 0 / 1: units of the order (n_units < 0: all t_tiles tiles)
     int q_lo1 = 0, len1 = 0, q_lo2 = 0;   // mode 2: chunks q_lo1 .. (len1 of them), then q_lo2 .. up to n_units in total
-    int shape = 0;                        // cluster shape CM x CN: 0 = 4x2, 1 = 2x2, 2 = 2x1, 3 = 1x1
+    int shape = 0;                        // cluster shape CM x CN: 0 = 2x4, 1 = 2x2, 2 = 2x1, 3 = 1x1
     unsigned *next_item = nullptr;        // zeroed device word: the item counter of this launch (required)
     unsigned *chunk_done = nullptr;       // [2 * t_tiles] zeroed device counters bumped per finished (tile, epilogue warp)
     const unsigned *src_done = nullptr;   // [2][t_tiles] progress of the layer-1 recurrence (middle-out launch only)
@@ -625,11 +627,11 @@ __global__ void resident_gate_kernel(const unsigned *__restrict__ resident, unsi
 static int tc_prepare()
 {
     int n = 0;
-    if (int rc = prepare_inproj<3, 8, 4, 2>(&n)) return rc;
-    if (int rc = prepare_inproj<5, 4, 4, 2>(&n)) return rc;
-    if (int rc = prepare_inproj<5, 4, 2, 2>(&n)) return rc;
-    if (int rc = prepare_inproj<5, 4, 2, 1>(&n)) return rc;
-    if (int rc = prepare_inproj<5, 4, 1, 1>(&n)) return rc;
+    if (int rc = prepare_inproj<3, 8, 2, 4>(&n)) return rc;
+    if (int rc = prepare_inproj<4, 4, 2, 4>(&n)) return rc;
+    if (int rc = prepare_inproj<4, 4, 2, 2>(&n)) return rc;
+    if (int rc = prepare_inproj<4, 4, 2, 1>(&n)) return rc;
+    if (int rc = prepare_inproj<4, 4, 1, 1>(&n)) return rc;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, resident_gate_kernel);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(resident_gate_kernel)");
@@ -641,7 +643,7 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
               float *xproj /*[2][T][B][960]*/, cudaStream_t st, const InprojJob &job, const unsigned *range = nullptr,
               const int *run_flag = nullptr)
 {
-    static const int SHAPES[4][2] = {{4, 2}, {2, 2}, {2, 1}, {1, 1}};
+    static const int SHAPES[4][2] = {{2, 4}, {2, 2}, {2, 1}, {1, 1}};
     if (job.shape < 0 || job.shape > 3 || !job.next_item) return fail(HSSB_E_MODE, "tc_inproj: bad job");
     const int CM = SHAPES[job.shape][0], CN = SHAPES[job.shape][1];
     InprojParams prm;
@@ -700,14 +702,14 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     const int n_items = (int)items;
     const char *name = job.name ? job.name : (layer == 0 ? "tc_inproj_l0" : "tc_inproj_l1");
     if (layer == 0) {                      // K = 48: epilogue bound -> 3 stages, 8 epilogue warps
-        if (job.shape != 0) return fail(HSSB_E_MODE, "tc_inproj: layer 1 runs on 4x2 clusters");
-        return launch_inproj<3, 8, 4, 2>(prm, n_items, name, st);
+        if (job.shape != 0) return fail(HSSB_E_MODE, "tc_inproj: layer 1 runs on 2x4 clusters");
+        return launch_inproj<3, 8, 2, 4>(prm, n_items, name, st);
     }
     switch (job.shape) {
-    case 0: return launch_inproj<5, 4, 4, 2>(prm, n_items, name, st);
-    case 1: return launch_inproj<5, 4, 2, 2>(prm, n_items, name, st);
-    case 2: return launch_inproj<5, 4, 2, 1>(prm, n_items, name, st);
-    default: return launch_inproj<5, 4, 1, 1>(prm, n_items, name, st);
+    case 0: return launch_inproj<4, 4, 2, 4>(prm, n_items, name, st);
+    case 1: return launch_inproj<4, 4, 2, 2>(prm, n_items, name, st);
+    case 2: return launch_inproj<4, 4, 2, 1>(prm, n_items, name, st);
+    default: return launch_inproj<4, 4, 1, 1>(prm, n_items, name, st);
     }
 }
 
