@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(RcCfg<NB, S, PAIR>::THREADS, 1) tc_recurrent_k
             };
             load_x();
             // outputs of (unit u, column 4i + j): element offset of step tt = o_base + i*o_stride + tt*480
-            const size_t o_stride = (size_t)4 * T * TC_OP;
-            size_t o_next = ((size_t)(b0 + j) * T + (dir ? T - 1 : 0)) * TC_OP + hcol;
+            const size_t o_stride = (size_t)4 * p.Tp * TC_OP;
+            size_t o_next = ((size_t)(b0 + j) * p.Tp + (dir ? T - 1 : 0)) * TC_OP + hcol;
             const long long o_step = (dir ? -1 : 1) * TC_OP;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + s * NB;
             if (p.stagger_ns) __nanosleep((unsigned)(s * p.stagger_ns));   // de-phase the sub-tiles of a cluster

@@ -530,7 +530,8 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
             for (int i = 0; i < S; ++i) live += (prm.b_base + ((long long)g * S + i) * RP_NBH < prm.B) ? 1u : 0u;
         info->signals_per_dir = live * RC_CL * 4 * EW;
     }
-    ProfScope prof("tc_recurrent", st);
+    // (the stand-in launch of the input-range guard is a no-op unless the guard fired: timed under its own name)
+    ProfScope prof((prm.skip_flag && !prm.skip_when) ? "range_standin" : (prm.layer ? "tc_recurrent_l2" : "tc_recurrent_l1"), st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
     return 0;

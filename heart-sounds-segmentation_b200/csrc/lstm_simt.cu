@@ -152,8 +152,11 @@ int simt_recurrent(const float *xproj, const float *const w_hhT[2], const float 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 head_kernel(const float *__restrict__ act, long long M, int H2, const float *__restrict__ lin_w,
-            const float *__restrict__ lin_b, float *__restrict__ logp, int32_t *__restrict__ labels, const int *__restrict__ poison)
+            const float *__restrict__ lin_b, float *__restrict__ logp, int32_t *__restrict__ labels, const int *__restrict__ poison,
+            long long T, long long Tp)
 {
+    // T != Tp: the activations are [B][Tp][H2] with Tp >= T time rows per window (act_pitch), the outputs dense [B][T]
+    auto src_row = [&](long long r) { return (T == Tp) ? r : (r / T) * Tp + r % T; };
     extern __shared__ float w_s[];   // [4][H2]
     // `poison` (nullable): a producer / consumer wait upstream gave up (see POLL_TIMEOUT_NS) -- the activations are not the
     // forward's result, so the outputs are NaN / -1 rather than plausible numbers
@@ -167,8 +170,8 @@ head_kernel(const float *__restrict__ act, long long M, int H2, const float *__r
         float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int nrow = (row0 + 1 < M) ? 2 : 1;
         if (vec) {
-            const float4 *a0 = reinterpret_cast<const float4 *>(act + (size_t)row0 * H2);
-            const float4 *a1 = reinterpret_cast<const float4 *>(act + (size_t)(row0 + nrow - 1) * H2);
+            const float4 *a0 = reinterpret_cast<const float4 *>(act + (size_t)src_row(row0) * H2);
+            const float4 *a1 = reinterpret_cast<const float4 *>(act + (size_t)src_row(row0 + nrow - 1) * H2);
             for (int k4 = lane; k4 < H2 / 4; k4 += 32) {
                 const float4 v0 = __ldcs(a0 + k4), v1 = __ldcs(a1 + k4);
 #pragma unroll
@@ -180,7 +183,7 @@ head_kernel(const float *__restrict__ act, long long M, int H2, const float *__r
             }
         } else {
             for (int r = 0; r < nrow; ++r) {
-                const float *a = act + (size_t)(row0 + r) * H2;
+                const float *a = act + (size_t)src_row(row0 + r) * H2;
                 for (int k = lane; k < H2; k += 32) {
                     const float v = __ldcs(a + k);
 #pragma unroll
@@ -216,8 +219,9 @@ head_kernel(const float *__restrict__ act, long long M, int H2, const float *__r
 }
 
 int head_forward(const float *act, int64_t M, int H2, const float *lin_w, const float *lin_b, float *logp,
-                 int32_t *labels, cudaStream_t st, const int *poison)
+                 int32_t *labels, cudaStream_t st, const int *poison, int64_t T, int64_t Tp)
 {
+    if (T <= 0 || Tp <= 0) T = Tp = 1;             // dense rows
     if (M == 0) return 0;
     long long blocks = (M + 15) / 16;
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -227,7 +231,7 @@ int head_forward(const float *act, int64_t M, int H2, const float *lin_w, const 
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(head_kernel)");
     }
     ProfScope prof("head", st);
-    head_kernel<<<(unsigned)blocks, 256, smem, st>>>(act, M, H2, lin_w, lin_b, logp, labels, poison);
+    head_kernel<<<(unsigned)blocks, 256, smem, st>>>(act, M, H2, lin_w, lin_b, logp, labels, poison, T, Tp);
     HSSB_LAUNCH_OK("head_kernel");
     return 0;
 }

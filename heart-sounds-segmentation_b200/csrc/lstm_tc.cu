@@ -18,6 +18,7 @@
 #include "lstm_tc_common.cuh"
 #include <mutex>
 #include <cstring>
+#include <climits>
 
 namespace hssb {
 
@@ -140,7 +141,12 @@ __global__ void pack_wih_kernel(const float *__restrict__ w, const float *__rest
 //   warps 2..       : epilogue TMEM -> registers (+bias) -> swizzled smem tile -> coalesced 16-byte global stores
 //   last warp       : item scheduler (cluster rank 0 fetches the next item and posts it into every CTA's item ring)
 // ------------------------------------------------------------------------------------------------
-constexpr int IP_BM = 128, IP_BN = 240, IP_BK = 32;      // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
+#ifndef HSSB_IP_BN
+#define HSSB_IP_BN 240
+#endif
+constexpr int IP_BM = 128, IP_BN = HSSB_IP_BN, IP_BK = 32;      // BK = 32 fp16 = 64-byte rows: SWIZZLE_64B
+// the large cluster shape (launches that have the machine to themselves) and the stage count of the layer-2 configuration
+constexpr int IP_BIG_CM = (IP_BN == 240) ? 2 : 4, IP_BIG_CN = (IP_BN == 240) ? 4 : 2, IP_L2_STAGES = (IP_BN == 240) ? 4 : 5;
 constexpr int IP_NT_DIR = TC_G / IP_BN;                  // n-tiles per direction (4)
 static_assert(IP_BM == TC_TT, "the M tile of the projection is the time tile of the producer / consumer flags");
 static_assert(TC_G % IP_BN == 0 && IP_BN % 16 == 0 && IP_BN <= 256, "n-tiles must not straddle the two directions");
@@ -163,7 +169,7 @@ struct IpCfg {
     static constexpr int CONSUMERS = 2 + EPI_WARPS;      // roles of one CTA that read an item slot
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two warps per TMEM lane quadrant");
-    static_assert(IP_NT_DIR % CN == 0 && IP_BM % CN == 0 && IP_BN % CM == 0 && (IP_BN / CM) % 8 == 0, "cluster shape must split the tiles");
+    static_assert((2 * IP_NT_DIR) % CN == 0 && IP_BM % CN == 0 && IP_BN % CM == 0 && (IP_BN / CM) % 8 == 0, "cluster shape must split the tiles");
     static_assert((2 * STAGES + 4 + 2 * IP_RING) * 8 + 4 + 4 * IP_RING <= BAR_BYTES, "barrier area too small");
 };
 constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 240 columns (at 0 and 256)
@@ -271,7 +277,9 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         const int slot = ring_it % IP_RING;
         mbar_wait_cluster(&item_full[slot], (ring_it / IP_RING) & 1);
         const int item = *reinterpret_cast<volatile int *>(&item_ring[slot]);
-        mbar_arrive_remote(&item_empty[slot], 0);
+        // relaxed: nothing but the value just read is ordered by this hand-back (a release would wait for the epilogue's
+        // outstanding global stores); the comparison makes the arrive depend on the load having returned
+        if (item != INT_MIN) mbar_arrive_remote_relaxed(&item_empty[slot], 0);
         ++ring_it;
         return item;
     };
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         mbar_wait_cluster(&item_full[slot], (ring_it / IP_RING) & 1);
         const int item = *reinterpret_cast<volatile int *>(&item_ring[slot]);
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&item_empty[slot], 0);
+        if (lane == 0 && item != INT_MIN) mbar_arrive_remote_relaxed(&item_empty[slot], 0);
         ++ring_it;
         return item;
     };
@@ -364,6 +372,20 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         constexpr int CSTEP = EPI_WARPS / 4;
         unsigned char *ob = out_base + (warp - 2) * IP_OUT_TILE;
         uint32_t tile = 0;
+        // The completion of a tile is published one tile late, right after the NEXT accumulator has been pulled into registers:
+        // the fence in front of the flag then only waits for stores issued a whole tile ago (long since written) instead of
+        // stalling the drain of the tile that follows.
+        int pending_q = -1;
+        auto publish_pending = [&]() {
+            if (pending_q >= 0) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(p.chunk_done + pending_q, 1u);
+                }
+                pending_q = -1;
+            }
+        };
         for (int item = next_item_warp(); item < n_items; item = next_item_warp(), ++tile) {
             const Tile tl = tile_of(item);
             const int nl0 = tl.n0 - tl.dir * TC_G;
@@ -381,6 +403,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    publish_pending();                      // (the previous tile's stores: see above)
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -410,15 +433,9 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
                     __syncwarp();
                 }
             }
-            if (p.chunk_done && tl.b < p.B) {
-                // this warp's part of the tile is stored: publish it (the recurrence counts real tiles x epilogue warps per chunk)
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    atomicAdd(p.chunk_done + tl.q, 1u);
-                }
-            }
+            if (p.chunk_done && tl.b < p.B) pending_q = tl.q;      // this warp's part of a real tile is stored (the recurrence counts tiles x epilogue warps)
         }
+        publish_pending();
     } else {
         // ===== item scheduler (cluster rank 0): the next item of the launch -> every CTA's ring =====
         if (rank == 0 && elect_one()) {
@@ -627,11 +644,11 @@ __global__ void resident_gate_kernel(const unsigned *__restrict__ resident, unsi
 static int tc_prepare()
 {
     int n = 0;
-    if (int rc = prepare_inproj<3, 8, 2, 4>(&n)) return rc;
-    if (int rc = prepare_inproj<4, 4, 2, 4>(&n)) return rc;
-    if (int rc = prepare_inproj<4, 4, 2, 2>(&n)) return rc;
-    if (int rc = prepare_inproj<4, 4, 2, 1>(&n)) return rc;
-    if (int rc = prepare_inproj<4, 4, 1, 1>(&n)) return rc;
+    if (int rc = prepare_inproj<3, 8, IP_BIG_CM, IP_BIG_CN>(&n)) return rc;
+    if (int rc = prepare_inproj<IP_L2_STAGES, 4, IP_BIG_CM, IP_BIG_CN>(&n)) return rc;
+    if (int rc = prepare_inproj<IP_L2_STAGES, 4, 2, 2>(&n)) return rc;
+    if (int rc = prepare_inproj<IP_L2_STAGES, 4, 2, 1>(&n)) return rc;
+    if (int rc = prepare_inproj<IP_L2_STAGES, 4, 1, 1>(&n)) return rc;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, resident_gate_kernel);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(resident_gate_kernel)");
@@ -641,9 +658,10 @@ static int tc_prepare()
 // One layer's input projection on the tensor cores.  a_hi/a_lo: [B*T][pitch] fp16 planes.
 int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *a_lo, int pitch_elems, int64_t B, int64_t T,
               float *xproj /*[2][T][B][960]*/, cudaStream_t st, const InprojJob &job, const unsigned *range = nullptr,
-              const int *run_flag = nullptr)
+              const int *run_flag = nullptr, int64_t t_pitch = 0)
 {
-    static const int SHAPES[4][2] = {{2, 4}, {2, 2}, {2, 1}, {1, 1}};
+    if (t_pitch <= 0) t_pitch = T;          // time rows per window of the A planes
+    static const int SHAPES[4][2] = {{IP_BIG_CM, IP_BIG_CN}, {2, 2}, {2, 1}, {1, 1}};
     if (job.shape < 0 || job.shape > 3 || !job.next_item) return fail(HSSB_E_MODE, "tc_inproj: bad job");
     const int CM = SHAPES[job.shape][0], CN = SHAPES[job.shape][1];
     InprojParams prm;
@@ -653,7 +671,7 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     const int kreal = kreal_of_layer(layer, m->F);
     {
         const uint64_t dims[3] = {(uint64_t)(layer == 0 ? Kp : kreal), (uint64_t)T, (uint64_t)B};
-        const uint64_t strides[2] = {(uint64_t)pitch_elems * 2, (uint64_t)T * pitch_elems * 2};
+        const uint64_t strides[2] = {(uint64_t)pitch_elems * 2, (uint64_t)t_pitch * pitch_elems * 2};
         const uint32_t box[3] = {IP_BK, (uint32_t)(IP_BM / CN), 1};
         if (int rc = make_tmap(&prm.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
         if (int rc = make_tmap(&prm.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
@@ -702,14 +720,14 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     const int n_items = (int)items;
     const char *name = job.name ? job.name : (layer == 0 ? "tc_inproj_l0" : "tc_inproj_l1");
     if (layer == 0) {                      // K = 48: epilogue bound -> 3 stages, 8 epilogue warps
-        if (job.shape != 0) return fail(HSSB_E_MODE, "tc_inproj: layer 1 runs on 2x4 clusters");
-        return launch_inproj<3, 8, 2, 4>(prm, n_items, name, st);
+        if (job.shape != 0) return fail(HSSB_E_MODE, "tc_inproj: layer 1 runs on the large clusters");
+        return launch_inproj<3, 8, IP_BIG_CM, IP_BIG_CN>(prm, n_items, name, st);
     }
     switch (job.shape) {
-    case 0: return launch_inproj<4, 4, 2, 4>(prm, n_items, name, st);
-    case 1: return launch_inproj<4, 4, 2, 2>(prm, n_items, name, st);
-    case 2: return launch_inproj<4, 4, 2, 1>(prm, n_items, name, st);
-    default: return launch_inproj<4, 4, 1, 1>(prm, n_items, name, st);
+    case 0: return launch_inproj<IP_L2_STAGES, 4, IP_BIG_CM, IP_BIG_CN>(prm, n_items, name, st);
+    case 1: return launch_inproj<IP_L2_STAGES, 4, 2, 2>(prm, n_items, name, st);
+    case 2: return launch_inproj<IP_L2_STAGES, 4, 2, 1>(prm, n_items, name, st);
+    default: return launch_inproj<IP_L2_STAGES, 4, 1, 1>(prm, n_items, name, st);
     }
 }
 
@@ -851,12 +869,13 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
     prm.h0 = h0; prm.c0 = c0; prm.hn = hn; prm.cn = cn;
     prm.out_hi = out_hi; prm.out_lo = out_lo; prm.out_f32 = out_f32;
     prm.B = B; prm.T = T;
+    prm.Tp = act_pitch(T);
     prm.Bp = xproj_pitch(B);
     {
         const bool f32 = out_f32 != nullptr;
         const uint64_t es = f32 ? 4 : 2;
         const uint64_t dims[3] = {(uint64_t)TC_OP, (uint64_t)T, (uint64_t)B};
-        const uint64_t strides[2] = {(uint64_t)TC_OP * es, (uint64_t)T * TC_OP * es};
+        const uint64_t strides[2] = {(uint64_t)TC_OP * es, (uint64_t)prm.Tp * TC_OP * es};
         const uint32_t box[3] = {8, 1, RP_NBH};
         const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
         if (int rc = make_tmap(&prm.out_map[0], dt, 3, f32 ? (const void *)out_f32 : (const void *)out_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
@@ -920,9 +939,10 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
     w.xhi = off;   off += align_up(sizeof(__half) * Mp * 64, 1024);
     w.xlo = off;   off += align_up(sizeof(__half) * Mp * 64, 1024);
     w.xproj = off; off += align_up(sizeof(float) * 2 * (size_t)T * xproj_pitch(B) * TC_G, 1024);
-    w.o1hi = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
-    w.o1lo = off;  off += align_up(sizeof(__half) * M * TC_OP, 1024);
-    w.out2 = off;  off += align_up(sizeof(float) * M * TC_OP, 1024);
+    const size_t Ma = (size_t)B * act_pitch(T);                  // rows of the pitched [B][Tp][512] activations
+    w.o1hi = off;  off += align_up(sizeof(__half) * Ma * TC_OP, 1024);
+    w.o1lo = off;  off += align_up(sizeof(__half) * Ma * TC_OP, 1024);
+    w.out2 = off;  off += align_up(sizeof(float) * Ma * TC_OP, 1024);
     w.hn = off;    off += align_up(sizeof(float) * 2 * B * TC_H, 1024);
     w.cn = off;    off += align_up(sizeof(float) * 2 * B * TC_H, 1024);
     w.gather = off; off += TC_GATHER_BYTES;
@@ -1040,7 +1060,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     if (!overlap) {
         InprojJob job;
         job.next_item = next_item + 1;
-        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, job)) return rc;
+        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, job, nullptr, nullptr, act_pitch(T))) return rc;
         if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, st)) return rc;
     } else {
         bool mid_running = false;
@@ -1054,7 +1074,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
             mid.next_item = next_item + 3; mid.chunk_done = chunk_done;
             mid.src_done = tile_done; mid.src_need = l1_signals; mid.timeout_flag = timeout_flag;
             mid.name = "tc_inproj_l1_mid";
-            if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, m->side_stream, mid)) return rc;
+            if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, m->side_stream, mid, nullptr, nullptr, act_pitch(T))) return rc;
             HSSB_CUDA_OK(cudaEventRecord(m->ev[3], m->side_stream));
             mid_running = true;
         } else {
@@ -1063,7 +1083,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         const int m_lo = (t_tiles - tM) / 2, m_hi = m_lo + tM - 1;      // middle tiles [m_lo, m_hi] (empty when tM == 0)
         InprojJob a;
         a.unit_mode = 0; a.u_lo = 0; a.n_units = 2 * kA; a.shape = 0; a.next_item = next_item + 1; a.chunk_done = chunk_done;
-        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, a)) return rc;
+        if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, a, nullptr, nullptr, act_pitch(T))) return rc;
         HSSB_CUDA_OK(cudaEventRecord(m->ev[1], st));
         HSSB_CUDA_OK(cudaStreamWaitEvent(m->hi_stream, m->ev[1], 0));
         RecurSync l2;
@@ -1080,12 +1100,12 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         if (b.n_units > 0) {
             resident_gate_kernel<<<1, 32, 0, st>>>(resident + 1, (unsigned)l2.ctas_first, timeout_flag);
             HSSB_LAUNCH_OK("resident_gate_kernel");
-            if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, b)) return rc;
+            if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, b, nullptr, nullptr, act_pitch(T))) return rc;
         }
         HSSB_CUDA_OK(cudaStreamWaitEvent(st, m->ev[2], 0));
         if (mid_running) HSSB_CUDA_OK(cudaStreamWaitEvent(st, m->ev[3], 0));
     }
-    return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st, timeout_flag);
+    return head_forward(out2, M, TC_OP, m->tc_lin_w, m->lin_b, logp, labels, st, timeout_flag, T, act_pitch(T));
 }
 
 }  // namespace hssb

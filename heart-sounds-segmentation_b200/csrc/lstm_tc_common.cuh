@@ -22,6 +22,10 @@ constexpr int TC_OP = 512;
 // xproj is [dir][t][Bp][960] with an odd number of batch rows per time step: with B = 512 the t stride would be 15 * 2^17 bytes and
 // every one of the 128 rows a projection tile writes would fall on the same HBM channel / L2 slice.
 static inline long long xproj_pitch(long long B) { return B | 1; }
+// The [B][T][512] activations between the layers (relu(h1) planes, relu(h2)) are pitched to an ODD number of time rows per
+// window for the same reason: with T = 2000 consecutive windows would be 2 000 KB apart, and the CTAs of the projection GEMM --
+// which all work on the same time tile of different windows -- would keep hitting the same HBM channels / L2 slices.
+static inline long long act_pitch(long long T) { return T | 1; }
 constexpr size_t TC_GATHER_BYTES = (size_t)16 * 8 * 3 * 2 * 4096;   // L2 scratch of the multicast all-gather: [cluster][rank][S][parity][4 KB]
 
 
@@ -76,6 +80,7 @@ struct RecurParams {
     __half *out_hi, *out_lo;    // layer 1: relu(h) planes [B*T][480]  (nullptr for layer 2)
     float *out_f32;             // layer 2: relu(h) [B*T][480]         (nullptr for layer 1)
     long long B, T;
+    long long Tp;               // time rows per window of the [B][Tp][512] outputs (act_pitch(T))
     long long Bp;               // row pitch of xproj in batch rows (xproj_pitch(B))
     int b_base;                 // first batch column handled by this launch
     int groups;                 // groups of S*NB columns per direction in this launch

@@ -40,7 +40,7 @@ int simt_inproj(const float *A, int64_t M, int K, const float *Wt, const float *
 int simt_recurrent(const float *xproj /*[2][B*T][4H]*/, const float *const w_hhT[2], const float *h0, const float *c0,
                    int64_t B, int64_t T, int H, float *out /*[B,T,2H] relu'd*/, float *hn, float *cn, cudaStream_t st);
 int head_forward(const float *act /*[M,2H] already relu'd*/, int64_t M, int H2, const float *lin_w, const float *lin_b,
-                 float *logp, int32_t *labels, cudaStream_t st, const int *poison = nullptr);
+                 float *logp, int32_t *labels, cudaStream_t st, const int *poison = nullptr, int64_t T = 0, int64_t Tp = 0);
 
 // tcgen05 path (lstm_tc.cu)
 size_t tc_pack_bytes(int F, int H);

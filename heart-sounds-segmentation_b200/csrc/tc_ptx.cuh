@@ -48,6 +48,15 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta)
         "r"(cta)
         : "memory");
 }
+// The same without release semantics (no memory barrier): for hand-backs that order nothing but a value already in a register.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t *bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
 // upper bound (ns) the hardware may keep a waiting thread suspended before try_wait returns false:
 // long enough that waiting warps do not burn issue slots; completion of the phase wakes the thread
 constexpr uint32_t MBAR_SUSPEND_HINT_NS = 20000;

@@ -52,6 +52,10 @@ _SIGNATURES = {
     "hssb_debug_sync_offset": (ctypes.c_longlong, [ctypes.c_longlong, ctypes.c_longlong]),
     "hssb_lstm_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hssb_lstm_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "hssb_ce_head_forward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hssb_ce_head_backward": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hssb_clip_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int64, c_float,
+                                    c_void_p, c_void_p, c_void_p]),
     "hssb_confusion": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hssb_metrics_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hssb_auroc_hist": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),

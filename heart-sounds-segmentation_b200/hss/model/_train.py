@@ -98,3 +98,61 @@ def training_forward(model, x: torch.Tensor) -> torch.Tensor:
     out, _, _ = _layer(model.lstm_2, out, hn, cn)
     out = model.dropout(F.relu(out))
     return F.log_softmax(model.linear(out), dim=2)
+
+
+class HeadLossFunction(torch.autograd.Function):
+    """``(act[B,T,2H], weight[4,2H], bias[4], target[B,T]) -> (loss, logp[B,T,4])``: linear + log_softmax (segmenter.py:86-87)
+    and ``nn.CrossEntropyLoss`` on the permuted output (main.py:69-70) in one kernel each way (``hssb_ce_head_forward`` /
+    ``hssb_ce_head_backward``).  ``logp`` is returned for the metrics and carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, act, weight, bias, target):
+        if not act.is_cuda:
+            raise RuntimeError("the fused head + loss runs on the GPU (no CPU fallback)")
+        act = act.detach().to(torch.float32).contiguous()
+        weight = weight.detach().to(torch.float32).contiguous()
+        bias = bias.detach().to(torch.float32).contiguous()
+        target = target.to(device=act.device, dtype=torch.int64).contiguous()
+        B, T, K = act.shape
+        M = B * T
+        logp = torch.empty((B, T, 4), dtype=torch.float32, device=act.device)
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=act.device)
+        with torch.cuda.device(act.device):
+            rc = _lib.lib().hssb_ce_head_forward(act.data_ptr(), M, K, weight.data_ptr(), bias.data_ptr(), target.data_ptr(),
+                                                 logp.data_ptr(), loss_sum.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "hssb_ce_head_forward")
+        ctx.save_for_backward(act, weight, target, logp)
+        ctx.mark_non_differentiable(logp)
+        return (loss_sum / max(M, 1)).to(torch.float32).reshape(()), logp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss, _d_logp):
+        act, weight, target, logp = ctx.saved_tensors
+        B, T, K = act.shape
+        M = B * T
+        d_act = torch.empty_like(act)
+        d_w = torch.zeros_like(weight)
+        d_b = torch.zeros(4, dtype=torch.float32, device=act.device)
+        scale = float(d_loss) / max(M, 1)
+        with torch.cuda.device(act.device):
+            rc = _lib.lib().hssb_ce_head_backward(act.data_ptr(), logp.data_ptr(), M, K, weight.data_ptr(), target.data_ptr(), scale,
+                                                  d_act.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "hssb_ce_head_backward")
+        return d_act, d_w, d_b, None
+
+
+def training_loss(model, x: torch.Tensor, y: torch.Tensor):
+    """``(loss, logp)`` of one training batch: ``loss_fn(model(x).permute(0, 2, 1), y)`` of reference main.py:67-70 with the head
+    and the loss fused (``HeadLossFunction``); ``logp`` feeds the metrics exactly as ``model(x)`` would."""
+    p = model.linear.weight
+    if not (x.is_cuda and p.is_cuda and x.device == p.device):
+        raise RuntimeError("training mode needs the module and its input on the same CUDA device (model.to('cuda'))")
+    model._check_input(x)
+    h0 = model.h0.to(device=x.device, dtype=torch.float32)
+    c0 = model.c0.to(device=x.device, dtype=torch.float32)
+    out, hn, cn = _layer(model.lstm_1, x, h0, c0)
+    out = model.dropout(F.relu(out))
+    out, _, _ = _layer(model.lstm_2, out, hn, cn)
+    out = model.dropout(F.relu(out))
+    return HeadLossFunction.apply(out, model.linear.weight, model.linear.bias, y)

@@ -184,6 +184,13 @@ class HeartSoundSegmenter(nn.Module):
             return training_forward(self, x)
         return self._run(x, True, False)[0]
 
+    def training_loss(self, x: torch.Tensor, y: torch.Tensor):
+        """``(loss, logp)`` of a training batch: what ``loss_fn(self(x).permute(0, 2, 1), y)`` computes in reference
+        main.py:67-70, with linear + log-softmax + cross-entropy (and their backward) fused into one kernel each way."""
+        from ._train import training_loss
+
+        return training_loss(self, x, y)
+
     @torch.no_grad()
     def predict(self, x: torch.Tensor) -> torch.Tensor:
         """argmax labels ``[B, T]`` (int32), computed in the head kernel without materialising logp."""

@@ -169,6 +169,26 @@ int hssb_lstm_train_backward(float *gates, const float *cells, const float *w_hh
                              const float *d_out, const float *d_hn, const float *d_cn, int64_t B, int64_t T, int H,
                              float *dh0, float *dc0, void *stream);
 
+/* Fused head + loss of the training step: linear(2H -> 4) + log_softmax (segmenter.py:86-87) + nn.CrossEntropyLoss on the
+ * permuted output (main.py:69-70).  act [M,K] f32 (K = 2H <= 512, after ReLU / dropout), w [4,K], b [4], target [M] int64.
+ * forward : logp [M,4]; *loss_sum (float64 device, caller zeroes) += sum over rows of (lse(logp) - logp[target]).
+ * backward: with scale = upstream gradient / number of rows (mean reduction): d_act [M,K] (written), d_w [4,K] and d_b [4]
+ *           (accumulated: caller zeroes). */
+int hssb_ce_head_forward(const float *act, int64_t M, int K, const float *w, const float *b, const int64_t *target,
+                         float *logp, double *loss_sum, void *stream);
+int hssb_ce_head_backward(const float *act, const float *logp, int64_t M, int K, const float *w, const int64_t *target,
+                          float scale, float *d_act, float *d_w, float *d_b, void *stream);
+
+/* Gradient clipping by global norm (pl.Trainer(gradient_clip_val=1), main.py:226; torch.nn.utils.clip_grad_norm_ semantics:
+ * coef = min(1, max_norm / (norm + 1e-6)); max_norm <= 0 disables) fused with one torch.optim.Adam step (main.py:130: default
+ * betas / eps, no weight decay) over all n_tensors (<= 32) parameter tensors: two launches.  params / grads / exp_avg /
+ * exp_avg_sq: HOST arrays of device pointers, numel: host array; lr = the step's learning rate (the LambdaLR 0.9^epoch schedule of
+ * main.py:133-134 is applied by the caller); step counts from 1; norm2_scratch: 8 bytes of device scratch; grad_norm_out
+ * (nullable, device): the un-clipped global norm. */
+int hssb_clip_adam_step(int n_tensors, float *const *params, const float *const *grads, float *const *exp_avg,
+                        float *const *exp_avg_sq, const int64_t *numel, float lr, float beta1, float beta2, float eps,
+                        int64_t step, float max_norm, double *norm2_scratch, float *grad_norm_out, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Metric counters: replaces the torchmetrics confusion statistics of main.py:36-62.
  * cm16 [4,4] int64 device, cm[target][pred] += 1 (accumulates; caller zeroes).

@@ -17,6 +17,6 @@ except Exception as e:
 PY
 }
 for spec in "$@"; do
-    label=$(echo "$spec" | tr ' =' '__')
+    label=$(echo "$spec" | sed -e 's#[^ ]*/##g' | tr ' =' '__')
     run "$label" $spec
 done

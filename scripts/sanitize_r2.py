@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Workloads for compute-sanitizer (racecheck / synccheck / memcheck): every default kernel at sizes that span several
+clusters, the overlapped projection (T >= 1024) and one training step through the cluster kernels.
+
+    compute-sanitizer --tool racecheck python scripts/sanitize_r2.py [fsst] [lstm] [overlap] [train]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "heart-sounds-segmentation_b200"))
+sys.path.insert(0, ROOT)
+import torch
+from hss.model.segmenter import HeartSoundSegmenter
+from hss.transforms import FSST
+from workloads import reference_window, synth_pcg_batch
+
+what = sys.argv[1:] or ["fsst", "lstm", "overlap", "train"]
+if "fsst" in what:
+    for B, N in ((3, 300), (37, 170)):
+        x = torch.from_numpy(synth_pcg_batch(B, N)).cuda()
+        feats = FSST(1000.0, window=reference_window(128), truncate_freq=(25, 200), stack=True).batch(x)
+        torch.cuda.synchronize()
+        print("fsst", B, N, float(feats.abs().mean()))
+if "lstm" in what:
+    for B, T in ((70, 24), (200, 12)):          # 3 and 7 sub-tiles per direction: several clusters, ragged last group
+        torch.manual_seed(1)
+        m = HeartSoundSegmenter(input_size=44, batch_size=B).eval()
+        logp, labels = m.forward_with_labels(torch.randn(B, T, 44, device="cuda"))
+        torch.cuda.synchronize()
+        print("lstm", B, T, float(logp.exp().sum(-1).mean()), int(labels.sum()))
+if "overlap" in what:
+    B, T = 40, 1030                              # 9 time tiles: the projection runs as launches M / A / B around the recurrences
+    os.environ.setdefault("HSSB_K4_MID", "25")
+    torch.manual_seed(2)
+    m = HeartSoundSegmenter(input_size=44, batch_size=B).eval()
+    logp, labels = m.forward_with_labels(torch.randn(B, T, 44, device="cuda"))
+    torch.cuda.synchronize()
+    print("overlap", B, T, float(logp.exp().sum(-1).mean()), int(labels.sum()))
+if "train" in what:
+    B, T = 9, 20
+    torch.manual_seed(3)
+    m = HeartSoundSegmenter(input_size=44, batch_size=B).cuda().train()
+    m.h0, m.c0 = m.h0.cuda(), m.c0.cuda()
+    x = torch.randn(B, T, 44, device="cuda")
+    y = torch.randint(0, 4, (B, T), device="cuda")
+    loss = torch.nn.functional.cross_entropy(m(x).permute(0, 2, 1), y)
+    loss.backward()
+    torch.cuda.synchronize()
+    print("train", float(loss))

@@ -137,3 +137,51 @@ def test_cluster_and_streaming_kernels_agree(lib, monkeypatch):
         assert abs(loss - results[2][0]) < 1e-6 * abs(results[2][0])
         for name in grads:
             assert rel_err(grads[name], results[2][1][name]) < 2e-5, name
+
+
+def test_fused_head_loss_and_clip_adam_match_the_eager_ops(lib):
+    """hssb_ce_head_forward / _backward (linear + log_softmax + CrossEntropyLoss of segmenter.py:86-87 + main.py:69-70) and
+    hssb_clip_adam_step (clip_grad_norm_ 1.0 + Adam lr 0.01 * 0.9^epoch, main.py:130-135,226) against the eager torch ops the
+    reference runs, over three steps of two epochs on two identically initialised modules (dropout off: p = 0)."""
+    from hss.optim import ClipAdam
+
+    B, T, F = 6, 40, 44
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, F, generator=g).cuda()
+    y = torch.randint(0, 4, (B, T), generator=g).cuda()
+    a = make_model(5, F, B, 240).cuda().train()
+    b = make_model(5, F, B, 240).cuda().train()
+    a.dropout.p = b.dropout.p = 0.0
+    opt_a = torch.optim.Adam(a.parameters(), lr=0.01)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt_a, lr_lambda=lambda epoch: 0.9 ** epoch)
+    opt_b = ClipAdam(b.parameters(), lr=0.01, max_norm=1.0)
+    for step in range(3):
+        opt_a.zero_grad()
+        logp_a = a(x)
+        loss_a = torch.nn.functional.cross_entropy(logp_a.permute(0, 2, 1), y)
+        loss_a.backward()
+        norm_a = torch.nn.utils.clip_grad_norm_(a.parameters(), 1.0)
+        opt_b.zero_grad()
+        loss_b, logp_b = b.training_loss(x, y)
+        loss_b.backward()
+        assert abs(float(loss_a) - float(loss_b)) < 2e-6 * max(1.0, abs(float(loss_a)))
+        assert (logp_a.detach() - logp_b).abs().max() < 2e-6
+        for (name, pa), pb in zip(a.named_parameters(), b.parameters()):
+            # pa.grad was clipped in place; pb.grad is still the raw gradient
+            coef = min(1.0, 1.0 / (float(norm_a) + 1e-6))
+            assert rel_err(pb.grad * coef, pa.grad) < 2e-5, (step, name)
+        opt_a.step()
+        opt_b.step()
+        assert abs(float(opt_b.grad_norm) - float(norm_a)) < 1e-5 * float(norm_a)
+        for (name, pa), pb in zip(a.named_parameters(), b.parameters()):
+            assert rel_err(pb.detach(), pa.detach()) < 1e-5, (step, name)
+        if step == 1:                       # epoch boundary: lr 0.01 -> 0.009
+            sched.step()
+            opt_b.set_epoch(1)
+            assert abs(opt_b.current_lr - opt_a.param_groups[0]["lr"]) < 1e-12
+    b.eval()
+    with torch.no_grad():
+        out = b(x)                          # the inference kernels see the updated (repacked) parameters
+    a.eval()
+    with torch.no_grad():
+        assert (out - a(x)).abs().max() < 1e-4
