@@ -155,7 +155,7 @@ constexpr int IP_B_BYTES = IP_BN * IP_BK * 2;            // one fp16 plane of th
 constexpr int IP_STAGE_BYTES = 2 * IP_A_BYTES + 2 * IP_B_BYTES;   // 46 KB
 constexpr int IP_OUT_TILE = 32 * 32 * 4;                 // epilogue transposition tile of one warp: 32 rows x 32 fp32 (4 KB)
 constexpr int IP_BIAS_BYTES = (TC_NG + 32) * 4;          // all 1920 folded biases, staged once per CTA (+ slack for the last half chunk)
-constexpr int IP_RING = 4;                               // item ring depth
+constexpr int IP_RING = 8;                               // item ring depth: the producer runs up to this many items ahead of the slowest epilogue warp of the cluster
 constexpr int IP_NCHUNK = (IP_BN + 31) / 32;             // 32-column chunks of the accumulator (7 + one half chunk)
 // STAGES / EPI_WARPS: layer 2's projection (K = 512) is main-loop bound: 4 smem stages, 4 epilogue warps.  Layer 1's (K = 48)
 // is epilogue bound -- one warp per SMSP cannot hide the TMEM-load / shared-memory latencies of the drain: 3 stages, 8 warps.
@@ -438,19 +438,22 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         publish_pending();
     } else {
         // ===== item scheduler (cluster rank 0): the next item of the launch -> every CTA's ring =====
+        // One round trip per item: the CL remote stores are issued back to back, ONE cluster-scope fence orders them, then CL
+        // relaxed remote arrives publish the slot (a release-arrive per CTA would wait for its own store's acknowledgement CL times,
+        // about as long as a tile takes); the next item is fetched from the global counter while the slot is being waited for.
         if (rank == 0 && elect_one()) {
-            uint32_t it = 0;
-            for (;; ++it) {
+            int item = (int)atomicAdd(p.next_item, 1u);
+            for (uint32_t it = 0;; ++it) {
                 const int slot = it % IP_RING;
                 mbar_wait_cluster(&item_empty[slot], ((it / IP_RING) & 1) ^ 1);
-                const int item = (int)atomicAdd(p.next_item, 1u);
                 const uint32_t ring_addr = smem_u32(&item_ring[slot]);
 #pragma unroll
-                for (int r = 0; r < CL; ++r) {
-                    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa(ring_addr, r)), "r"(item) : "memory");
-                    mbar_arrive_remote(&item_full[slot], r);       // release.cluster: the store above is visible to the waiter
-                }
+                for (int r = 0; r < CL; ++r) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa(ring_addr, r)), "r"(item) : "memory");
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#pragma unroll
+                for (int r = 0; r < CL; ++r) mbar_arrive_remote_relaxed(&item_full[slot], r);
                 if (item >= n_items) break;
+                item = (int)atomicAdd(p.next_item, 1u);
             }
         }
     }
@@ -1008,9 +1011,9 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     // under layer 1); what lies between: launch B (single-direction chunks in the order the layer-2 recurrence needs them, under it)
     int kA = t_tiles / 2, tM = 0;
     if (overlap) {
-        tM = t_tiles * std::min(40, std::max(0, env_int("HSSB_K4_MID", 0))) / 100;
+        tM = t_tiles * std::min(40, std::max(0, env_int("HSSB_K4_MID", 30))) / 100;
         if (tM && ((tM ^ t_tiles) & 1)) --tM;                        // the middle tiles must be symmetric about the centre
-        kA = std::min((t_tiles - tM) / 2, std::max(1, (t_tiles * std::min(100, std::max(5, env_int("HSSB_K4_SPLIT", 65))) / 100 + 1) / 2));
+        kA = std::min((t_tiles - tM) / 2, std::max(1, (t_tiles * std::min(100, std::max(5, env_int("HSSB_K4_SPLIT", 40))) / 100 + 1) / 2));
         HSSB_CUDA_OK(cudaMemsetAsync(sync_base, 0, SYNC_HEAD + sizeof(unsigned) * Q, st));
         if (tM) {
             HSSB_CUDA_OK(cudaMemsetAsync(tile_done, 0, sizeof(unsigned) * Q, st));

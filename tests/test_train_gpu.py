@@ -160,21 +160,22 @@ def test_fused_head_loss_and_clip_adam_match_the_eager_ops(lib):
         logp_a = a(x)
         loss_a = torch.nn.functional.cross_entropy(logp_a.permute(0, 2, 1), y)
         loss_a.backward()
+        raw = [p.grad.detach().clone() for p in a.parameters()]
         norm_a = torch.nn.utils.clip_grad_norm_(a.parameters(), 1.0)
         opt_b.zero_grad()
         loss_b, logp_b = b.training_loss(x, y)
         loss_b.backward()
-        assert abs(float(loss_a) - float(loss_b)) < 2e-6 * max(1.0, abs(float(loss_a)))
+        assert abs(float(loss_a.detach()) - float(loss_b.detach())) < 2e-6 * max(1.0, abs(float(loss_a.detach())))
         assert (logp_a.detach() - logp_b).abs().max() < 2e-6
-        for (name, pa), pb in zip(a.named_parameters(), b.parameters()):
-            # pa.grad was clipped in place; pb.grad is still the raw gradient
-            coef = min(1.0, 1.0 / (float(norm_a) + 1e-6))
-            assert rel_err(pb.grad * coef, pa.grad) < 2e-5, (step, name)
+        for (name, _), pb, g in zip(a.named_parameters(), b.parameters(), raw):
+            assert rel_err(pb.grad, g) < 2e-5, (step, name)                 # fused head + loss backward == the eager chain
+            pb.grad.copy_(g)     # Adam divides by sqrt(v): entries whose gradient is rounding noise would amplify it -- feed both
+            #                      optimisers the SAME gradients so that the comparison below tests the optimiser kernel alone
         opt_a.step()
         opt_b.step()
         assert abs(float(opt_b.grad_norm) - float(norm_a)) < 1e-5 * float(norm_a)
         for (name, pa), pb in zip(a.named_parameters(), b.parameters()):
-            assert rel_err(pb.detach(), pa.detach()) < 1e-5, (step, name)
+            assert float((pb.detach() - pa.detach()).abs().max()) < 2e-6 * opt_b.current_lr + 1e-7 * float(pa.detach().abs().max()), (step, name)
         if step == 1:                       # epoch boundary: lr 0.01 -> 0.009
             sched.step()
             opt_b.set_epoch(1)
