@@ -352,9 +352,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     use_shard(rank % n_shards)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step(x, state):
-        feats = fsst.batch(x)
-        logp, labels = model.forward_with_labels(feats)
+    from hss.pipeline import SegmentationPipeline
+
+    pipe = SegmentationPipeline(fsst, model, dev)
+
+    def step(x, state, x_next=None):
+        """One pass of the hot path over one batch.  x_next (the following step's input, when the loop has it): its FSST is
+        enqueued on a second stream and runs under this batch's recurrences (hss.pipeline) -- same kernels, same results."""
+        if args.pipeline:
+            logp, labels = pipe(x, prefetch=x_next)
+        else:
+            logp, labels = model.forward_with_labels(fsst.batch(x))
         metric_state(logp, y_dev, labels=labels, state=state)
         return labels
 
@@ -381,12 +389,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     gc.collect()        # (before the barrier: a gen-2 collection takes 10-50 ms and differs per rank)
     gc.disable()
     barrier()
-    for a, b in ev[:-1]:
+    for i, (a, b) in enumerate(ev[:-1]):
         flush.zero_()
         a.record()
-        step(x_dev, state)
+        step(x_dev, state, x_dev if i + 1 < args.steps else None)
         b.record()
     ev[-1][0].record()
+    pipe.close()
     allreduce_counts(state)                   # the one collective of the job: 18 scalars
     ev[-1][1].record()
     barrier()
@@ -405,12 +414,18 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     lab_slots = [torch.empty((B, N_SAMPLES), dtype=torch.int32).pin_memory() for _ in range(2)]
     st_slots = [torch.empty(18, dtype=torch.float64).pin_memory() for _ in range(2)]
     done = [torch.cuda.Event(), torch.cuda.Event()]
-    x_in = torch.empty_like(x_dev)
+    x_in = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     state_e = torch.zeros(18, dtype=torch.float64, device=dev)
 
-    def e2e_enqueue(i):
-        x_in.copy_(x_host, non_blocking=True)
-        labels = step(x_in, state_e)
+    def e2e_enqueue(i, n):
+        # the H2D copy of step i + 1 is issued before step i's kernels so that its transform can be prefetched under them
+        if i == 0:
+            x_in[0].copy_(x_host, non_blocking=True)
+        nxt = None
+        if i + 1 < n:
+            nxt = x_in[(i + 1) & 1]
+            nxt.copy_(x_host, non_blocking=True)
+        labels = step(x_in[i & 1], state_e, nxt)
         lab_slots[i & 1].copy_(labels, non_blocking=True)
         st_slots[i & 1].copy_(state_e, non_blocking=True)
         done[i & 1].record()
@@ -422,10 +437,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     def e2e_run(n):
         seen = 0.0
         for i in range(n):
-            e2e_enqueue(i)
+            e2e_enqueue(i, n)
             if i:
                 seen += e2e_collect(i - 1)
         seen += e2e_collect(n - 1)
+        pipe.close()
         allreduce_counts(state_e)
         return seen
 
@@ -543,6 +559,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "data": "synthetic",
             "config": bench_config(B),
             "timing": {"l2": "flushed between timed steps (256 MiB write)", "lstm_impl": os.environ.get("HSSB_LSTM_IMPL", "auto"),
+                       "pipeline": "the FSST of step i+1 runs on a second stream under the BiLSTM of step i (hss.pipeline)" if args.pipeline else "none",
                        "collective": "one all-reduce of the 18-scalar metric state after the last step, inside the timed region",
                        "allreduce_ms": ms_allreduce},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
@@ -570,6 +587,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0, help="windows per step of the reference arm (0 = the same as --windows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the config 2 / 3 / 5 sub-records (N = 1 only)")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="prefetch the next step's FSST on a second stream under the current step's BiLSTM (hss.pipeline); measured slower "
+                         "at 512 windows -- the transform's kernels slow the layer-1 recurrence by more than they hide -- hence off by default")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -109,11 +109,44 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
     cluster_sync();                          // every CTA's barriers are initialised before any multicast can target them
     if (p.resident && threadIdx.x == 0) atomicAdd(p.resident, 1u);      // this CTA holds its SM: the gated projection launch may start
 
+    // one-time: the W_hh slice (and, fused, the W_ih slice) -> TMEM, by the first four epilogue warps (one TMEM lane quadrant each)
+    if (warp >= S && warp < S + 4) {
+        const int q = warp & 3;
+        // this thread owns lane 32q + lane; column c holds k' = 2c, 2c+1
+        const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * RC_KP;
+#pragma unroll 1
+        for (int plane = 0; plane < 2; ++plane) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
+#pragma unroll 4
+            for (int c8 = 0; c8 < 16; ++c8) {
+                const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
+                const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
+            }
+        }
+        if (FUSE_X) {
+            // W_ih slice (rows in the same fragment order, K = 16*RX_KSTEPS features): hi plane, then lo plane
+            const __half *xrow = p.wih0 + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * 64;
+#pragma unroll 1
+            for (int plane = 0; plane < 2; ++plane) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(xrow + (size_t)plane * 128 * 64);
+#pragma unroll
+                for (int c8 = 0; c8 < RX_KSTEPS; ++c8) {
+                    const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
+                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + RX_TMEM + plane * 8 * RX_KSTEPS + c8 * 8, r);
+                }
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();                         // weights are in TMEM (a block-wide barrier: every warp passes here exactly once)
+    tc_fence_after();
+
     if (warp < S) {
         // ================= MMA issuer of sub-tile s = warp (one elected thread) =================
         const int s = warp;
-        named_barrier(9, 32 * S + 128);          // weights are in TMEM
-        tc_fence_after();
         if (sub_b0(s) < B && elect_one()) {
             const int g0 = (int)(rank >> 1);
             for (int i = 0; i < 2 * RP_G; ++i) mbar_arrive_expect_tx(&h_full[s * 2 * RP_G + i], 2 * RP_SLICE);
@@ -192,38 +225,6 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
         // fused: the relu(h) tile (fp16 hi / lo) lives in this warp's own two runs of its image piece, free once its publish completed
         unsigned char *out_tile = FUSE_X ? image(s) + q * RP_PIECE + cbase * 16 : out_tiles + (warp - S) * C::TILE_BYTES;
         constexpr int LO_OFF = FUSE_X ? RP_PIECE / 2 : C::NW * 16;      // lo plane of the tile
-
-        if (s == 0 && half == 0) {
-            // one-time: W_hh slice -> TMEM.  This thread owns lane 32q + lane; column c holds k' = 2c, 2c+1.
-            const __half *wrow = p.whh + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * RC_KP;
-#pragma unroll 1
-            for (int plane = 0; plane < 2; ++plane) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(wrow + (size_t)plane * 128 * RC_KP);
-#pragma unroll 4
-                for (int c8 = 0; c8 < 16; ++c8) {
-                    const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
-                    const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + plane * 128 + c8 * 8, r);
-                }
-            }
-            if (FUSE_X) {
-                // W_ih slice (rows in the same fragment order, K = 16*RX_KSTEPS features): hi plane, then lo plane
-                const __half *xrow = p.wih0 + ((((size_t)dir * RC_CL + rank) * 2) * 128 + q * 32 + lane) * 64;
-#pragma unroll 1
-                for (int plane = 0; plane < 2; ++plane) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(xrow + (size_t)plane * 128 * 64);
-#pragma unroll
-                    for (int c8 = 0; c8 < RX_KSTEPS; ++c8) {
-                        const uint4 v0 = __ldg(src + 2 * c8), v1 = __ldg(src + 2 * c8 + 1);
-                        const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                        tmem_st_x8(tmem_base + ((uint32_t)(q * 32) << 16) + RX_TMEM + plane * 8 * RX_KSTEPS + c8 * 8, r);
-                    }
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            named_barrier(9, 32 * S + 128);
-        }
 
         if (b0 < B) {
             constexpr int NW = C::NW;

@@ -66,15 +66,15 @@ __global__ void split_planes_kernel(const float *__restrict__ x, long long M, in
                                     __half *__restrict__ lo, const unsigned *__restrict__ range, const int *__restrict__ run_flag)
 {
     if (run_flag && *run_flag == 0) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * Kp) return;
     const float down = range ? pow2f(-range_exponent(range[1])) : 1.0f;
-    const long long m = i / Kp;
-    const int k = (int)(i % Kp);
-    __half h = __float2half_rn(0.f), l = h;
-    if (k < F) split_f16(x[m * F + k] * down, h, l);
-    hi[i] = h;
-    lo[i] = l;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M * Kp; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / Kp;
+        const int k = (int)(i % Kp);
+        __half h = __float2half_rn(0.f), l = h;
+        if (k < F) split_f16(x[m * F + k] * down, h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
 }
 
 // max |x| of the model input as float bits (word 1 of `range`; non-negative floats order like unsigned integers, NaN sorts above inf)
@@ -163,14 +163,14 @@ template <int STAGES, int EPI_WARPS, int CM, int CN>
 struct IpCfg {
     static constexpr int CL = CM * CN;
     static constexpr int OUT_BYTES = EPI_WARPS * IP_OUT_TILE;
-    static constexpr int BAR_BYTES = 512;
+    static constexpr int BAR_BYTES = 1024;
     static constexpr int SMEM_BYTES = STAGES * IP_STAGE_BYTES + OUT_BYTES + IP_BIAS_BYTES + 1024 /*align*/ + BAR_BYTES;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;
     static constexpr int CONSUMERS = 2 + EPI_WARPS;      // roles of one CTA that read an item slot
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two warps per TMEM lane quadrant");
     static_assert((2 * IP_NT_DIR) % CN == 0 && IP_BM % CN == 0 && IP_BN % CM == 0 && (IP_BN / CM) % 8 == 0, "cluster shape must split the tiles");
-    static_assert((2 * STAGES + 4 + 2 * IP_RING) * 8 + 4 + 4 * IP_RING <= BAR_BYTES, "barrier area too small");
+    static_assert((2 * STAGES + 4 + 2 * IP_RING) * 8 + 16 + 16 + 32 * IP_RING <= BAR_BYTES, "barrier area too small");
 };
 constexpr int IP_TMEM_COLS = 512;                        // 2 accumulators of 240 columns (at 0 and 256)
 
@@ -214,7 +214,9 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
     uint64_t *full = bars, *empty = bars + IP_STAGES, *tmem_full = bars + 2 * IP_STAGES, *tmem_empty = bars + 2 * IP_STAGES + 2;
     uint64_t *item_full = bars + 2 * IP_STAGES + 4, *item_empty = item_full + IP_RING;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(item_empty + IP_RING);
-    int *item_ring = reinterpret_cast<int *>(tmem_slot + 1);
+    // item ring: 16-byte slots (the granularity of a bulk copy); item_src is the scheduler's staging copy in cluster rank 0
+    int4 *item_ring = reinterpret_cast<int4 *>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
+    int4 *item_src = item_ring + IP_RING;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
     auto next_item = [&]() {                   // called by a single thread
         const int slot = ring_it % IP_RING;
         mbar_wait_cluster(&item_full[slot], (ring_it / IP_RING) & 1);
-        const int item = *reinterpret_cast<volatile int *>(&item_ring[slot]);
+        const int item = *reinterpret_cast<volatile int *>(&item_ring[slot].x);
         // relaxed: nothing but the value just read is ordered by this hand-back (a release would wait for the epilogue's
         // outstanding global stores); the comparison makes the arrive depend on the load having returned
         if (item != INT_MIN) mbar_arrive_remote_relaxed(&item_empty[slot], 0);
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
     auto next_item_warp = [&]() {              // called by a converged warp
         const int slot = ring_it % IP_RING;
         mbar_wait_cluster(&item_full[slot], (ring_it / IP_RING) & 1);
-        const int item = *reinterpret_cast<volatile int *>(&item_ring[slot]);
+        const int item = *reinterpret_cast<volatile int *>(&item_ring[slot].x);
         __syncwarp();
         if (lane == 0 && item != INT_MIN) mbar_arrive_remote_relaxed(&item_empty[slot], 0);
         ++ring_it;
@@ -438,20 +440,22 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         publish_pending();
     } else {
         // ===== item scheduler (cluster rank 0): the next item of the launch -> every CTA's ring =====
-        // One round trip per item: the CL remote stores are issued back to back, ONE cluster-scope fence orders them, then CL
-        // relaxed remote arrives publish the slot (a release-arrive per CTA would wait for its own store's acknowledgement CL times,
-        // about as long as a tile takes); the next item is fetched from the global counter while the slot is being waited for.
+        // Fully asynchronous broadcast: the item goes into a staging slot, then per CTA one remote arrive.expect_tx arms its
+        // item_full barrier and one 16-byte bulk copy (shared -> shared::cluster, complete_tx on that barrier) delivers the slot.
+        // Nothing here waits for a round trip (release-arrives behind remote stores cost one per CTA: about as long as a tile
+        // takes); the next item is fetched from the global counter right after the previous one was posted.
         if (rank == 0 && elect_one()) {
             int item = (int)atomicAdd(p.next_item, 1u);
             for (uint32_t it = 0;; ++it) {
                 const int slot = it % IP_RING;
-                mbar_wait_cluster(&item_empty[slot], ((it / IP_RING) & 1) ^ 1);
-                const uint32_t ring_addr = smem_u32(&item_ring[slot]);
+                mbar_wait_cluster(&item_empty[slot], ((it / IP_RING) & 1) ^ 1);      // every consumer of the cluster has read the slot's previous item
+                *reinterpret_cast<volatile int *>(&item_src[slot].x) = item;        // (the copies of the previous use of this staging slot completed
+                fence_proxy_async_smem();                                            //  before its consumers could read, i.e. before item_empty)
 #pragma unroll
-                for (int r = 0; r < CL; ++r) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa(ring_addr, r)), "r"(item) : "memory");
-                asm volatile("fence.acq_rel.cluster;" ::: "memory");
-#pragma unroll
-                for (int r = 0; r < CL; ++r) mbar_arrive_remote_relaxed(&item_full[slot], r);
+                for (int r = 0; r < CL; ++r) {
+                    mbar_arrive_expect_tx_remote(&item_full[slot], 16, r);
+                    bulk_copy_to_cta(&item_ring[slot], &item_src[slot], 16, &item_full[slot], r);
+                }
                 if (item >= n_items) break;
                 item = (int)atomicAdd(p.next_item, 1u);
             }
@@ -1044,7 +1048,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     {
         ProfScope prof(fused ? "range_standin" : "split_planes", st);
         input_amax_kernel<<<148 * 4, 256, 0, st>>>(x, M * m->F, range, standin);
-        split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo, range, standin);
+        split_planes_kernel<<<(unsigned)std::min<long long>((M * 64 + 255) / 256, 148 * 16), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo, range, standin);
         HSSB_LAUNCH_OK("split_planes_kernel");
     }
     {
@@ -1161,7 +1165,7 @@ extern "C" int hssb_debug_inproj(const hssb_model *m, const float *x, int64_t B,
     if (!workspace || workspace_bytes < need) return fail(HSSB_E_WORKSPACE, "hssb_debug_inproj: workspace %zu < %zu", workspace_bytes, need);
     float *raw = static_cast<float *>(workspace);
     __half *hi = reinterpret_cast<__half *>(raw + raw_floats), *lo = hi + M * 64;
-    split_planes_kernel<<<(unsigned)((M * 64 + 255) / 256), 256, 0, st>>>(x, M, m->F, 64, hi, lo, nullptr, nullptr);
+    split_planes_kernel<<<(unsigned)std::min<long long>((M * 64 + 255) / 256, 148 * 16), 256, 0, st>>>(x, M, m->F, 64, hi, lo, nullptr, nullptr);
     HSSB_LAUNCH_OK("split_planes_kernel");
     InprojJob job;
     job.next_item = reinterpret_cast<unsigned *>(hi + 2 * M * 64);

@@ -57,6 +57,16 @@ __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t *bar, uint32
         "r"(cta)
         : "memory");
 }
+// one arrival plus `bytes` of expected transaction on the barrier at the same smem offset in CTA `cta`: arms a remote barrier for a
+// bulk copy that this thread issues next (bulk_copy_to_cta)
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint64_t *bar, uint32_t bytes, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [ra], %2;\n\t}" ::"r"(smem_u32(bar)),
+        "r"(cta), "r"(bytes)
+        : "memory");
+}
 // upper bound (ns) the hardware may keep a waiting thread suspended before try_wait returns false:
 // long enough that waiting warps do not burn issue slots; completion of the phase wakes the thread
 constexpr uint32_t MBAR_SUSPEND_HINT_NS = 20000;

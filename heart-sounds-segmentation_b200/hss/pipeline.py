@@ -1,0 +1,59 @@
+"""Batch pipeline of the hot path: FSST of batch i+1 overlapped with the BiLSTM of batch i.
+
+The reference transforms and segments strictly one after the other (``hss/datasets/heart_sounds.py:199-201`` then
+``main.py:64-65``).  On the GPU the BiLSTM is two latency-bound recurrences that leave about a third of the SMs idle, while the
+FSST kernels are short and wide -- so a serving / evaluation loop that has the NEXT batch at hand runs its transform on a second
+CUDA stream underneath the current batch's model.  Per-batch results are identical to ``model(fsst.batch(x))``: the same kernels
+run on the same data, only their placement in time changes.
+
+    pipe = SegmentationPipeline(fsst, model)
+    for x in batches:                      # x[B, N] on the device (or pinned host memory)
+        logp, labels = pipe(x)             # results of THIS batch, valid on the current stream
+    pipe.close()
+
+``pipe(x, prefetch=x_next)`` transforms ``x_next`` while ``x`` is segmented; a loop that knows its next batch passes it, a
+loop that does not simply pays the un-overlapped transform (first call or missing prefetch).
+"""
+from __future__ import annotations
+
+import torch
+
+
+class SegmentationPipeline:
+    def __init__(self, fsst, model, device: torch.device | str | None = None):
+        self.fsst, self.model = fsst, model
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.side = torch.cuda.Stream(self.device)
+        self._ready: dict[int, tuple[torch.Tensor, torch.cuda.Event, torch.Tensor]] = {}     # id(x) -> (features, event, x)
+
+    def _transform_async(self, x: torch.Tensor) -> None:
+        """Enqueue ``fsst.batch(x)`` on the side stream, behind whatever produced ``x`` on the current stream."""
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            feats = self.fsst.batch(x.to(self.device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self._ready[id(x)] = (feats, ev, x)
+
+    def __call__(self, x: torch.Tensor, prefetch: torch.Tensor | None = None, labels_only: bool = False):
+        """``(logp[B, N, 4], labels[B, N])`` (or only the labels) of ``x``; ``prefetch``: the next batch, transformed meanwhile."""
+        main = torch.cuda.current_stream(self.device)
+        entry = self._ready.pop(id(x), None)
+        if entry is None:
+            feats = self.fsst.batch(x.to(self.device, non_blocking=True))
+        else:
+            feats, ev, _ = entry
+            main.wait_event(ev)
+            feats.record_stream(main)
+        # enqueue the next transform BEFORE the model: its (short) kernels then queue up behind the current ones of the side stream
+        # and run as soon as SMs are free, i.e. under this batch's recurrences
+        if prefetch is not None and id(prefetch) not in self._ready:
+            self._transform_async(prefetch)
+        if labels_only:
+            return None, self.model.predict(feats)
+        return self.model.forward_with_labels(feats)
+
+    def close(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        self._ready.clear()

@@ -4,7 +4,9 @@ OUT=gpurun_out/r2
 mkdir -p $OUT
 run() { # label env...
     local label=$1; shift
-    env "$@" timeout -s KILL 200 python bench.py --no-cpu-baseline --no-side-configs --steps 5 > $OUT/exp_$label.json 2> $OUT/exp_$label.err
+    local extra=""
+    case "$label" in *USEPIPE*) extra="--pipeline";; esac
+    env "$@" timeout -s KILL 200 python bench.py --no-cpu-baseline --no-side-configs --steps ${STEPS:-5} $extra > $OUT/exp_$label.json 2> $OUT/exp_$label.err
     python - "$label" $OUT/exp_$label.json <<'PY'
 import json, sys
 try:
