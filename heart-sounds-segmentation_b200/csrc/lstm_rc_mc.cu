@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     cluster_sync();                          // every CTA's barriers are initialised before any multicast can target them
-    if (p.resident && threadIdx.x == 0) atomicAdd(p.resident, 1u);      // this CTA holds its SM: the gated projection launch may start
+    if (p.resident && threadIdx.x == 0 && atomicAdd(p.resident, 1u) + 1 == gridDim.x)
+        atomicExch(p.resident + 1, 1u);      // every CTA of this launch holds its SM: the gated projection launch may start
 
     // one-time: the W_hh slice (and, fused, the W_ih slice) -> TMEM, by the first four epilogue warps (one TMEM lane quadrant each)
     if (warp >= S && warp < S + 4) {

@@ -183,6 +183,7 @@ struct InprojParams {
     int debug;                // HSSB_IP_DEBUG bit 0: skip the global stores (timing experiment; results are wrong when set)
     const unsigned *range;    // nullable: {flag, bits of max|x|} of a pre-scaled A operand -- the accumulator is scaled back by 2^e here
     const int *run_flag;      // nullable: the launch is a no-op while *run_flag == 0 (stand-in path of the input-range guard)
+    const int *skip_flag;     // nullable: the launch is a no-op when *skip_flag != 0
     int k_real;               // true K rounded up to 16 (48 / 512)
     int T;
     int t_tiles;              // ceil(T/128)
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
     constexpr int IP_OUT_BYTES = C::OUT_BYTES;
     constexpr int CL = C::CL;
     if (p.run_flag && *p.run_flag == 0) return;        // uniform over the grid; before any barrier / TMEM allocation
+    if (p.skip_flag && *p.skip_flag != 0) return;
     const float up = p.range ? pow2f(range_exponent(p.range[1])) : 1.0f;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -589,6 +591,7 @@ struct InprojJob {
     const unsigned *src_done = nullptr;   // [2][t_tiles] progress of the layer-1 recurrence (middle-out launch only)
     unsigned src_need = 0;
     int *timeout_flag = nullptr;
+    const int *skip_flag = nullptr;       // the launch is a no-op when *skip_flag != 0
     const char *name = nullptr;
 };
 
@@ -645,7 +648,7 @@ static int launch_inproj(const InprojParams &prm, int n_items, const char *name,
     return 0;
 }
 
-__global__ void resident_gate_kernel(const unsigned *__restrict__ resident, unsigned expected, int *__restrict__ timeout_flag);
+__global__ void resident_gate_kernel(const unsigned *__restrict__ resident);
 
 // Loads and configures every kernel that may be launched while another one is polling for it (see prepare_recurrent_mc).
 static int tc_prepare()
@@ -813,15 +816,18 @@ __global__ void pack_linw_kernel(const float *__restrict__ w, float *__restrict_
     dst[c * TC_OP + k] = slot < 30 ? w[c * 2 * TC_H + (k >> 8) * TC_H + ((k >> 5) & 7) * 30 + slot] : 0.f;
 }
 
-// Holds the side stream back until every CTA of the layer-1 recurrence is on the machine: the middle-out projection launch behind it
-// waits on that recurrence's progress flags, so its persistent CTAs must never occupy an SM the recurrence still needs.
-__global__ void resident_gate_kernel(const unsigned *__restrict__ resident, unsigned expected, int *__restrict__ timeout_flag)
+// Holds a stream back until every CTA of a recurrence launch is on the machine (resident[1] != 0): the projection launch behind it
+// either waits on that recurrence's progress flags or must leave it the SMs it needs, so its persistent CTAs must not be placed
+// first.  Gives up quietly after 20 ms: under a profiler that serialises kernels (ncu) the recurrence is queued BEHIND this
+// kernel and can never become resident -- the projection launch then simply runs before it, alone, which is correct.
+constexpr unsigned long long GATE_TIMEOUT_NS = 20000000ull;
+__global__ void resident_gate_kernel(const unsigned *__restrict__ resident)
 {
     if (threadIdx.x != 0) return;
     const unsigned long long t_start = globaltimer_ns();
-    while (ld_acquire_u32(resident) < expected) {
+    while (ld_acquire_u32(resident + 1) == 0) {
         __nanosleep(1000);
-        if (globaltimer_ns() - t_start > POLL_TIMEOUT_NS) { *timeout_flag = 1; break; }
+        if (globaltimer_ns() - t_start > GATE_TIMEOUT_NS) break;
     }
 }
 
@@ -1003,7 +1009,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     unsigned char *sync_base = reinterpret_cast<unsigned char *>(base + w.sync);
     unsigned *next_item = reinterpret_cast<unsigned *>(sync_base);                   // [8]
     int *timeout_flag = reinterpret_cast<int *>(sync_base + 32);
-    unsigned *resident = reinterpret_cast<unsigned *>(sync_base + 36);               // [2]: CTAs of the layer-1 / layer-2 recurrence on the machine
+    unsigned *resident = reinterpret_cast<unsigned *>(sync_base + 36);               // [2][2]: {CTA counter, all-resident flag} of the layer-1 / layer-2 recurrence
     unsigned *chunk_done = reinterpret_cast<unsigned *>(sync_base + SYNC_HEAD);
     unsigned *tile_done = chunk_done + SYNC_MAX_CHUNKS;
     const int t_tiles = (int)((T + TC_TT - 1) / TC_TT), Q = 2 * t_tiles;
@@ -1074,12 +1080,15 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         if (tM && l1_single && l1.multicast && l1_ctas > 0 && m->sm_count - l1_ctas >= 16) {
             // launch M: behind the gate on the side stream, concurrent with the layer-1 launches enqueued above
             HSSB_CUDA_OK(cudaStreamWaitEvent(m->side_stream, m->ev[0], 0));
-            resident_gate_kernel<<<1, 32, 0, m->side_stream>>>(resident, (unsigned)l1_ctas, timeout_flag);
+            resident_gate_kernel<<<1, 32, 0, m->side_stream>>>(resident);
             HSSB_LAUNCH_OK("resident_gate_kernel");
             InprojJob mid;
             mid.unit_mode = 1; mid.u_lo = 0; mid.n_units = tM; mid.shape = shape_small;
             mid.next_item = next_item + 3; mid.chunk_done = chunk_done;
             mid.src_done = tile_done; mid.src_need = l1_signals; mid.timeout_flag = timeout_flag;
+            // (input-range guard fired: layer 1 runs as the slower stand-in chain, which this launch must not crowd out -- it
+            //  stands down and its tiles are produced by a stand-in of launch B below)
+            mid.skip_flag = standin;
             mid.name = "tc_inproj_l1_mid";
             if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, m->side_stream, mid, nullptr, nullptr, act_pitch(T))) return rc;
             HSSB_CUDA_OK(cudaEventRecord(m->ev[3], m->side_stream));
@@ -1092,23 +1101,32 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         a.unit_mode = 0; a.u_lo = 0; a.n_units = 2 * kA; a.shape = 0; a.next_item = next_item + 1; a.chunk_done = chunk_done;
         if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, a, nullptr, nullptr, act_pitch(T))) return rc;
         HSSB_CUDA_OK(cudaEventRecord(m->ev[1], st));
-        HSSB_CUDA_OK(cudaStreamWaitEvent(m->hi_stream, m->ev[1], 0));
-        RecurSync l2;
-        l2.chunk_done = chunk_done; l2.chunk_need = chunk_need; l2.timeout_flag = timeout_flag; l2.resident = resident + 1;
-        if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, m->hi_stream, nullptr, nullptr, &l2)) return rc;
-        HSSB_CUDA_OK(cudaEventRecord(m->ev[2], m->hi_stream));
-        // launch B: chunks k in [kA, m_lo) and (m_hi, t_tiles - kA) of both directions, i.e. q in [2 kA, 2 m_lo) and [2 m_hi + 2, Q - 2 kA),
-        // held back until the recurrence's clusters are on the machine (they are placed first, B takes what is left)
+        // launch B: chunks k in [kA, m_lo) and (m_hi, t_tiles - kA) of both directions, i.e. q in [2 kA, 2 m_lo) and [2 m_hi + 2, Q - 2 kA).
+        // It is ENQUEUED before the recurrence (a profiler that serialises kernels then runs it first and the recurrence finds every
+        // flag set) but held back by the gate until the recurrence's clusters are on the machine: they are placed first, B takes
+        // the SMs that are left.
         InprojJob b;
         b.unit_mode = 2; b.shape = shape_small; b.next_item = next_item + 2; b.chunk_done = chunk_done;
         b.q_lo1 = 2 * kA; b.len1 = tM ? 2 * (m_lo - kA) : Q - 4 * kA;
         b.q_lo2 = 2 * m_hi + 2; b.n_units = tM ? b.len1 + (Q - 2 * kA) - (2 * m_hi + 2) : b.len1;
         b.name = "tc_inproj_l1_tail";
         if (b.n_units > 0) {
-            resident_gate_kernel<<<1, 32, 0, st>>>(resident + 1, (unsigned)l2.ctas_first, timeout_flag);
+            resident_gate_kernel<<<1, 32, 0, st>>>(resident + 2);
             HSSB_LAUNCH_OK("resident_gate_kernel");
             if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, b, nullptr, nullptr, act_pitch(T))) return rc;
         }
+        if (mid_running && standin) {
+            InprojJob bm;                  // the middle tiles, when launch M stood down (no-op otherwise)
+            bm.unit_mode = 2; bm.shape = shape_small; bm.next_item = next_item + 4; bm.chunk_done = chunk_done;
+            bm.q_lo1 = 2 * m_lo; bm.len1 = 2 * tM; bm.n_units = bm.len1;
+            bm.name = "range_standin";
+            if (int rc = tc_inproj(m, 1, o1hi, o1lo, TC_OP, B, T, xproj, st, bm, nullptr, standin, act_pitch(T))) return rc;
+        }
+        HSSB_CUDA_OK(cudaStreamWaitEvent(m->hi_stream, m->ev[1], 0));
+        RecurSync l2;
+        l2.chunk_done = chunk_done; l2.chunk_need = chunk_need; l2.timeout_flag = timeout_flag; l2.resident = resident + 2;
+        if (int rc = tc_recurrent(m, 1, xproj, hn, cn, hn, cn, nullptr, nullptr, out2, gather, B, T, m->hi_stream, nullptr, nullptr, &l2)) return rc;
+        HSSB_CUDA_OK(cudaEventRecord(m->ev[2], m->hi_stream));
         HSSB_CUDA_OK(cudaStreamWaitEvent(st, m->ev[2], 0));
         if (mid_running) HSSB_CUDA_OK(cudaStreamWaitEvent(st, m->ev[3], 0));
     }

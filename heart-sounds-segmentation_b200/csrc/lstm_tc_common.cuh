@@ -106,7 +106,7 @@ struct RecurParams {
     // producer / consumer flags of the overlapped layer-2 projection (tc_forward).  chunk_done (nullable): the xproj of time tile tt
     // and this direction may be read once chunk_done[q] reached chunk_need (q = 2 tt forward, 2 (t_tiles - 1 - tt) + 1 reverse);
     // tile_done (nullable): bumped per epilogue warp when its relu(h) stores of a time tile are complete, [dir][t_tiles];
-    // resident (nullable): bumped once per CTA when the launch is on the machine; timeout_flag: raised instead of hanging
+    // resident (nullable): [0] bumped once per CTA, [1] set when all CTAs of a launch are on the machine; timeout_flag: raised instead of hanging
     const unsigned *chunk_done;
     unsigned chunk_need;
     unsigned *tile_done;

@@ -220,6 +220,24 @@ def test_input_range_of_the_fp16_split(lib, scale):
         check(logp, labels, ref)
 
 
+def test_range_guard_with_the_overlapped_projection(lib):
+    """T >= 1024 runs the layer-2 projection as launches M / A / B around the recurrences; with the input-range guard firing the
+    middle launch stands down (layer 1 is then the stand-in chain) and its tiles come from a stand-in of launch B."""
+    B, T = 24, 1100
+    m = make_model(31, 44, B, 240)
+    x = torch.randn(B, T, 44, generator=torch.Generator().manual_seed(8))
+    x[3, 500, 7] = 2.0e5                                   # one sample outside the fp16-split range
+    params, h0, c0 = lo.reference_params(31, 44, B, 240)
+    logp, labels = m.forward_with_labels(x.cuda())
+    assert torch.isfinite(logp).all()
+    ref = lo.forward_torch(params, h0, c0, x)
+    rep = lo.label_report(logp.cpu(), ref)
+    assert rep["max_abs_dlogp"] < 2e-4 and rep["flips"] <= 2, rep       # (|W x| ~ 1e4 at the spike: fp32 noise of the reference itself)
+    x[3, 500, 7] = 0.5
+    logp2, labels2 = m.forward_with_labels(x.cuda())                     # same module, guard not firing
+    check(logp2.cpu(), labels2.cpu(), lo.forward_torch(params, h0, c0, x))
+
+
 def test_weights_outside_the_split_range_use_the_fp32_kernels(lib):
     m = make_model(4, 44, 3, 240)
     with torch.no_grad():
