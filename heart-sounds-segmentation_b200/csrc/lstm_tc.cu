@@ -674,7 +674,7 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     static const int SHAPES[4][2] = {{IP_BIG_CM, IP_BIG_CN}, {2, 2}, {2, 1}, {1, 1}};
     if (job.shape < 0 || job.shape > 3 || !job.next_item) return fail(HSSB_E_MODE, "tc_inproj: bad job");
     const int CM = SHAPES[job.shape][0], CN = SHAPES[job.shape][1];
-    InprojParams prm;
+    InprojParams prm = {};
     prm.range = range;
     prm.run_flag = run_flag;
     const int Kp = kp_of_layer(layer, m->F);
@@ -715,6 +715,7 @@ int tc_inproj(const hssb_model *m, int layer, const __half *a_hi, const __half *
     prm.src_done = job.src_done;
     prm.src_need = job.src_need;
     prm.timeout_flag = job.timeout_flag;
+    prm.skip_flag = job.skip_flag;
     const int nt_unit = (job.unit_mode == 2 ? IP_NT_DIR : 2 * IP_NT_DIR);
     if (job.unit_mode < 0 || job.unit_mode > 2 || nt_unit % CN != 0) return fail(HSSB_E_MODE, "tc_inproj: cluster shape %dx%d does not fit unit mode %d", CM, CN, job.unit_mode);
     if (job.unit_mode == 2) {
