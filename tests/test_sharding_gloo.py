@@ -85,3 +85,36 @@ def test_two_rank_auroc_histogram_allreduce(tmp_path):
     assert torch.equal(got["hist"], whole)
     assert torch.equal(got["auroc"]["auroc_per_class"], auroc_from_histograms(whole)["auroc_per_class"])
     assert abs(got["auroc"]["auroc"] - float(mo.auroc_binned(logp.numpy(), target.numpy(), 256).mean())) < 1e-12
+
+
+def _state_worker(rank, world, port, logp, target, out_path):
+    sys.path.insert(0, os.path.join(ROOT, "heart-sounds-segmentation_b200"))
+    from hss.sharding import allreduce_counts, metrics_from_state, shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(logp.shape[0], rank, world)
+    # (on a GPU rank this state comes from hss.sharding.metric_state = kernel hssb_metrics_update, accumulated over the steps)
+    lp, t = logp[lo:hi].reshape(-1, 4).double(), target[lo:hi].reshape(-1)
+    state = torch.zeros(18, dtype=torch.float64)
+    state[:16] = _cpu_counts(lp.argmax(-1), t).reshape(-1).double()
+    state[16] = (torch.logsumexp(lp, dim=1) - lp[torch.arange(lp.shape[0]), t]).sum()
+    state[17] = lp.shape[0]
+    state = allreduce_counts(state)                      # the ONE collective of the job
+    if rank == 0:
+        torch.save({"state": state, "metrics": metrics_from_state(state)}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_metric_state_allreduce(tmp_path):
+    """The 18-scalar metric state (confusion counts + loss sum + count, reference main.py:36-62,69-70) of two ranks adds up to
+    the single-process state: same confusion matrix, same mean cross-entropy as nn.CrossEntropyLoss on the whole batch."""
+    g = torch.Generator().manual_seed(4)
+    logp = torch.log_softmax(torch.randn(9, 40, 4, generator=g), dim=2)
+    target = torch.randint(0, 4, (9, 40), generator=g)
+    out = str(tmp_path / "state.pt")
+    mp.spawn(_state_worker, args=(2, _free_port(), logp, target, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    assert torch.equal(got["state"][:16].round().long().reshape(4, 4), _cpu_counts(logp.argmax(-1), target))
+    ref_loss = torch.nn.CrossEntropyLoss()(logp.permute(0, 2, 1).double(), target)
+    assert abs(got["metrics"]["loss"] - float(ref_loss)) < 1e-12 and got["metrics"]["count"] == 9 * 40
