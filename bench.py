@@ -513,6 +513,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         # ncu evidence committed under profiles/: DRAM bytes per launch and tensor-pipe activity of every kernel of this workload;
         # only attached when the workload is the profiled one
         traffic, traffic_src = load_traffic() if (B == WINDOWS_PER_GPU) else ({}, None)
+        if "tc_recurrent_l1" in traffic and "tc_recurrent_l2" in traffic and "tc_recurrent" not in traffic:
+            a, b = traffic["tc_recurrent_l1"], traffic["tc_recurrent_l2"]
+            ta, tb = a["ncu_ms_per_launch"], b["ncu_ms_per_launch"]
+            traffic["tc_recurrent"] = {"dram_bytes_per_launch": a["dram_bytes_per_launch"] + b["dram_bytes_per_launch"],
+                                       "tensor_pipe_active_pct": (a["tensor_pipe_active_pct"] * ta + b["tensor_pipe_active_pct"] * tb) / (ta + tb)}
         for name, entry in per_kernel.items():
             tr = traffic.get(name)
             if tr:

@@ -10,6 +10,7 @@
 #include "fsst_phases.cuh"
 #include <mutex>
 #include <cstdlib>
+#include <algorithm>
 
 namespace hssb {
 
@@ -169,6 +170,135 @@ if_reassign_kernel(const float2 *__restrict__ Sg, const float2 *__restrict__ Sdg
 }
 
 // ------------------------------------------------------------------------------------------------
+// Generic window lengths (4 <= nwin <= 1024, even or odd; nfft = nwin).  ssq.fsst takes any window (reference
+// hss/transforms/synchrosqueeze.py:48); 128 and 256 run on the radix kernels above, every other length on these two: a direct
+// DFT of every frame (double accumulators: the sums run over up to 1024 terms) and a reassignment kernel with modulo-nfft rows
+// and the general phase shift exp(-2 pi i floor(nwin/2) k / nfft) (exactly (-1)^k only for even nwin).  Same Sg / Sdg / T /
+// partial-moment layouts as K1 / K2, so K3 and the wrappers do not care which pair ran.  Correct, not tuned.
+// ------------------------------------------------------------------------------------------------
+constexpr int GT = 32;          // time columns per CTA of the generic STFT
+
+__global__ void __launch_bounds__(256)
+stft_dft_kernel(const float *__restrict__ x, long long N, const float *__restrict__ g, const float *__restrict__ dg, int nwin,
+                float2 *__restrict__ Sg, float2 *__restrict__ Sdg)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);       // [nwin]  exp(-2 pi i j / nwin)
+    float *gs = reinterpret_cast<float *>(tw + nwin);        // [nwin]
+    float *dgs = gs + nwin;                                   // [nwin]
+    float *xs = dgs + nwin;                                   // [GT + nwin]
+    const int tid = threadIdx.x;
+    const long long b = blockIdx.y, t0 = (long long)blockIdx.x * GT;
+    const int K = nwin / 2 + 1, left = nwin / 2;             // zero padding: nwin/2 (even) or (nwin-1)/2 (odd) samples on the left
+    for (int i = tid; i < nwin; i += 256) {
+        gs[i] = g[i];
+        dgs[i] = dg[i];
+        float sn, cs;
+        sincospif(-2.0f * (float)i / (float)nwin, &sn, &cs);
+        tw[i] = make_float2(cs, sn);
+    }
+    const float *xb = x + b * N;
+    for (int i = tid; i < GT + nwin; i += 256) {
+        const long long src = t0 - left + i;
+        xs[i] = (src >= 0 && src < N) ? __ldg(xb + src) : 0.0f;
+    }
+    __syncthreads();
+    const long long ncols = (N - t0 < GT) ? (N - t0) : GT;
+    for (int idx = tid; idx < K * GT; idx += 256) {
+        const int k = idx / GT, c = idx % GT;                // a warp shares k: the twiddle and window reads are broadcasts
+        if (c >= ncols) continue;
+        double gr = 0.0, gi = 0.0, dr = 0.0, di = 0.0;
+        int ph = 0;
+        for (int n = 0; n < nwin; ++n) {
+            const float v = xs[c + n];
+            const float2 w = tw[ph];
+            const float a = v * gs[n], d = v * dgs[n];
+            gr += (double)(a * w.x); gi += (double)(a * w.y);
+            dr += (double)(d * w.x); di += (double)(d * w.y);
+            ph += k;
+            if (ph >= nwin) ph -= nwin;
+        }
+        const size_t o = ((size_t)b * K + k) * N + t0 + c;
+        Sg[o] = make_float2((float)gr, (float)gi);
+        Sdg[o] = make_float2((float)dr, (float)di);
+    }
+}
+
+__device__ __forceinline__ int wrap_row_generic(float r, int nfft)
+{
+    if (!(fabsf(r) < 2147483648.0f)) return 0;               // garbage IF of an empty bin: any row, but no trap
+    int m = ((int)r) % nfft;
+    return m < 0 ? m + nfft : m;
+}
+
+// One warp per CTA, 128 columns as four passes of 32 (the per-column accumulators of a pass: [Kout][32] in shared memory), one
+// moment partial per 128-column tile like K2.
+__global__ void __launch_bounds__(32)
+if_reassign_generic_kernel(const float2 *__restrict__ Sg, const float2 *__restrict__ Sdg, long long N, int nfft, float bins_per_hz,
+                           int k_lo, int k_hi, float2 *__restrict__ T, double *__restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *acc = reinterpret_cast<float2 *>(smem_raw);      // [Kout][32]
+    const int lane = threadIdx.x;
+    const long long b = blockIdx.y;
+    const int K = nfft / 2 + 1, Kout = k_hi - k_lo + 1, half = nfft / 2;
+    Moments tile_m[2] = {Moments{0.0, 0.0, 0.0}, Moments{0.0, 0.0, 0.0}};
+    for (int pass = 0; pass < RT / 32; ++pass) {
+        const long long t = (long long)blockIdx.x * RT + pass * 32 + lane;
+        const bool active = t < N;
+        for (int r = 0; r < Kout; ++r) acc[r * 32 + lane] = make_float2(0.f, 0.f);
+        Moments m[2] = {Moments{0.0, 0.0, 0.0}, Moments{0.0, 0.0, 0.0}};
+        if (active) {
+            const float2 *sg = Sg + (size_t)b * K * N + t;
+            const float2 *sdg = Sdg + (size_t)b * K * N + t;
+            for (int k = 0; k < K; ++k) {
+                const float2 a = __ldcs(sg + (size_t)k * N), d = __ldcs(sdg + (size_t)k * N);
+                const float den = a.x * a.x + a.y * a.y;
+                const float num = d.x * a.y - d.y * a.x;     // -imag(Sdg * conj(Sg))
+                float fc = __fdividef(num, den);
+                if (!(fabsf(fc) <= 3.0e38f)) fc = 0.0f;
+                const float off = fc * bins_per_hz;
+                float sn, cs;                                 // exp(-2 pi i floor(nwin/2) k / nfft), argument reduced in integers
+                sincospif(-2.0f * (float)((int)(((long long)half * k) % nfft)) / (float)nfft, &sn, &cs);
+                if ((nfft & 1) == 0) { cs = (k & 1) ? -1.0f : 1.0f; sn = 0.0f; }
+                const float vx = a.x * cs - a.y * sn, vy = a.x * sn + a.y * cs;
+                const int row = wrap_row_generic(round_half_away((float)k + off), nfft);
+                if (row >= k_lo && row <= k_hi) { float2 *p = acc + (row - k_lo) * 32 + lane; p->x += vx; p->y += vy; }
+                if (k > 0 && 2 * k != nfft) {                 // the negative-frequency mirror of the bin: value conj, correction negated
+                    const int rowm = wrap_row_generic(round_half_away((float)(nfft - k) - off), nfft);
+                    if (rowm >= k_lo && rowm <= k_hi) { float2 *p = acc + (rowm - k_lo) * 32 + lane; p->x += vx; p->y -= vy; }
+                }
+            }
+            float2 *tout = T + (size_t)b * Kout * N + t;
+            double sx = 0.0, sy = 0.0;
+            for (int r = 0; r < Kout; ++r) { const float2 v = acc[r * 32 + lane]; __stcs(tout + (size_t)r * N, v); sx += v.x; sy += v.y; }
+            const double mx = sx / Kout, my = sy / Kout;
+            double qx = 0.0, qy = 0.0;
+            for (int r = 0; r < Kout; ++r) { const float2 v = acc[r * 32 + lane]; qx += (v.x - mx) * (v.x - mx); qy += (v.y - my) * (v.y - my); }
+            m[0] = Moments{(double)Kout, mx, qx};
+            m[1] = Moments{(double)Kout, my, qy};
+        }
+        if (partials) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int s2 = 1; s2 < 32; s2 <<= 1) {
+                    const Moments o = shfl_xor_moments(m[c], s2);
+                    m[c] = ((lane & s2) == 0) ? merge_moments(m[c], o) : merge_moments(o, m[c]);
+                }
+                tile_m[c] = merge_moments(tile_m[c], m[c]);
+            }
+        }
+        __syncwarp();
+    }
+    if (partials && lane < 2) {
+        double *p = partials + (((size_t)b * gridDim.x + blockIdx.x) * 2 + lane) * 3;
+        const Moments r = lane ? tile_m[1] : tile_m[0];
+        p[0] = r.n; p[1] = r.mean; p[2] = r.m2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3
 // ------------------------------------------------------------------------------------------------
 // one CTA per window, warp c merges the tiles' partials of channel c -> final[b] = {mean_re, std_re, mean_im, std_im}
@@ -268,9 +398,10 @@ using namespace hssb;
 // ------------------------------------------------------------------------------------------------
 static int check_nwin(int nwin)
 {
-    if (nwin != 128 && nwin != 256) return fail(HSSB_E_NWIN, "nwin=%d unsupported (128 or 256)", nwin);
+    if (nwin < 4 || nwin > 1024) return fail(HSSB_E_NWIN, "nwin=%d unsupported (4 .. 1024)", nwin);
     return 0;
 }
+static bool radix_nwin(int nwin) { return nwin == 128 || nwin == 256; }
 
 static int ntiles_reassign(int64_t N) { return (int)((N + RT - 1) / RT); }
 
@@ -289,6 +420,10 @@ extern "C" int hssb_fsst_stft(const float *x, int64_t B, int64_t N, const float 
         HSSB_CUDA_OK(cudaFuncSetAttribute(stft_hop1_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));   // per device: set on every call
         dim3 grid((unsigned)((N + C::TT - 1) / C::TT), (unsigned)B);
         stft_hop1_kernel<8><<<grid, C::NT, C::SMEM_BYTES, st>>>(x, N, g, dg, (float2 *)Sg, (float2 *)Sdg);
+    } else if (nwin != 256) {
+        const size_t smem = sizeof(float2) * nwin + sizeof(float) * (2 * nwin + GT + nwin);
+        dim3 grid((unsigned)((N + GT - 1) / GT), (unsigned)B);
+        stft_dft_kernel<<<grid, 256, smem, st>>>(x, N, g, dg, nwin, (float2 *)Sg, (float2 *)Sdg);
     } else {
         using C = StftCfg<16>;
         HSSB_CUDA_OK(cudaFuncSetAttribute(stft_hop1_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
@@ -316,6 +451,16 @@ extern "C" int hssb_fsst_reassign(const hssb_c32 *Sg, const hssb_c32 *Sdg, int64
     if (B == 0 || N == 0) return 0;
     if (int rc = require_sm100()) return rc;
     const int Kout = k_hi - k_lo + 1;
+    if (!radix_nwin(nwin)) {
+        const size_t gsmem = sizeof(float2) * (size_t)Kout * 32;
+        HSSB_CUDA_OK(cudaFuncSetAttribute(if_reassign_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float2) * 513 * 32)));
+        dim3 ggrid((unsigned)ntiles_reassign(N), (unsigned)B);
+        ProfScope prof("if_reassign", as_stream(stream));
+        if_reassign_generic_kernel<<<ggrid, 32, gsmem, as_stream(stream)>>>((const float2 *)Sg, (const float2 *)Sdg, N, nwin,
+                                                                             (float)((double)nwin / (double)fs), k_lo, k_hi, (float2 *)T, stats);
+        HSSB_LAUNCH_OK("if_reassign_generic_kernel");
+        return 0;
+    }
     const size_t smem = sizeof(float2) * (size_t)Kout * RT;
     static PerDeviceInt attr_set;                 // the opt-in shared-memory size is a per-device attribute
     if (!attr_set.get()) {
@@ -346,7 +491,7 @@ extern "C" int hssb_fsst_finish(const hssb_c32 *T, const double *stats, int64_t 
     if (!T || !out) return fail(HSSB_E_NULL, "hssb_fsst_finish: null pointer");
     if (mode != HSSB_MODE_ABS && mode != HSSB_MODE_STACK) return fail(HSSB_E_MODE, "hssb_fsst_finish: mode %d", mode);
     if (mode == HSSB_MODE_STACK && !stats) return fail(HSSB_E_NULL, "hssb_fsst_finish: STACK needs stats");
-    if (B < 0 || N < 0 || Kt < 1 || Kt > 129 || B > 65535) return fail(HSSB_E_SHAPE, "hssb_fsst_finish: bad shape");
+    if (B < 0 || N < 0 || Kt < 1 || Kt > 513 || B > 65535) return fail(HSSB_E_SHAPE, "hssb_fsst_finish: bad shape");
     if (B == 0 || N == 0) return 0;
     if (int rc = require_sm100()) return rc;
     cudaStream_t st = as_stream(stream);
@@ -360,7 +505,8 @@ extern "C" int hssb_fsst_finish(const hssb_c32 *T, const double *stats, int64_t 
     }
     const int W = (mode == HSSB_MODE_STACK) ? 2 * Kt : Kt;
     const size_t smem = sizeof(float) * FT * (size_t)(W | 1);
-    HSSB_CUDA_OK(cudaFuncSetAttribute(normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * FT * 259)));
+    if (smem > 227 * 1024) return fail(HSSB_E_BAND, "hssb_fsst_finish: %d rows do not fit the normalise tile (<= 220 in stack mode, <= 440 otherwise)", Kt);
+    HSSB_CUDA_OK(cudaFuncSetAttribute(normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, sizeof(float) * FT * 259)));
     dim3 grid((unsigned)((N + FT - 1) / FT), (unsigned)B);
     ProfScope prof("normalise", st);
     normalise_kernel<<<grid, 256, smem, st>>>((const float2 *)T, final_stats, N, Kt, mode, out);
@@ -456,7 +602,7 @@ extern "C" int hssb_fsst_host(const float *x, int64_t B, int64_t N, double fs, c
     float *dwin = reinterpret_cast<float *>(base + x_bytes);
     void *dout = base + x_bytes + win_bytes;
     void *dws = base + x_bytes + win_bytes + align_up(out_bytes, 256);
-    float hwin[512];
+    float hwin[2048];
     for (int i = 0; i < nwin; ++i) { hwin[i] = (float)window[i]; hwin[nwin + i] = (float)dwindow[i]; }
     cudaStream_t st = nullptr;   // legacy default stream: ordered with the synchronous copies below
     HSSB_CUDA_OK(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)B * N, cudaMemcpyHostToDevice, st));

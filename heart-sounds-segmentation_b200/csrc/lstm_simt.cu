@@ -156,7 +156,12 @@ head_kernel(const float *__restrict__ act, long long M, int H2, const float *__r
             long long T, long long Tp)
 {
     // T != Tp: the activations are [B][Tp][H2] with Tp >= T time rows per window (act_pitch), the outputs dense [B][T]
-    auto src_row = [&](long long r) { return (T == Tp) ? r : (r / T) * Tp + r % T; };
+    const bool small = M < 0x7fffffffLL;       // 32-bit division (a 64-bit one costs more than the row's dot products)
+    auto src_row = [&](long long r) -> long long {
+        if (T == Tp) return r;
+        if (small) { const unsigned b = (unsigned)r / (unsigned)T; return (long long)b * Tp + ((unsigned)r - b * (unsigned)T); }
+        return (r / T) * Tp + r % T;
+    };
     extern __shared__ float w_s[];   // [4][H2]
     // `poison` (nullable): a producer / consumer wait upstream gave up (see POLL_TIMEOUT_NS) -- the activations are not the
     // forward's result, so the outputs are NaN / -1 rather than plausible numbers

@@ -44,8 +44,8 @@ class FSST:
 
         w = np.asarray(window, dtype=np.float64).reshape(-1)
         self._nwin = int(w.size)
-        if self._nwin not in (128, 256):
-            raise ValueError(f"FSST (B200 build) supports window lengths 128 and 256, got {self._nwin}")
+        if not 4 <= self._nwin <= 1024:
+            raise ValueError(f"FSST (B200 build) supports window lengths 4 .. 1024, got {self._nwin}")
         dw = derivative_window(w, fs)
         self._host_windows = torch.from_numpy(np.concatenate([w, dw]).astype(np.float32))
         self._dev_windows: dict[int, torch.Tensor] = {}

@@ -39,7 +39,7 @@ enum {
     HSSB_OK = 0,
     HSSB_E_NULL = -1,      /* required pointer is NULL */
     HSSB_E_SHAPE = -2,     /* negative / inconsistent sizes */
-    HSSB_E_NWIN = -3,      /* unsupported window length (supported: 128, 256) */
+    HSSB_E_NWIN = -3,      /* unsupported window length (supported: 4 .. 1024; 128 and 256 run on the radix kernels) */
     HSSB_E_BAND = -4,      /* k_lo / k_hi outside [0, nwin/2] or k_hi < k_lo */
     HSSB_E_MODE = -5,      /* unknown output mode */
     HSSB_E_WORKSPACE = -6, /* workspace too small / misaligned */

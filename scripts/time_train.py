@@ -15,11 +15,22 @@ x = torch.randn(B, T, F, device="cuda")
 y = torch.randint(0, 4, (B, T), device="cuda")
 
 
+from hss.optim import ClipAdam
+
+fused = "--eager" not in sys.argv          # fused head + loss and clip + Adam kernels (default) or the reference's eager torch ops
+if fused:
+    opt = ClipAdam(m.parameters(), lr=0.01, max_norm=1.0)
+
+
 def step():
     opt.zero_grad(set_to_none=True)
-    loss = torch.nn.functional.cross_entropy(m(x).permute(0, 2, 1), y)
-    loss.backward()
-    torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    if fused:
+        loss, _ = m.training_loss(x, y)
+        loss.backward()
+    else:
+        loss = torch.nn.functional.cross_entropy(m(x).permute(0, 2, 1), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
     opt.step()
     return loss
 
@@ -36,6 +47,6 @@ for _ in range(n):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
 prof = _lib.prof_read()
-print(f"training step B={B} T={T}: {dt * 1e3:.1f} ms  ({B * T / dt / 1e6:.2f} M samples/s), loss {float(loss.detach()):.4f}")
+print(f"training step ({'fused head/loss + clip/Adam kernels' if fused else 'eager torch head / loss / clip / Adam'}) B={B} T={T}: {dt * 1e3:.1f} ms  ({B * T / dt / 1e6:.2f} M samples/s), loss {float(loss.detach()):.4f}")
 for k, (c, ms) in sorted(prof.items()):
     print(f"  {k}: {c // n} launches/step, {ms / n:.2f} ms/step")

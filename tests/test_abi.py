@@ -48,7 +48,7 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert b"null" in lib.hssb_last_error()
     buf = (ctypes.c_float * 8)()
     p = ctypes.addressof(buf)
-    assert lib.hssb_fsst_stft(p, 1, 8, p, p, 100, p, p, None) == -3                          # HSSB_E_NWIN
+    assert lib.hssb_fsst_stft(p, 1, 8, p, p, 3, p, p, None) == -3                            # HSSB_E_NWIN (4 .. 1024)
     assert lib.hssb_fsst_stft(p, -1, 8, p, p, 128, p, p, None) == -2                         # HSSB_E_SHAPE
     assert lib.hssb_fsst_reassign(p, p, 1, 8, 128, 1000.0, 30, 20, p, None, None) == -4      # HSSB_E_BAND
     assert lib.hssb_fsst_finish(p, None, 1, 8, 22, 7, p, None) == -5                         # HSSB_E_MODE

@@ -342,3 +342,27 @@ def test_stream_recordings_pipeline_equals_per_recording_path(lib, tmp_path):
     assert len(streamed) == len(expected) == 6                    # only the 1500-sample recording is shorter than one frame
     for (a, la), (b, lb) in zip(streamed, expected):
         assert a.shape == b.shape and torch.equal(a, b) and torch.equal(la, lb)
+
+
+@pytest.mark.parametrize("nwin,beta", [(64, 4.0), (100, 6.0), (101, 6.0), (255, 10.0), (512, 10.0)])
+def test_generic_window_lengths(lib, nwin, beta):
+    """ssq.fsst takes any window (reference synchrosqueeze.py:48): lengths other than 128 / 256 -- even and odd -- run on the
+    direct-DFT STFT kernel and the modulo-nfft reassignment kernel; same checks against the float64 oracle as the radix kernels."""
+    from hss.transforms import FSST
+
+    fs, N, B = 1000.0, 1500, 3
+    w = np.kaiser(nwin, beta)
+    x = fo.synth_pcg_batch(B, N, seed=nwin)
+    raw = FSST(fs, window=w).batch(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert raw.shape == (B, nwin // 2 + 1, N)
+    for b in range(B):
+        s, _, _ = fo.fsst(x[b], fs, w)
+        rows_and_values_ok(raw[b], s, frac=1e-4, tol=4e-6)
+    band = (40, 180)
+    feats = FSST(fs, window=w, truncate_freq=band, stack=True).batch(torch.from_numpy(x).cuda()).cpu().numpy()
+    mags = FSST(fs, window=w, truncate_freq=band, abs=True)(torch.from_numpy(x[0]))
+    for b in range(B):
+        ref = fo.fsst_features(x[b], fs, w, stack=True, truncate_freq=band)
+        assert feats[b].shape == ref.shape and np.abs(feats[b] - ref).max() < 5e-4
+    ref_m = fo.fsst_features(x[0], fs, w, abs=True, truncate_freq=band)
+    assert mags.shape == ref_m.shape and (np.abs(mags.numpy() - ref_m) > 1e-5 * ref_m.max()).mean() < 1e-4

@@ -35,8 +35,9 @@ def test_fsst_signature_matches_reference():
     f = FSST(1000, window=fo.reference_window(), truncate_freq=(25, 200), stack=True)
     assert f.num_rows == 22 and f.fs == 1000 and f.stack and not f.abs
     assert torch.allclose(f.frequencies(), torch.arange(4, 26) * 7.8125)
+    assert FSST(1000, window=np.kaiser(101, 5.0)).num_rows == 51           # any window length 4 .. 1024 (ssq.fsst takes any window)
     with pytest.raises(ValueError):
-        FSST(1000, window=np.ones(100))
+        FSST(1000, window=np.ones(2000))
 
 
 def test_segmenter_signature_state_dict_and_rng_order():
