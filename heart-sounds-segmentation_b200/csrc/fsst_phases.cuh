@@ -126,10 +126,16 @@ HSSB_HD void reassign_one(int k, float2 a, float2 d, int nfft, float bins_per_hz
         p->x += vx; p->y += vy;
     }
     if (k > 0 && k < nfft / 2) {
-        const int rowm = wrap_row(round_half_away((float)(nfft - k) - off), nfft);
-        if (rowm >= k_lo && rowm <= k_hi) {
-            float2 *p = acc + (rowm - k_lo) * astride;
-            p->x += vx; p->y -= vy;
+        // The mirror bin nfft - k lands on a kept row only after a correction of dozens of bins: between k_hi + 1 and
+        // nfft + k_lo - 1 the (unwrapped) destination rounds to a row outside [k_lo, k_hi] whatever the wrap does, so the rounding,
+        // wrapping and range test are skipped there -- the usual case (the test is conservative by a whole row: exact).
+        const float vm = (float)(nfft - k) - off;
+        if (!(vm > (float)(k_hi + 1) && vm < (float)(nfft + k_lo - 1))) {
+            const int rowm = wrap_row(round_half_away(vm), nfft);
+            if (rowm >= k_lo && rowm <= k_hi) {
+                float2 *p = acc + (rowm - k_lo) * astride;
+                p->x += vx; p->y -= vy;
+            }
         }
     }
 }

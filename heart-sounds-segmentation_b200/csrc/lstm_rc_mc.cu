@@ -87,10 +87,21 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
     const long long T = p.T, B = p.B;
     auto sub_b0 = [&](int s) { return (long long)p.b_base + ((long long)group * S + s) * RP_NBH; };
     unsigned long long *const tr_buf = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+    // clock64 stamps of the roles (scripts/trace_recurrent.py) and the knock-out switches exist only in diagnostic builds
+    // (-DHSSB_TRACE / -DHSSB_KNOCKOUTS): every instruction of the epilogue warps is on the dependent chain of a step
+#ifdef HSSB_TRACE
 #define RM_TRACE(ev, step, sub)                                                                                       \
     do {                                                                                                              \
         if (tr_buf && (step) >= 0 && (step) < p.trace_steps) tr_buf[(((step) * 4 + (sub)) * TR_EVENTS) + (ev)] = clock64(); \
     } while (0)
+#else
+#define RM_TRACE(ev, step, sub) do { (void)tr_buf; } while (0)
+#endif
+#ifdef HSSB_KNOCKOUTS
+    const int knock = p.debug;
+#else
+    constexpr int knock = 0;
+#endif
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * S * RP_G + 4 * S; ++i) mbar_init(&bars[i], 1);
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                 for (int i = 0; i < NI; ++i) {
                     const int c = col_of(i);
                     if (FUSE_X) continue;               // fused: xnext holds the (constant) biases of this unit's four gates
-                    xnext[i] = (c < ncols && !(p.debug & 1)) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xnext[i] = (c < ncols && !(knock & 1)) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 xp_next += xstep;
             };
@@ -377,7 +388,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                         eo[i] = ex2_approx((__uint_as_float(b[r + 2]) + xnext[i].w) * -LOG2E);
                     }
                     if (tracer) RM_TRACE(TR_EPI_ACT, t, s);
-                    if (p.debug & 4) {                                  // (timing experiment: no cell math)
+                    if (knock & 4) {                                  // (timing experiment: no cell math)
 #pragma unroll
                         for (int i = 0; i < NI; ++i) hv[i] = unit_ok ? 0.25f * (ei[i] + ef[i]) * 1e-3f + 1e-3f * (eg[i] + eo[i]) : 0.0f;
                     } else
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (!(p.debug & 2) && elect_one()) {
+                if (!(knock & 2) && elect_one()) {
                     const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;       // box of 32 / 16 batch columns
                     tma_store_3d(&om[0], out_tile, out_c0, t_idx, (int)b0 + cbase);
                     if (!p.out_f32) tma_store_3d(&om[1], out_tile + LO_OFF, out_c0, t_idx, (int)b0 + cbase);

@@ -3,6 +3,7 @@
 
     python scripts/trace_recurrent.py [B] [T] [steps]
 
+Needs a diagnostic build (the stamps are compiled out of the default one): HSSB_TRACE=1 python __graft_entry__.py --force
 Runs one eval forward with tracing on and prints, per sub-tile, the mean cycle offsets of every
 event relative to the MMA thread's "h_full seen" stamp of the same step, plus the step period.
 """

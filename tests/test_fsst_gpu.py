@@ -366,3 +366,48 @@ def test_generic_window_lengths(lib, nwin, beta):
         assert feats[b].shape == ref.shape and np.abs(feats[b] - ref).max() < 5e-4
     ref_m = fo.fsst_features(x[0], fs, w, abs=True, truncate_freq=band)
     assert mags.shape == ref_m.shape and (np.abs(mags.numpy() - ref_m) > 1e-5 * ref_m.max()).mean() < 1e-4
+
+
+def test_closed_form_properties_on_the_cuda_output(lib):
+    """Independent of the oracle (which restates MATLAB fsst and cannot be pinned against libssq): closed-form facts asserted
+    directly on the CUDA transform, for the reference's Kaiser(128, 0.5) window and MATLAB's default Kaiser(256, 10).
+
+    1. Reconstruction identity.  Reassignment only moves S_g[k, t] e^{-i pi k} between rows of a column, so the two-sided column
+       sum is the inverse DFT of the windowed frame at its centre sample: sum_k T[k, t] = nfft * g[nwin/2] * x[t] for EVERY t,
+       i.e. with the one-sided rows  2 Re sum_{k=0}^{K-1} T - Re T[0] - Re T[K-1] = nfft * g[nwin/2] * x[t].
+    2. Linear chirp cos(2 pi (f0 t + c t^2 / 2)): the ridge of column t sits at row round((f0 + c t) nfft / fs), and holds
+       most of the column's energy (steps 4-6: IF estimate, phase shift, frequency reassignment).
+    3. Two bin-centred tones of amplitudes 1 and 0.5: interior columns have |T[k1]| = nfft g[nwin/2] / 2 and half of that at k2."""
+    from hss.transforms import FSST
+
+    fs, N = 1000.0, 2000
+    t = np.arange(N) / fs
+    for nwin, beta in ((128, 0.5), (256, 10.0)):
+        w = np.kaiser(nwin, beta)
+        K, g_c = nwin // 2 + 1, w[nwin // 2]
+        f = FSST(fs, window=w)
+        # 1. identity on a PCG-like signal and on noise
+        x = np.stack([fo.synth_pcg(N, seed=3), np.random.default_rng(1).standard_normal(N).astype(np.float32)])
+        T = f.batch(torch.from_numpy(x).cuda()).cpu().numpy().astype(np.complex128)
+        lhs = 2 * T.real.sum(axis=1) - T[:, 0].real - T[:, K - 1].real
+        assert np.abs(lhs - nwin * g_c * x).max() < 2e-5 * nwin * np.abs(x).max()
+        # 2. chirp 100 -> 300 Hz
+        f0, c = 100.0, 100.0
+        chirp = np.cos(2 * np.pi * (f0 * t + 0.5 * c * t * t)).astype(np.float32)
+        Tc = np.abs(f(torch.from_numpy(chirp)).numpy())
+        inner = slice(nwin, N - nwin)
+        ridge = Tc[:, inner].argmax(axis=0)
+        expect = np.rint((f0 + c * t[inner]) * nwin / fs).astype(int)
+        assert np.abs(ridge - expect).max() <= 1 and (ridge == expect).mean() > 0.9
+        if beta >= 4.0:          # (a well-concentrated window; the reference's near-rectangular Kaiser(0.5) leaks by design)
+            e = Tc[:, inner] ** 2
+            near = sum(np.take_along_axis(e, np.clip(expect + d, 0, K - 1)[None, :], axis=0)[0] for d in (-1, 0, 1))
+            assert (near / e.sum(axis=0)).min() > 0.9
+        # 3. two bin-centred tones
+        k1, k2 = nwin // 8, nwin // 4 + 3
+        tone = (np.cos(2 * np.pi * k1 * fs / nwin * t) + 0.5 * np.cos(2 * np.pi * k2 * fs / nwin * t)).astype(np.float32)
+        Tt = np.abs(f(torch.from_numpy(tone)).numpy())[:, inner]
+        assert np.abs(Tt[k1] - nwin * g_c / 2).max() < 5e-3 * nwin * g_c / 2
+        assert np.abs(Tt[k2] - nwin * g_c / 4).max() < 1e-2 * nwin * g_c / 4
+        rest = np.delete(Tt, [k1, k2], axis=0)
+        assert rest.max() < 2e-2 * nwin * g_c / 2
