@@ -974,6 +974,9 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
 {
     const TcWs w = tc_ws_layout(B, T);
     if (!ws || ws_bytes < w.total) return fail(HSSB_E_WORKSPACE, "model workspace %zu < %zu", ws_bytes, w.total);
+    // Calls on different caller streams (each with its own workspace) share the model's internal streams and events: their
+    // launches are enqueued one call at a time, the device work of different calls still overlaps where the streams allow.
+    std::lock_guard<std::mutex> enqueue_lock(*m->enqueue_mu);
     char *base = static_cast<char *>(ws);
     __half *xhi = reinterpret_cast<__half *>(base + w.xhi), *xlo = reinterpret_cast<__half *>(base + w.xlo);
     float *xproj = reinterpret_cast<float *>(base + w.xproj);

@@ -102,6 +102,7 @@ extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, v
     m->F = F; m->H = H;
     cudaGetDevice(&m->device);
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
+    m->enqueue_mu = new std::mutex();
     {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
@@ -157,6 +158,7 @@ extern "C" void hssb_model_destroy(hssb_model *m)
     if (m->hi_stream) cudaStreamDestroy(m->hi_stream);
     if (m->side_stream) cudaStreamDestroy(m->side_stream);
     for (int i = 0; i < 6; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    delete m->enqueue_mu;
     delete m;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "hssb_common.cuh"
 #include <cuda_fp16.h>
+#include <mutex>
 
 struct hssb_model {
     int F;          // input features (44)
@@ -31,6 +32,7 @@ struct hssb_model {
     cudaStream_t hi_stream, side_stream;
     cudaEvent_t ev[6];
     int sm_count;
+    std::mutex *enqueue_mu;   // the internal streams / events belong to the model: forwards on one model are ENQUEUED one at a time
 };
 
 namespace hssb {
