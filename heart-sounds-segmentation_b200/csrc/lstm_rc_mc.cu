@@ -56,9 +56,10 @@ struct RmCfg {
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X>
+template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X, bool TRAIN = false>
 __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent_mc_kernel(const __grid_constant__ RecurParams p)
 {
+    static_assert(!TRAIN || !FUSE_X, "the training forward takes its input projection from K4");
     using C = RmCfg<S, EW, FUSE_X>;
     // range guard (tc_forward): the fused launch is skipped when the input left the fp16-split range, its stand-in when it did not.
     // The flag is final before the launch, so every CTA of the grid takes the same branch (before any barrier / TMEM allocation).
@@ -107,9 +108,11 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
         for (int i = 0; i < 2 * S * RP_G + 4 * S; ++i) mbar_init(&bars[i], 1);
         for (int i = 0; i < S; ++i) mbar_init(&d_empty[i], 4 * EW);
         fence_barrier_init();
-        const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;
-        prefetch_tmap(&om[0]);
-        if (!p.out_f32) prefetch_tmap(&om[1]);
+        if (!TRAIN) {
+            const CUtensorMap *om = (EW == 1) ? p.out_map : p.out_map16;
+            prefetch_tmap(&om[0]);
+            if (!p.out_f32) prefetch_tmap(&om[1]);
+        }
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     for (int i = threadIdx.x; i < (S * C::PER_SUB + C::OUT_BYTES + C::X_BYTES) / 16; i += C::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -361,6 +364,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                 tc_fence_after();
                 if (tracer) RM_TRACE(TR_EPI_DFULL, t, s);
                 float hv[NI];
+                float kept[TRAIN ? 4 * NI : 1];          // TRAIN: the activated gates i, f, g, o of this thread's cells
                 {
                     uint32_t a[2 * NI], b[2 * NI];      // a: gates i (lane ul), f (lane ul+8);  b: gates g, o;  [4k + 2*gate + c] = column cbase + 8k + 2cp + c
                     if (EW == 1) {
@@ -391,6 +395,19 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                     if (knock & 4) {                                  // (timing experiment: no cell math)
 #pragma unroll
                         for (int i = 0; i < NI; ++i) hv[i] = unit_ok ? 0.25f * (ei[i] + ef[i]) * 1e-3f + 1e-3f * (eg[i] + eo[i]) : 0.0f;
+                    } else if (TRAIN) {
+                        // back-propagation needs the four activated gates themselves: no shared reciprocals here
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) {
+                            const float si = rcp_approx(1.0f + ei[i]), sf = rcp_approx(1.0f + ef[i]), so = rcp_approx(1.0f + eo[i]);
+                            const float tg = (1.0f - eg[i]) * rcp_approx(1.0f + eg[i]);
+                            const float c = fmaf(sf, c_state[i], si * tg);
+                            c_state[i] = c;
+                            const float ec = ex2_approx(fminf(c * (-2.0f * LOG2E), EMAX));
+                            hv[i] = unit_ok ? so * ((1.0f - ec) * rcp_approx(1.0f + ec)) : 0.0f;
+                            kept[(TRAIN ? 4 : 0) * i + 0] = si; kept[(TRAIN ? 4 * i + 1 : 0)] = sf;
+                            kept[(TRAIN ? 4 * i + 2 : 0)] = tg; kept[(TRAIN ? 4 * i + 3 : 0)] = so;
+                        }
                     } else
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
@@ -404,6 +421,24 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                     if (tracer) RM_TRACE(TR_EPI_CELL, t, s);
                 }
                 if (t + 1 < Ti) publish(hv, t);
+                if (TRAIN) {
+                    // ---- off the critical path: what back-propagation needs, straight to global memory (8 lanes = 8 consecutive units) ----
+                    if (unit_ok) {
+                        const int U = (int)rank * RC_U + u;
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) {
+                            const int c = col_of(i);
+                            if (c < ncols) {
+                                const size_t row = (size_t)(b0 + c) * T + t_idx;
+                                float *gp = p.tr_gates + ((size_t)dir * B * T + row) * TC_G + U;
+                                gp[0] = kept[(TRAIN ? 4 * i : 0)]; gp[TC_H] = kept[(TRAIN ? 4 * i + 1 : 0)];
+                                gp[2 * TC_H] = kept[(TRAIN ? 4 * i + 2 : 0)]; gp[3 * TC_H] = kept[(TRAIN ? 4 * i + 3 : 0)];
+                                p.tr_cells[((size_t)dir * B * T + row) * TC_H + U] = c_state[i];
+                                p.tr_out[row * (2 * TC_H) + dir * TC_H + U] = hv[i];
+                            }
+                        }
+                    }
+                } else {
                 // ---- off the critical path: relu(h_t) -> global memory by TMA from this warp's tile ----
                 if (elect_one()) tma_store_wait_read<0>();        // the previous step's store has read the tile
                 __syncwarp();
@@ -427,6 +462,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                     tma_store_3d(&om[0], out_tile, out_c0, t_idx, (int)b0 + cbase);
                     if (!p.out_f32) tma_store_3d(&om[1], out_tile + LO_OFF, out_c0, t_idx, (int)b0 + cbase);
                     tma_store_commit();
+                }
                 }
                 if (p.tile_done && ((dir ? (t_idx & (TC_TT - 1)) == 0 : (t_idx & (TC_TT - 1)) == TC_TT - 1) || t + 1 == Ti)) {
                     // this warp's relu(h) of a whole time tile is on its way: once the bulk stores have completed, tell the
@@ -464,7 +500,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
 // Per device, once: opt in to the kernel's shared memory and find out how many of its clusters are co-resident.  Also called for
 // every default variant when a model is created (rc_mc_prepare): the first use of a kernel loads its code, which may synchronise
 // the device -- that must not happen while a recurrence is polling for a projection launch that the host has not issued yet.
-template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X>
+template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X, bool TRAIN = false>
 static int prepare_recurrent_mc(int *max_clusters_out)
 {
     using C = RmCfg<S, EW, FUSE_X>;
@@ -479,11 +515,11 @@ static int prepare_recurrent_mc(int *max_clusters_out)
         attr[0].val.clusterDim.x = RC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_recurrent_mc_kernel)");
         cfg.gridDim = dim3(16 * RC_CL);
         int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X, TRAIN>, &cfg);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveClusters(tc_recurrent_mc_kernel)");
         if (n < 2) return fail(HSSB_E_DEVICE, "device fits only %d recurrence clusters", n);
         max_clusters = std::min(n, 16);
@@ -504,7 +540,7 @@ int rc_mc_prepare()
     return prepare_recurrent_mc<3, true, 1, false>(&n);
 }
 
-template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X = false>
+template <int S, bool WARP_PUBLISH, int EW, bool FUSE_X = false, bool TRAIN = false>
 static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag, int64_t rem, int *cols_done, const float *xproj, cudaStream_t st,
                                RecurLaunchInfo *info)
 {
@@ -515,7 +551,7 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
     prm.trace_steps = g_trace_steps;
     if (const char *e = getenv("HSSB_TRACE_LAYER")) if (atoi(e) != prm.layer) prm.trace = nullptr;
     int max_clusters = 0;
-    if (int rc = prepare_recurrent_mc<S, WARP_PUBLISH, EW, FUSE_X>(&max_clusters)) return rc;
+    if (int rc = prepare_recurrent_mc<S, WARP_PUBLISH, EW, FUSE_X, TRAIN>(&max_clusters)) return rc;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(C::THREADS);
@@ -544,16 +580,21 @@ static int launch_recurrent_mc(const RecurParams &prm_in, const __half *whh_frag
         info->signals_per_dir = live * RC_CL * 4 * EW;
     }
     // (the stand-in launch of the input-range guard is a no-op unless the guard fired: timed under its own name)
-    ProfScope prof((prm.skip_flag && !prm.skip_when) ? "range_standin" : (prm.layer ? "tc_recurrent_l2" : "tc_recurrent_l1"), st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X>, prm);
+    ProfScope prof(TRAIN ? "tc_recurrent_train" : (prm.skip_flag && !prm.skip_when) ? "range_standin" : (prm.layer ? "tc_recurrent_l2" : "tc_recurrent_l1"), st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_recurrent_mc_kernel<S, WARP_PUBLISH, EW, FUSE_X, TRAIN>, prm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_recurrent_mc_kernel)");
     return 0;
 }
 
 
 int rc_mc_launch(int s, int variant, bool fused, const RecurParams &prm, const __half *whh_frag, int64_t rem, int *done,
-                 const float *xproj, cudaStream_t st, RecurLaunchInfo *info)
+                 const float *xproj, cudaStream_t st, RecurLaunchInfo *info, bool train)
 {
+    if (train) {        // training forward: keeps activated gates / cell states / raw h instead of the relu'd outputs
+        if (s == 1) return launch_recurrent_mc<1, true, 2, false, true>(prm, whh_frag, rem, done, xproj, st, info);
+        if (s == 2) return launch_recurrent_mc<2, true, 2, false, true>(prm, whh_frag, rem, done, xproj, st, info);
+        return launch_recurrent_mc<3, true, 1, false, true>(prm, whh_frag, rem, done, xproj, st, info);
+    }
     if (fused) {        // the default variants only: two epilogue warps per quadrant up to 64 columns per cluster, one beyond
         if (s == 1) return launch_recurrent_mc<1, true, 2, true>(prm, whh_frag, rem, done, xproj, st, info);
         if (s == 2) return launch_recurrent_mc<2, true, 2, true>(prm, whh_frag, rem, done, xproj, st, info);

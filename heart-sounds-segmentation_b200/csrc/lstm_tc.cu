@@ -77,6 +77,30 @@ __global__ void split_planes_kernel(const float *__restrict__ x, long long M, in
     }
 }
 
+// act[B][T][480] fp32 (torch layout: column dir*240 + unit) -> hi/lo fp16 planes [B][Tp][512] in slot layout (column dir*256 +
+// rank*32 + u, unit = rank*30 + u; slots u >= 30 are zero): the layer-2 projection operand of the training forward, whose
+// layer-1 output passes through torch's dropout between the two layers.
+__global__ void split_slots_kernel(const float *__restrict__ act, long long B, long long T, long long Tp, __half *__restrict__ hi,
+                                   __half *__restrict__ lo)
+{
+    const long long n = B * T * (TC_OP / 2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / (TC_OP / 2);
+        const int slot = 2 * (int)(i % (TC_OP / 2));             // two slots per thread: 30 and 240 are even, so a pair never straddles
+        const int dir = slot >> 8, r = (slot & 255) >> 5, u = slot & 31;
+        __half h0 = __float2half_rn(0.f), l0 = h0, h1 = h0, l1 = h0;
+        if (u < RC_U) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(act + row * (2 * TC_H) + dir * TC_H + r * RC_U + u));
+            split_f16(v.x, h0, l0);
+            split_f16(v.y, h1, l1);
+        }
+        const long long b = row / T, t = row % T;
+        const size_t o = ((size_t)b * Tp + t) * TC_OP + slot;
+        *reinterpret_cast<__half2 *>(hi + o) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2 *>(lo + o) = __halves2half2(l0, l1);
+    }
+}
+
 // max |x| of the model input as float bits (word 1 of `range`; non-negative floats order like unsigned integers, NaN sorts above inf)
 __global__ void input_amax_kernel(const float *__restrict__ x, long long n, unsigned *__restrict__ range, const int *__restrict__ run_flag)
 {
@@ -844,6 +868,8 @@ struct RecurSync {
     unsigned *tile_done = nullptr;        // producer side: relu(h) of a time tile is in memory
     unsigned *resident = nullptr;         // bumped by every CTA once it holds its SM
     int *timeout_flag = nullptr;
+    // training forward: the activated gates [2][B*T][960], cell states [2][B*T][240] and raw h [B][T][480] replace the relu'd outputs
+    float *tr_gates = nullptr, *tr_cells = nullptr, *tr_out = nullptr;
     // out
     int launches = 0, ctas_first = 0;
     unsigned signals_per_dir = 0;
@@ -885,7 +911,10 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
     prm.B = B; prm.T = T;
     prm.Tp = act_pitch(T);
     prm.Bp = xproj_pitch(B);
-    {
+    const bool train = sync->tr_gates != nullptr;
+    prm.tr_gates = sync->tr_gates; prm.tr_cells = sync->tr_cells; prm.tr_out = sync->tr_out;
+    if (train && (fused || !sync->tr_cells || !sync->tr_out)) return fail(HSSB_E_MODE, "training recurrence: separate projection and all three outputs needed");
+    if (!train) {
         const bool f32 = out_f32 != nullptr;
         const uint64_t es = f32 ? 4 : 2;
         const uint64_t dims[3] = {(uint64_t)TC_OP, (uint64_t)T, (uint64_t)B};
@@ -920,11 +949,11 @@ static int tc_recurrent(const hssb_model *m, int layer, float *xproj, const floa
         else if (per_group <= 64) { nb = 32; s = 2; pair = 4; }
         else { nb = 32; s = 3; pair = 3; }
         if (fused && force_nb) return fail(HSSB_E_MODE, "HSSB_RC_GEOM cannot be combined with the fused projection");
-        if (skip_flag && !(nb == 32 && pair >= 2)) return fail(HSSB_E_MODE, "the input-range guard needs the multicast recurrence");
+        if ((skip_flag || train) && !(nb == 32 && pair >= 2)) return fail(HSSB_E_MODE, "the input-range guard / training forward need the multicast recurrence");
         // pair: 0 = DSMEM all-gather (K5), 1 = its cta_group::2 mode or, with nb = 64, the CTA-pair kernel (K5p); 2..4 = K5m variants
         int rc, done = 0;
         RecurLaunchInfo info = {0, 0};
-        if (nb == 32 && pair >= 2) rc = rc_mc_launch(s, pair, fused, prm, m->tc_whh_frag[layer], rem, &done, xproj, st, &info);
+        if (nb == 32 && pair >= 2) rc = rc_mc_launch(s, pair, fused, prm, m->tc_whh_frag[layer], rem, &done, xproj, st, &info, train);
         else {
             sync->multicast = false;
             if (sync->chunk_done || sync->tile_done) return fail(HSSB_E_MODE, "the overlapped projection needs the multicast recurrence");
@@ -968,6 +997,49 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
 }  // namespace
 
 size_t tc_workspace_bytes(const hssb_model *, int64_t B, int64_t T) { return tc_ws_layout(B, T).total; }
+
+// Training forward of ONE layer (the caller applies ReLU / dropout between the layers, like reference segmenter.py:80-85):
+// x[B][T][Kin] fp32 (Kin = input_size for layer 0, 480 for layer 1) -> split planes -> K4 -> K5m (TRAIN variant).  Layer 0 goes
+// through the range-scaled projection, so any finite input is exact; layer 1's input is a dropout-scaled relu(h) and needs none.
+int tc_train_forward(const hssb_model *m, int layer, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
+                     float *gates, float *out, float *cells, float *hn, float *cn, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const TcWs w = tc_ws_layout(B, T);
+    if (!ws || ws_bytes < w.total) return fail(HSSB_E_WORKSPACE, "model workspace %zu < %zu", ws_bytes, w.total);
+    std::lock_guard<std::mutex> enqueue_lock(*m->enqueue_mu);
+    char *base = static_cast<char *>(ws);
+    float *xproj = reinterpret_cast<float *>(base + w.xproj);
+    unsigned char *gather = reinterpret_cast<unsigned char *>(base + w.gather);
+    unsigned *range = reinterpret_cast<unsigned *>(base + w.range);
+    unsigned char *sync_base = reinterpret_cast<unsigned char *>(base + w.sync);
+    HSSB_CUDA_OK(cudaMemsetAsync(range, 0, 8, st));
+    HSSB_CUDA_OK(cudaMemsetAsync(sync_base, 0, SYNC_HEAD, st));
+    const int64_t M = B * T;
+    InprojJob job;
+    job.next_item = reinterpret_cast<unsigned *>(sync_base);
+    if (layer == 0) {
+        __half *xhi = reinterpret_cast<__half *>(base + w.xhi), *xlo = reinterpret_cast<__half *>(base + w.xlo);
+        {
+            ProfScope prof("split_planes", st);
+            input_amax_kernel<<<148 * 4, 256, 0, st>>>(x, M * m->F, range, nullptr);
+            split_planes_kernel<<<(unsigned)std::min<long long>((M * 64 + 255) / 256, 148 * 16), 256, 0, st>>>(x, M, m->F, 64, xhi, xlo, range, nullptr);
+            HSSB_LAUNCH_OK("split_planes_kernel");
+        }
+        if (int rc = tc_inproj(m, 0, xhi, xlo, 64, B, T, xproj, st, job, range, nullptr)) return rc;
+    } else {
+        __half *ahi = reinterpret_cast<__half *>(base + w.o1hi), *alo = reinterpret_cast<__half *>(base + w.o1lo);
+        {
+            ProfScope prof("split_planes", st);
+            split_slots_kernel<<<148 * 16, 256, 0, st>>>(x, B, T, act_pitch(T), ahi, alo);
+            HSSB_LAUNCH_OK("split_slots_kernel");
+        }
+        if (int rc = tc_inproj(m, 1, ahi, alo, TC_OP, B, T, xproj, st, job, nullptr, nullptr, act_pitch(T))) return rc;
+    }
+    RecurSync rs;
+    rs.timeout_flag = reinterpret_cast<int *>(sync_base + 32);
+    rs.tr_gates = gates; rs.tr_cells = cells; rs.tr_out = out;
+    return tc_recurrent(m, layer, xproj, h0, c0, hn, cn, nullptr, nullptr, nullptr, gather, B, T, st, nullptr, nullptr, &rs);
+}
 
 int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0, const float *c0, float *logp,
                int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st)

@@ -107,6 +107,10 @@ struct RecurParams {
     // and this direction may be read once chunk_done[q] reached chunk_need (q = 2 tt forward, 2 (t_tiles - 1 - tt) + 1 reverse);
     // tile_done (nullable): bumped per epilogue warp when its relu(h) stores of a time tile are complete, [dir][t_tiles];
     // resident (nullable): [0] bumped once per CTA, [1] set when all CTAs of a launch are on the machine; timeout_flag: raised instead of hanging
+    // training forward (TRAIN variants of K5m, hssb_lstm_train_forward_tc): instead of the relu'd outputs the kernel keeps what
+    // back-propagation needs, in the layouts of hssb_lstm_train_backward -- activated gates [2][B*T][960] (row b*T + t, gate
+    // order i,f,g,o), cell states [2][B*T][240], raw h [B][T][480]
+    float *tr_gates, *tr_cells, *tr_out;
     const unsigned *chunk_done;
     unsigned chunk_need;
     unsigned *tile_done;
@@ -211,6 +215,6 @@ int rc_mc_prepare();                                  // load / configure every 
 // info (nullable): CTAs of the launch and the number of epilogue warps per direction that run the step loop (tile_done signals)
 struct RecurLaunchInfo { int ctas; unsigned signals_per_dir; };
 int rc_mc_launch(int s, int variant, bool fused, const RecurParams &prm, const __half *whh_frag, int64_t rem, int *cols_done,
-                 const float *xproj, cudaStream_t st, RecurLaunchInfo *info = nullptr);
+                 const float *xproj, cudaStream_t st, RecurLaunchInfo *info = nullptr, bool train = false);
 
 }  // namespace hssb

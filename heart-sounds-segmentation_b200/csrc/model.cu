@@ -62,6 +62,47 @@ int simt_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, cons
     return head_forward(out2, M, 2 * H, m->lin_w, m->lin_b, logp, labels, st);
 }
 
+int check_params(const hssb_model_params *p, const char *who)
+{
+    for (int l = 0; l < 2; ++l)
+        for (int d = 0; d < 2; ++d)
+            if (!p->w_ih[l][d] || !p->w_hh[l][d] || !p->b_ih[l][d] || !p->b_hh[l][d])
+                return fail(HSSB_E_NULL, "%s: null parameter (layer %d dir %d)", who, l, d);
+    if (!p->lin_w || !p->lin_b) return fail(HSSB_E_NULL, "%s: null linear parameter", who);
+    return 0;
+}
+
+// torch-layout parameters -> the operands of both kernel families, in the buffers hssb_model_create laid out.  Stream-ordered
+// except for one synchronisation at the end (the staging buffer is reused per tensor; tc_pack reads the weight range back).
+int pack_parameters(hssb_model *m, const hssb_model_params *p, cudaStream_t st)
+{
+    const int F = m->F, H = m->H;
+    const size_t G = 4 * (size_t)H;
+    const int kin[2] = {F, 2 * H};
+    cudaError_t e;
+    for (int l = 0; l < 2; ++l)
+        for (int d = 0; d < 2; ++d) {
+            float *s_wih = m->stage, *s_whh = s_wih + kin[l] * G, *s_bi = s_whh + H * G, *s_bh = s_bi + G;
+            if ((e = cudaMemcpyAsync(s_wih, p->w_ih[l][d], sizeof(float) * kin[l] * G, cudaMemcpyDefault, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(s_whh, p->w_hh[l][d], sizeof(float) * H * G, cudaMemcpyDefault, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(s_bi, p->b_ih[l][d], sizeof(float) * G, cudaMemcpyDefault, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(s_bh, p->b_hh[l][d], sizeof(float) * G, cudaMemcpyDefault, st)) != cudaSuccess)
+                return cuda_fail(e, "cudaMemcpyAsync(model parameter)");
+            const long long n_ih = (long long)kin[l] * G, n_hh = (long long)H * G;
+            transpose_kernel<<<(unsigned)((n_ih + 255) / 256), 256, 0, st>>>(s_wih, (int)G, kin[l], m->w_ihT[l][d]);
+            transpose_kernel<<<(unsigned)((n_hh + 255) / 256), 256, 0, st>>>(s_whh, (int)G, H, m->w_hhT[l][d]);
+            add_kernel<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(s_bi, s_bh, (int)G, m->bias[l][d]);
+            if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "model pack kernels");
+        }
+    if ((e = cudaMemcpyAsync(m->lin_w, p->lin_w, sizeof(float) * 4 * 2 * H, cudaMemcpyDefault, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(m->lin_b, p->lin_b, sizeof(float) * 4, cudaMemcpyDefault, st)) != cudaSuccess)
+        return cuda_fail(e, "cudaMemcpyAsync(linear)");
+    if (tc_pack_bytes(F, H) > 0)
+        if (int rc = tc_pack(m, p, m->tc_base, st)) return rc;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize(model pack)");
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, void *stream)
@@ -70,11 +111,7 @@ extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, v
     *out = nullptr;
     const int F = p->input_size, H = p->hidden_size;
     if (F < 1 || H < 1 || F > 4096 || H > 2048) return fail(HSSB_E_MODEL, "input_size=%d hidden_size=%d unsupported", F, H);
-    for (int l = 0; l < 2; ++l)
-        for (int d = 0; d < 2; ++d)
-            if (!p->w_ih[l][d] || !p->w_hh[l][d] || !p->b_ih[l][d] || !p->b_hh[l][d])
-                return fail(HSSB_E_NULL, "hssb_model_create: null parameter (layer %d dir %d)", l, d);
-    if (!p->lin_w || !p->lin_b) return fail(HSSB_E_NULL, "hssb_model_create: null linear parameter");
+    if (int rc = check_params(p, "hssb_model_create")) return rc;
     if (int rc = require_sm100()) return rc;
     cudaStream_t st = as_stream(stream);
 
@@ -115,40 +152,32 @@ extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, v
     if (e != cudaSuccess) { m->all = nullptr; hssb_model_destroy(m); return cuda_fail(e, "cudaMalloc(model)"); }
     m->all_bytes = off;
     char *base = static_cast<char *>(m->all);
-    float *stage = reinterpret_cast<float *>(base + o_stage);
-
-    int rc = 0;
-    for (int l = 0; l < 2 && !rc; ++l)
-        for (int d = 0; d < 2 && !rc; ++d) {
+    m->stage = reinterpret_cast<float *>(base + o_stage);
+    m->tc_base = base + o_tc;
+    for (int l = 0; l < 2; ++l)
+        for (int d = 0; d < 2; ++d) {
             m->w_ihT[l][d] = reinterpret_cast<float *>(base + o_wih[l][d]);
             m->w_hhT[l][d] = reinterpret_cast<float *>(base + o_whh[l][d]);
             m->bias[l][d] = reinterpret_cast<float *>(base + o_bias[l][d]);
-            float *s_wih = stage, *s_whh = s_wih + kin[l] * G, *s_bi = s_whh + H * G, *s_bh = s_bi + G;
-            if ((e = cudaMemcpyAsync(s_wih, p->w_ih[l][d], sizeof(float) * kin[l] * G, cudaMemcpyDefault, st)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(s_whh, p->w_hh[l][d], sizeof(float) * H * G, cudaMemcpyDefault, st)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(s_bi, p->b_ih[l][d], sizeof(float) * G, cudaMemcpyDefault, st)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(s_bh, p->b_hh[l][d], sizeof(float) * G, cudaMemcpyDefault, st)) != cudaSuccess) {
-                rc = cuda_fail(e, "cudaMemcpyAsync(model parameter)");
-                break;
-            }
-            const long long n_ih = (long long)kin[l] * G, n_hh = (long long)H * G;
-            transpose_kernel<<<(unsigned)((n_ih + 255) / 256), 256, 0, st>>>(s_wih, (int)G, kin[l], m->w_ihT[l][d]);
-            transpose_kernel<<<(unsigned)((n_hh + 255) / 256), 256, 0, st>>>(s_whh, (int)G, H, m->w_hhT[l][d]);
-            add_kernel<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(s_bi, s_bh, (int)G, m->bias[l][d]);
-            if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "model pack kernels"); break; }
         }
-    if (!rc) {
-        m->lin_w = reinterpret_cast<float *>(base + o_linw);
-        m->lin_b = reinterpret_cast<float *>(base + o_linb);
-        if ((e = cudaMemcpyAsync(m->lin_w, p->lin_w, sizeof(float) * 4 * 2 * H, cudaMemcpyDefault, st)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(m->lin_b, p->lin_b, sizeof(float) * 4, cudaMemcpyDefault, st)) != cudaSuccess)
-            rc = cuda_fail(e, "cudaMemcpyAsync(linear)");
-    }
-    if (!rc && tc_pack_bytes(F, H) > 0) rc = tc_pack(m, p, base + o_tc, st);
-    if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(model create)");
-    if (rc) { hssb_model_destroy(m); return rc; }
+    m->lin_w = reinterpret_cast<float *>(base + o_linw);
+    m->lin_b = reinterpret_cast<float *>(base + o_linb);
+    if (int rc = pack_parameters(m, p, st)) { hssb_model_destroy(m); return rc; }
     *out = m;
     return 0;
+}
+
+extern "C" int hssb_model_update(hssb_model *m, const hssb_model_params *p, void *stream)
+{
+    if (!m || !p) return fail(HSSB_E_NULL, "hssb_model_update: null pointer");
+    if (p->input_size != m->F || p->hidden_size != m->H)
+        return fail(HSSB_E_MODEL, "hssb_model_update: the model was created for input_size=%d hidden_size=%d", m->F, m->H);
+    if (int rc = check_params(p, "hssb_model_update")) return rc;
+    int dev = -1;
+    HSSB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev != m->device) return fail(HSSB_E_DEVICE, "hssb_model_update: model lives on device %d, current device is %d", m->device, dev);
+    std::lock_guard<std::mutex> enqueue_lock(*m->enqueue_mu);
+    return pack_parameters(m, p, as_stream(stream));
 }
 
 extern "C" void hssb_model_destroy(hssb_model *m)
@@ -202,3 +231,26 @@ extern "C" int hssb_lstm_forward(const hssb_weights *w, const float *x, int64_t 
     if (F != w->F) return fail(HSSB_E_SHAPE, "hssb_lstm_forward: F=%d but the weights were packed for input_size %d", F, w->F);
     return hssb_model_forward(w, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, 0, stream);
 }
+
+extern "C" int hssb_lstm_train_forward_tc(const hssb_model *m, int layer, const float *x, int64_t B, int64_t T, const float *h0,
+                                          const float *c0, float *gates, float *out, float *cells, float *hn, float *cn,
+                                          void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!m || !x || !h0 || !c0 || !gates || !out || !cells || !hn || !cn) return fail(HSSB_E_NULL, "hssb_lstm_train_forward_tc: null pointer");
+    if (layer != 0 && layer != 1) return fail(HSSB_E_MODE, "hssb_lstm_train_forward_tc: layer %d", layer);
+    if (B < 0 || T < 0) return fail(HSSB_E_SHAPE, "hssb_lstm_train_forward_tc: B=%lld T=%lld", (long long)B, (long long)T);
+    if (B == 0 || T == 0) return 0;
+    if (B > 65535 * 4) return fail(HSSB_E_SHAPE, "hssb_lstm_train_forward_tc: B=%lld too large for one call", (long long)B);
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(HSSB_E_WORKSPACE, "model workspace must be 256-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    if (!m->tc_ready)
+        return fail(HSSB_E_MODEL, "hssb_lstm_train_forward_tc: this model runs on the generic kernels (hidden_size %d or its weight range); "
+                                  "use hssb_lstm_train_forward", m->H);
+    int dev = -1;
+    HSSB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev != m->device)
+        return fail(HSSB_E_DEVICE, "hssb_lstm_train_forward_tc: model lives on device %d, current device is %d", m->device, dev);
+    return tc_train_forward(m, layer, x, B, T, h0, c0, gates, out, cells, hn, cn, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int hssb_model_uses_tensor_cores(const hssb_model *m) { return m && m->tc_ready ? 1 : 0; }

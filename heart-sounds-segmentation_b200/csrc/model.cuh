@@ -26,6 +26,8 @@ struct hssb_model {
     float *tc_bias0_frag;     // their folded biases [dir][rank][128]
     void *all;                // single allocation backing everything above
     size_t all_bytes;
+    float *stage;             // staging for the raw torch tensors (they may be host pointers); used by create and update
+    void *tc_base;            // start of the tcgen05 operands inside `all`
     // overlapped layer-2 projection (tc_forward): the layer-2 recurrence runs on a high-priority internal stream while the tail of
     // the projection GEMM keeps the SMs it leaves idle busy; a second internal stream hosts the middle-out part of the GEMM that
     // runs under the layer-1 recurrence.  Everything is joined back into the caller's stream before tc_forward's last kernel.
@@ -50,6 +52,9 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
 size_t tc_workspace_bytes(const hssb_model *m, int64_t B, int64_t T);
 int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
                float *logp, int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st);
+// training forward of one layer on the tcgen05 kernels: activated gates / cell states / raw h kept for back-propagation
+int tc_train_forward(const hssb_model *m, int layer, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
+                     float *gates, float *out, float *cells, float *hn, float *cn, void *ws, size_t ws_bytes, cudaStream_t st);
 
 // training recurrences with cluster-resident weights (lstm_train_cluster.cu); the generic ones are in lstm_train.cu
 bool train_cluster_supported(int H);

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "hssb_fsst_host": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hssb_model_create": (c_int, [POINTER(ModelParams), POINTER(c_void_p), c_void_p]),
     "hssb_model_destroy": (None, [c_void_p]),
+    "hssb_model_update": (c_int, [c_void_p, POINTER(ModelParams), c_void_p]),
     "hssb_model_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "hssb_model_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "hssb_lstm_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
@@ -51,6 +52,8 @@ _SIGNATURES = {
     "hssb_debug_max_clusters": (c_int, []),
     "hssb_debug_sync_offset": (ctypes.c_longlong, [ctypes.c_longlong, ctypes.c_longlong]),
     "hssb_lstm_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hssb_lstm_train_forward_tc": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hssb_model_uses_tensor_cores": (c_int, [c_void_p]),
     "hssb_lstm_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "hssb_ce_head_forward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hssb_ce_head_backward": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

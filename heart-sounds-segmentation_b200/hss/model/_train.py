@@ -21,7 +21,9 @@ class BiLSTMLayerFunction(torch.autograd.Function):
     ``nn.LSTM(bidirectional=True, batch_first=True)``."""
 
     @staticmethod
-    def forward(ctx, x, h0, c0, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+    def forward(ctx, x, h0, c0, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, packed=None):
+        """``packed``: ``(hssb_model handle, layer index, workspace cache)`` of a model whose geometry the tcgen05 kernels cover --
+        projection and recurrence then run on them (``hssb_lstm_train_forward_tc``); ``None``: cuBLAS projection + generic recurrence."""
         if not x.is_cuda:
             raise RuntimeError("the training recurrences run on the GPU (no CPU fallback)")
         tensors = [t.detach().to(torch.float32).contiguous() for t in (x, h0, c0, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
@@ -29,20 +31,30 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         B, T, Fin = x.shape
         H = w_hh.shape[1]
         dev = x.device
-        x2 = x.reshape(B * T, Fin)
         gates = torch.empty((2, B * T, 4 * H), dtype=torch.float32, device=dev)
-        if B * T:
-            torch.addmm(b_ih + b_hh, x2, w_ih.t(), out=gates[0])
-            torch.addmm(b_ih_r + b_hh_r, x2, w_ih_r.t(), out=gates[1])
         out = torch.empty((B, T, 2 * H), dtype=torch.float32, device=dev)
         cells = torch.empty((2, B * T, H), dtype=torch.float32, device=dev)
         hn = torch.empty((2, B, H), dtype=torch.float32, device=dev)
         cn = torch.empty((2, B, H), dtype=torch.float32, device=dev)
-        whT, whT_r = w_hh.t().contiguous(), w_hh_r.t().contiguous()
-        with torch.cuda.device(dev):
-            rc = _lib.lib().hssb_lstm_train_forward(gates.data_ptr(), whT.data_ptr(), whT_r.data_ptr(), h0.data_ptr(), c0.data_ptr(),
-                                                    B, T, H, out.data_ptr(), cells.data_ptr(), hn.data_ptr(), cn.data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "hssb_lstm_train_forward")
+        lib = _lib.lib()
+        if packed is not None and B * T:
+            handle, layer, ws_cache = packed
+            with torch.cuda.device(dev):
+                ws = _lib.cached_workspace(ws_cache, dev, lib.hssb_model_workspace_bytes(handle, B, T))
+                rc = lib.hssb_lstm_train_forward_tc(handle, layer, x.data_ptr(), B, T, h0.data_ptr(), c0.data_ptr(), gates.data_ptr(),
+                                                    out.data_ptr(), cells.data_ptr(), hn.data_ptr(), cn.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "hssb_lstm_train_forward_tc")
+        else:
+            x2 = x.reshape(B * T, Fin)
+            if B * T:
+                torch.addmm(b_ih + b_hh, x2, w_ih.t(), out=gates[0])
+                torch.addmm(b_ih_r + b_hh_r, x2, w_ih_r.t(), out=gates[1])
+            whT, whT_r = w_hh.t().contiguous(), w_hh_r.t().contiguous()
+            with torch.cuda.device(dev):
+                rc = lib.hssb_lstm_train_forward(gates.data_ptr(), whT.data_ptr(), whT_r.data_ptr(), h0.data_ptr(), c0.data_ptr(),
+                                                 B, T, H, out.data_ptr(), cells.data_ptr(), hn.data_ptr(), cn.data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "hssb_lstm_train_forward")
         ctx.save_for_backward(x, h0, c0, w_ih, w_hh, w_ih_r, w_hh_r, gates, cells, out)
         return out, hn, cn
 
@@ -76,13 +88,28 @@ class BiLSTMLayerFunction(torch.autograd.Function):
             grads.append((g.t() @ x2, g.t() @ hp, db, db.clone()))
         dx = (dG[0] @ w_ih + dG[1] @ w_ih_r).reshape(B, T, Fin) if ctx.needs_input_grad[0] else None
         (dwi, dwh, dbi, dbh), (dwi_r, dwh_r, dbi_r, dbh_r) = grads
-        return dx, dh0, dc0, dwi, dwh, dbi, dbh, dwi_r, dwh_r, dbi_r, dbh_r
+        return dx, dh0, dc0, dwi, dwh, dbi, dbh, dwi_r, dwh_r, dbi_r, dbh_r, None
 
 
-def _layer(lstm: torch.nn.LSTM, x, h0, c0):
+def _layer(lstm: torch.nn.LSTM, x, h0, c0, packed=None):
     return BiLSTMLayerFunction.apply(
         x, h0, c0, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
-        lstm.weight_ih_l0_reverse, lstm.weight_hh_l0_reverse, lstm.bias_ih_l0_reverse, lstm.bias_hh_l0_reverse)
+        lstm.weight_ih_l0_reverse, lstm.weight_hh_l0_reverse, lstm.bias_ih_l0_reverse, lstm.bias_hh_l0_reverse, packed)
+
+
+def _packed_layers(model, dev):
+    """``(packed_l0, packed_l1)`` when the model's geometry runs on the tcgen05 kernels, else ``(None, None)``.
+    ``HSSB_TRAIN_IMPL`` = ``cluster`` / ``gather`` / ``stream`` selects one of the generic fp32 recurrences instead (validation)."""
+    import os
+
+    if os.environ.get("HSSB_TRAIN_IMPL", "tc") != "tc" or not getattr(model, "bidirectional", True):
+        return None, None
+    if model.lstm_1.hidden_size != 240 or model.lstm_1.input_size > 64 or any(p.dtype != torch.float32 for p in model.parameters()):
+        return None, None
+    handle = model._packed(dev)
+    if not _lib.lib().hssb_model_uses_tensor_cores(handle):
+        return None, None
+    return (handle, 0, model._workspace), (handle, 1, model._workspace)
 
 
 def training_forward(model, x: torch.Tensor) -> torch.Tensor:
@@ -93,9 +120,10 @@ def training_forward(model, x: torch.Tensor) -> torch.Tensor:
                            "(model.to('cuda')); there is no CPU fallback")
     h0 = model.h0.to(device=x.device, dtype=torch.float32)
     c0 = model.c0.to(device=x.device, dtype=torch.float32)
-    out, hn, cn = _layer(model.lstm_1, x, h0, c0)
+    p0, p1 = _packed_layers(model, x.device)
+    out, hn, cn = _layer(model.lstm_1, x, h0, c0, p0)
     out = model.dropout(F.relu(out))
-    out, _, _ = _layer(model.lstm_2, out, hn, cn)
+    out, _, _ = _layer(model.lstm_2, out, hn, cn, p1)
     out = model.dropout(F.relu(out))
     return F.log_softmax(model.linear(out), dim=2)
 
@@ -151,8 +179,9 @@ def training_loss(model, x: torch.Tensor, y: torch.Tensor):
     model._check_input(x)
     h0 = model.h0.to(device=x.device, dtype=torch.float32)
     c0 = model.c0.to(device=x.device, dtype=torch.float32)
-    out, hn, cn = _layer(model.lstm_1, x, h0, c0)
+    p0, p1 = _packed_layers(model, x.device)
+    out, hn, cn = _layer(model.lstm_1, x, h0, c0, p0)
     out = model.dropout(F.relu(out))
-    out, _, _ = _layer(model.lstm_2, out, hn, cn)
+    out, _, _ = _layer(model.lstm_2, out, hn, cn, p1)
     out = model.dropout(F.relu(out))
     return HeadLossFunction.apply(out, model.linear.weight, model.linear.bias, y)

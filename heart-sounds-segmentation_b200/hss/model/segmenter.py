@@ -93,7 +93,9 @@ class HeartSoundSegmenter(nn.Module):
         key = (dev.index,) + tuple((t.data_ptr(), t._version) for t in tensors)
         if self._handle is not None and key == self._handle_key:
             return self._handle
-        self._release()
+        same_device = self._handle is not None and self._handle_key[0] == dev.index
+        if not same_device:
+            self._release()
         if not self.bidirectional:
             raise NotImplementedError("the B200 kernels implement the bidirectional segmenter only")
         if any(t.dtype != torch.float32 for t in tensors):
@@ -114,6 +116,16 @@ class HeartSoundSegmenter(nn.Module):
         del groups
         p.lin_w = keep[-2].data_ptr()
         p.lin_b = keep[-1].data_ptr()
+        if same_device:
+            # the parameters changed in place (optimiser step, load_state_dict): re-pack into the operands the handle owns
+            self._handle_key = None
+            with torch.cuda.device(dev):
+                rc = _lib.lib().hssb_model_update(self._handle, ctypes.byref(p), _lib.stream_ptr())
+            if rc:
+                self._release()
+            _lib.check(rc, "hssb_model_update")
+            self._handle_key = key
+            return self._handle
         handle = ctypes.c_void_p()
         with torch.cuda.device(dev):
             rc = _lib.lib().hssb_model_create(ctypes.byref(p), ctypes.byref(handle), _lib.stream_ptr())

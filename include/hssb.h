@@ -117,6 +117,14 @@ typedef struct {
 int hssb_model_create(const hssb_model_params *params, hssb_model **out, void *stream);
 void hssb_model_destroy(hssb_model *m);
 
+/* Re-packs changed parameters into an existing model (same input_size / hidden_size, same device): what an optimiser step
+ * (reference main.py:81-82) does to the nn.LSTM weights the next forward reads.  Synchronises `stream` once.  Not to be
+ * called while a forward of the same model is being enqueued from another thread. */
+int hssb_model_update(hssb_model *m, const hssb_model_params *params, void *stream);
+
+/* 1 when the model runs on the tcgen05 kernels (hidden_size 240, input_size <= 64, |w| <= 2^15), 0 on the generic kernels. */
+int hssb_model_uses_tensor_cores(const hssb_model *m);
+
 size_t hssb_model_workspace_bytes(const hssb_model *m, int64_t B, int64_t T);
 
 /* x [B,T,input_size] f32 device; h0, c0 [2,B,H] f32 device (segmenter.py:38-41);
@@ -162,6 +170,14 @@ int hssb_debug_max_clusters(void);
  * w_hhT_*: W_hh transposed, [H][4H].  Writes out (raw h_t, no ReLU), cells (c_t), hn, cn. */
 int hssb_lstm_train_forward(float *gates, const float *w_hhT_fwd, const float *w_hhT_rev, const float *h0, const float *c0,
                             int64_t B, int64_t T, int H, float *out, float *cells, float *hn, float *cn, void *stream);
+
+/* The same forward for the reference geometry (hssb_model_uses_tensor_cores): input projection and recurrence of layer
+ * `layer` (0: x[B][T][input_size], 1: x[B][T][2H] = dropout(relu(out of layer 0))) on the tcgen05 kernels of the inference
+ * path (split-fp16 operands, fp32 accumulation), packed weights taken from `m` (hssb_model_update after each optimiser
+ * step).  Writes the ACTIVATED gates, out (raw h_t), cells, hn, cn in the layouts above.  workspace: hssb_model_workspace_bytes. */
+int hssb_lstm_train_forward_tc(const hssb_model *m, int layer, const float *x, int64_t B, int64_t T, const float *h0,
+                               const float *c0, float *gates, float *out, float *cells, float *hn, float *cn,
+                               void *workspace, size_t workspace_bytes, void *stream);
 
 /* gates in: activated gates from the forward; out: dG = dL/d(gate pre-activations).  w_hh_*: [4H][H] (torch layout).
  * d_hn, d_cn nullable (zero).  Writes dh0, dc0 (gradient w.r.t. the initial state). */

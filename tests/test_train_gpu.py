@@ -2,9 +2,10 @@
 reference's own arithmetic -- torch's CPU ``nn.LSTM`` under autograd (oracle/lstm_oracle.training_reference).
 
 Tolerance: fp32 with a different summation order (the gradients are sums over B*T terms): loss within 1e-5 relative,
-every gradient within 2e-4 of its tensor's max-abs against the fp32 reference (measured: ~1e-6).  The distance to a float64
-run of the reference is printed, not asserted: a ReLU input within rounding of zero switches sides between precisions and
-moves the gradient discontinuously (measured 9e-3 for the fp32 reference itself on the 9 x 64 case).
+every gradient within 2e-4 of its tensor's max-abs against the reference (measured: ~1e-6).  "The reference" is its fp32 run
+or, per tensor, its float64 run: a ReLU input within rounding of zero switches sides between two roundings of the same
+forward and moves the gradient discontinuously -- on the 9 x 64 case the reference's own fp32 and float64 runs differ by 9e-3
+for that reason, and the GPU forward (tcgen05 path: split-fp16 operands, approximate exp2) lands on the float64 side there.
 """
 import numpy as np
 import pytest
@@ -55,16 +56,16 @@ def test_training_step_gradients_match_torch_cpu(lib, B, T, F, H):
     assert (logp.detach().cpu() - ref_logp).abs().max() < 2e-5
     worst = worst64 = 0.0
     for name, p in m.named_parameters():
-        e = rel_err(p.grad.cpu(), ref_grads[name])
-        worst = max(worst, e)
-        worst64 = max(worst64, rel_err(p.grad.cpu().double(), grads64[name]), rel_err(ref_grads[name].double(), grads64[name]))
-        assert e < REL_TOL, (name, e)
-    assert rel_err(xg.grad.cpu(), ref_dx) < REL_TOL
+        e32, e64 = rel_err(p.grad.cpu(), ref_grads[name]), rel_err(p.grad.cpu().double(), grads64[name])
+        worst = max(worst, min(e32, e64))
+        worst64 = max(worst64, rel_err(ref_grads[name].double(), grads64[name]))
+        assert min(e32, e64) < REL_TOL, (name, e32, e64)
+    assert min(rel_err(xg.grad.cpu(), ref_dx), rel_err(xg.grad.cpu().double(), dx64)) < REL_TOL
     # eval mode on the same module = the inference kernels, same numbers as the training forward without dropout
     m.eval()
     with torch.no_grad():
         assert (m(x.cuda()) - logp.detach()).abs().max() < 2e-5
-    print(f"B={B} T={T} F={F} H={H}: worst relative gradient error {worst:.2e} (fp32 reference), {worst64:.2e} (either fp32 run vs float64)")
+    print(f"B={B} T={T} F={F} H={H}: worst relative gradient error {worst:.2e} (nearer of the fp32 / float64 reference runs), those two runs differ by {worst64:.2e}")
 
 
 def test_dropout_masks_and_an_optimizer_step(lib):
@@ -126,7 +127,8 @@ def test_cluster_and_streaming_kernels_agree(lib, monkeypatch):
     x = torch.randn(B, T, F, generator=g).cuda()
     y = torch.randint(0, 4, (B, T), generator=g).cuda()
     results = []
-    for impl in ("cluster", "gather", "stream"):     # default (reduce-scatter backward), all-gather backward, generic kernels
+    # cluster: fp32 cluster kernels (reduce-scatter backward); gather: all-gather backward; stream: generic kernels
+    for impl in ("cluster", "gather", "stream"):
         monkeypatch.setenv("HSSB_TRAIN_IMPL", impl)
         m = make_model(11, F, B, 240).cuda().train()
         m.dropout.p = 0.0
@@ -137,6 +139,101 @@ def test_cluster_and_streaming_kernels_agree(lib, monkeypatch):
         assert abs(loss - results[2][0]) < 1e-6 * abs(results[2][0])
         for name in grads:
             assert rel_err(grads[name], results[2][1][name]) < 2e-5, name
+
+
+@pytest.mark.parametrize("B,T", [(21, 300), (50, 2000), (70, 130), (200, 260)])
+def test_tensor_core_forward_agrees_with_the_fp32_kernels(lib, monkeypatch, B, T):
+    """The default training forward of the reference geometry runs projection + recurrence on the tcgen05 kernels
+    (hssb_lstm_train_forward_tc: split-fp16 operands, fp32 accumulation, approximate exp2 / reciprocal); HSSB_TRAIN_IMPL=stream
+    is the plain fp32 path.  Shapes: the reference's training shape (50 x 2000, main.py:130) and batches that use 1, 2 and 3
+    sub-tiles per cluster with ragged last groups.
+
+    (a) Per layer, everything the forward hands to back-propagation -- activated gates, cell states, raw h, final states -- within
+        2e-5 of the fp32 kernels' (values in [-1, 1], cells a few units).  The backward kernels are shared, so this is the whole
+        difference between the two paths.
+    (b) The full step (dropout off, so that (a)'s tensors are the step's): loss within 1e-5 relative, log-probabilities within
+        5e-5; every gradient within 2e-4 of its tensor's max-abs when no ReLU input changes sign between the two forwards,
+        else within 1 % of its norm: of the ~10^7 ReLU inputs a handful lie within the 1e-6 the forwards differ by, their units
+        switch sides and each moves the gradient by one sample's worth (the count is printed)."""
+    from hss.model import _train
+
+    F = 44
+    g = torch.Generator().manual_seed(B)
+    x = (3.0 * torch.randn(B, T, F, generator=g)).cuda()
+    y = torch.randint(0, 4, (B, T), generator=g).cuda()
+    m = make_model(13, F, B, 240).cuda().train()
+    h0, c0 = m.h0.cuda().float(), m.c0.cuda().float()
+    captured = {}
+    real_save = torch.autograd.function.FunctionCtx.save_for_backward
+
+    def layer_outputs(packed):
+        outs = []
+        with torch.no_grad():
+            inp, h, c = x, h0, c0
+            for li, lstm in enumerate((m.lstm_1, m.lstm_2)):
+                ctx = type("Ctx", (), {"save_for_backward": lambda self, *t: captured.__setitem__("saved", t)})()
+                args = [getattr(lstm, f"{k}_l0{sfx}") for sfx in ("", "_reverse") for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                out, hn, cn = _train.BiLSTMLayerFunction.forward(ctx, inp, h, c, *args, None if packed is None else packed[li])
+                gates, cells = captured["saved"][7], captured["saved"][8]
+                outs.append((gates.clone(), cells.clone(), out.clone(), hn.clone(), cn.clone()))
+                inp, h, c = torch.relu(out), hn, cn
+        return outs
+
+    monkeypatch.setenv("HSSB_TRAIN_IMPL", "tc")
+    packed = _train._packed_layers(m, x.device)
+    assert packed[0] is not None
+    tc, ref = layer_outputs(packed), layer_outputs(None)
+    for li in range(2):
+        for name, a, b in zip(("gates", "cells", "out", "hn", "cn"), tc[li], ref[li]):
+            d = float((a - b).abs().max())
+            assert d < 2e-5, (li, name, d)
+    flips = sum(int(((tc[li][2] > 0) != (ref[li][2] > 0)).sum()) for li in range(2))
+
+    results = []
+    for impl in ("tc", "stream"):
+        monkeypatch.setenv("HSSB_TRAIN_IMPL", impl)
+        m = make_model(13, F, B, 240).cuda().train()
+        m.dropout.p = 0.0
+        loss, logp = m.training_loss(x, y)
+        loss.backward()
+        results.append((float(loss.detach()), logp.detach(), {n: p.grad.clone() for n, p in m.named_parameters()}))
+    (l_tc, logp_tc, g_tc), (l_ref, logp_ref, g_ref) = results
+    assert abs(l_tc - l_ref) < 1e-5 * abs(l_ref)
+    assert (logp_tc - logp_ref).abs().max() < 5e-5
+    worst = max(float((g_tc[n] - g_ref[n]).norm() / g_ref[n].norm()) for n in g_ref)
+    worst_max = max(rel_err(g_tc[n], g_ref[n]) for n in g_ref)
+    print(f"B={B} T={T}: loss {l_tc:.7f} vs {l_ref:.7f}, {flips} ReLU inputs of {2 * B * T * 480} change sign, "
+          f"gradient difference: {worst:.2e} of the tensor norm, {worst_max:.2e} of its max-abs")
+    assert worst_max < REL_TOL if flips == 0 else worst < 1e-2
+
+
+def test_repacked_weights_follow_the_optimizer(lib):
+    """hssb_model_update: after every optimiser step the tcgen05 operands are re-packed in place; the training forward and the
+    eval forward of the updated module agree with each other and the handle is reused, not recreated."""
+    B, T, F = 6, 150, 44
+    m = make_model(5, F, B, 240).cuda().train()
+    m.dropout.p = 0.0
+    from hss.optim import ClipAdam
+
+    opt = ClipAdam(m.parameters(), lr=0.01, max_norm=1.0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, F, generator=g).cuda()
+    y = torch.randint(0, 4, (B, T), generator=g).cuda()
+    handles = set()
+    for _ in range(3):
+        opt.zero_grad()
+        loss, logp = m.training_loss(x, y)
+        handles.add(m._handle.value)
+        loss.backward()
+        opt.step()
+        m.eval()
+        with torch.no_grad():
+            after = m(x)
+        m.train()
+        _, logp_after = m.training_loss(x, y)
+        assert (after - logp_after).abs().max() < 2e-5
+        assert (after - logp).abs().max() > 1e-4          # the step changed the outputs
+    assert len(handles) == 1
 
 
 def test_fused_head_loss_and_clip_adam_match_the_eager_ops(lib):
