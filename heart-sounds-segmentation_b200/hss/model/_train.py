@@ -86,6 +86,7 @@ class BiLSTMLayerFunction(torch.autograd.Function):
                                                  B, T, H, out.data_ptr(), cells.data_ptr(), hn.data_ptr(), cn.data_ptr(), _lib.stream_ptr())
             _lib.check(rc, "hssb_lstm_train_forward")
         ctx.save_for_backward(x, h0, c0, w_ih, w_hh, w_ih_r, w_hh_r, gates, cells, out)
+        ctx.tensor_cores = packed is not None
         return out, hn, cn
 
     @staticmethod
@@ -101,12 +102,23 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         dG = gates.clone()                       # the kernel turns activations into dG in place; keep the saved tensor intact
         dh0 = torch.empty_like(h0)
         dc0 = torch.empty_like(c0)
+        import os
+
+        lib = _lib.lib()
+        p_hn = d_hn.data_ptr() if d_hn is not None else None
+        p_cn = d_cn.data_ptr() if d_cn is not None else None
         with torch.cuda.device(dev):
-            rc = _lib.lib().hssb_lstm_train_backward(dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(),
-                                                     d_out.data_ptr(), d_hn.data_ptr() if d_hn is not None else None,
-                                                     d_cn.data_ptr() if d_cn is not None else None, B, T, H,
-                                                     dh0.data_ptr(), dc0.data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "hssb_lstm_train_backward")
+            if ctx.tensor_cores and B * T and os.environ.get("HSSB_TRAIN_BWD", "tc") == "tc":
+                # the forward ran on the tcgen05 kernels (reference geometry, weights in the fp16-split range): so does this
+                ws = torch.empty(lib.hssb_lstm_train_backward_tc_workspace_bytes(), dtype=torch.uint8, device=dev)
+                rc = lib.hssb_lstm_train_backward_tc(dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(),
+                                                     d_out.data_ptr(), p_hn, p_cn, B, T, dh0.data_ptr(), dc0.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+                _lib.check(rc, "hssb_lstm_train_backward_tc")
+            else:
+                rc = lib.hssb_lstm_train_backward(dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(),
+                                                  d_out.data_ptr(), p_hn, p_cn, B, T, H, dh0.data_ptr(), dc0.data_ptr(), _lib.stream_ptr())
+                _lib.check(rc, "hssb_lstm_train_backward")
         x2 = x.reshape(B * T, Fin)
         # h_{prev}: forward direction = out[:, t-1, :H] (h0 at t = 0); reverse direction = out[:, t+1, H:] (h0 at t = T-1)
         hp_f = torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(B * T, H)

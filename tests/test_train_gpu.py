@@ -240,6 +240,52 @@ def test_tf32_split_gemms_match_fp32(lib, monkeypatch):
     assert worst < 2e-5
 
 
+@pytest.mark.parametrize("B,T,nb", [(5, 40, 0), (21, 300, 0), (21, 300, 16), (21, 300, 32), (50, 500, 0), (70, 130, 0), (130, 90, 0), (300, 33, 0)])
+def test_tensor_core_backward_agrees_with_the_fp32_kernel(lib, monkeypatch, B, T, nb):
+    """Back-propagation through time on the tcgen05 kernel (hssb_lstm_train_backward_tc; the default after a tensor-core forward)
+    against the fp32 cluster kernel (HSSB_TRAIN_BWD=cluster) on the SAME forward: every parameter gradient and the input
+    gradient within 2e-5 of the tensor's max-abs (the recurrent product runs on split-fp16 operands scaled from max|d_out|).
+    Batches cover 8 / 16 / 32 columns per cluster (forced or chosen), ragged last groups and more groups than one wave."""
+    F = 44
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, F, generator=g).cuda()
+    y = torch.randint(0, 4, (B, T), generator=g).cuda()
+    if nb:
+        monkeypatch.setenv("HSSB_BPTT_NB", str(nb))
+    results = []
+    for impl in ("tc", "cluster"):
+        monkeypatch.setenv("HSSB_TRAIN_BWD", impl)
+        m = make_model(19, F, B, 240).cuda().train()
+        m.dropout.p = 0.0
+        xg = x.clone().requires_grad_(True)
+        loss, _ = m.training_loss(xg, y)
+        loss.backward()
+        results.append(({n: p.grad.clone() for n, p in m.named_parameters()}, xg.grad.clone()))
+    worst = max(rel_err(results[0][0][n], results[1][0][n]) for n in results[1][0])
+    worst = max(worst, rel_err(results[0][1], results[1][1]))
+    print(f"B={B} T={T} nb={nb or 'auto'}: worst relative gradient difference, tensor-core vs fp32 backward: {worst:.2e}")
+    assert worst < 2e-5
+
+
+def test_tensor_core_backward_keeps_tiny_and_huge_gradients(lib, monkeypatch):
+    """The power-of-two scale follows max|d_out|: the same step with the loss multiplied by 1e-20 and by 1e+20 gives gradients
+    scaled by exactly those factors (within the fp32 rounding of the factor itself)."""
+    B, T, F = 9, 64, 44
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, T, F, generator=g).cuda()
+    y = torch.randint(0, 4, (B, T), generator=g).cuda()
+    grads = []
+    for factor in (1.0, 1e-20, 1e20):
+        m = make_model(23, F, B, 240).cuda().train()
+        m.dropout.p = 0.0
+        loss, _ = m.training_loss(x, y)
+        (loss * factor).backward()
+        grads.append({n: p.grad.double() / factor for n, p in m.named_parameters()})
+    for other in grads[1:]:
+        for n in grads[0]:
+            assert rel_err(other[n], grads[0][n]) < 1e-5, n
+
+
 def test_repacked_weights_follow_the_optimizer(lib):
     """hssb_model_update: after every optimiser step the tcgen05 operands are re-packed in place; the training forward and the
     eval forward of the updated module agree with each other and the handle is reused, not recreated."""
