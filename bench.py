@@ -301,7 +301,29 @@ def side_configs(dev, flush, peaks, _lib) -> dict:
     m3 = HeartSoundSegmenter(input_size=2 * KT, batch_size=B3).eval()
     ms = timed(lambda: m3.forward_with_labels(fsst.batch(x3)), 5, 2, flush)
     out["config3_batch50"] = {"workload": f"FSST + BiLSTM, batch {B3} x {N_SAMPLES} samples", "ms": ms, "samples_per_s": B3 * N_SAMPLES / (ms * 1e-3)}
-    del m3, x3
+    del m3
+    # ---- config 3, training: one optimisation step (forward in training mode, loss, backward, clip + Adam) at batch 50 ----
+    from hss.optim import ClipAdam
+
+    torch.manual_seed(68)
+    mt = HeartSoundSegmenter(input_size=2 * KT, batch_size=B3).to(dev).train()
+    opt = ClipAdam(mt.parameters(), lr=0.01, max_norm=1.0)
+    feats = fsst.batch(x3)
+    y3 = torch.from_numpy(synthetic_targets(B3)).to(dev)
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        loss, _ = mt.training_loss(feats, y3)
+        loss.backward()
+        opt.step()
+
+    ms = timed(train_step, 5, 3, flush)
+    out["config3_training_step"] = {
+        "workload": f"training step (main.py:67-82, 130-135): batch {B3} x {N_SAMPLES} samples, dropout 0.2, CE loss, clip 1.0 + Adam",
+        "ms": ms, "samples_per_s": B3 * N_SAMPLES / (ms * 1e-3),
+        "kernels": "projection + recurrences forward (K4, K5m TRAIN) and back-propagation through time (K5b) on tcgen05; weight / input "
+                   "gradient GEMMs as 3 x TF32 library GEMMs on split operands; fused head + loss and clip + Adam kernels"}
+    del mt, opt, feats, y3, x3
     # ---- config 5 shard: 64 windows x 120 000 samples @ 2 kHz ----
     B5, N5, fs5 = 64, 120_000, 2000.0
     f5 = FSST(fs5, window=reference_window(NWIN), truncate_freq=(50, 400), stack=True)
@@ -571,6 +593,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "d2h_bytes_per_step": int(lab_slots[0].numel() * 4 + 18 * 8), "pipeline": "double buffered: results of step i-1 read on the host while step i runs"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel, "fsst": fsst_rec, "cpu_baseline": cpu,
             "configs": configs,
+            "train_step_ms": configs["config3_training_step"]["ms"] if configs else None,
             "metrics_of_timed_steps": {"count": final_metrics["count"], "loss": final_metrics["loss"], "micro_accuracy": final_metrics["micro_accuracy"]},
             "config4_confusion": {"windows": CONFIG4_WINDOWS if cm16 and sum(cm16) else 0, "cm": cm16, "loss_sum": float(cfg4_host[16]),
                                   "crc32": zlib.crc32(",".join(map(str, cm16)).encode()),
