@@ -14,7 +14,8 @@
 //      CTA's own gate rows
 //   4. drains the accumulator: TMEM lane quadrant q of tile j holds exactly the 32 slots of peer 4j + q, so each of the eight
 //      epilogue warps stages one [column][32 units] block and sends it with ONE bulk copy (shared::cta -> shared::cluster,
-//      complete_tx on the receiver's mbarrier): NB x 128 bytes per peer and step.
+//      complete_tx on the receiver's mbarrier): NB x 128 bytes per peer and step.  (The block for the CTA itself is stored
+//      straight into its receive buffer; a named barrier of the eight epilogue warps after the drain orders it.)
 // Hazards (no explicit "buffer free" signalling is needed): a peer can send step k+2 only after it received step k+1 from every
 // CTA, i.e. after all eight of my warps finished the math of step k+1 -- which read the receive buffer of step k (the one k+2
 // overwrites), drained the accumulator of step k and, one step earlier still, had their staged block of step k delivered.
@@ -52,7 +53,11 @@ struct BpCfg {
     static constexpr int RECV_BYTES = 2 * RC_CL * BLOCK;       // [parity][source rank]
     static constexpr int STAGE_BYTES = 2 * RC_CL * BLOCK;      // [parity][epilogue warp]
     static constexpr int BAR_BYTES = 128;
-    static constexpr int SMEM_BYTES = RECV_BYTES + STAGE_BYTES + B_BYTES + BAR_BYTES + 1024;
+    static constexpr int USED_BYTES = RECV_BYTES + STAGE_BYTES + B_BYTES + BAR_BYTES + 1024;
+    // Every CTA allocates all 512 TMEM columns of its SM for the whole launch: a second CTA on the same SM would block in
+    // tcgen05.alloc until the first one exits, and two clusters that hold each other's SMs that way never finish.  Asking for more
+    // than half of the SM's shared memory keeps it to one CTA per SM (the larger kernels K4 / K5m get that from their real needs).
+    static constexpr int SMEM_BYTES = USED_BYTES > 118 * 1024 ? USED_BYTES : 118 * 1024;
     static constexpr int THREADS = 32 + 8 * 32;                // issuer warp + 8 epilogue warps (two per TMEM lane quadrant: one per M tile)
     static_assert(NB == 8 || NB == 16 || NB == 32, "batch columns per cluster");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -87,7 +92,7 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
     const int Ti = (int)T;
 
     if (threadIdx.x == 0) {
-        mbar_init(&r_full[0], 1);
+        mbar_init(&r_full[0], 1);        // armed with the bytes of the seven peer blocks (my own block does not travel)
         mbar_init(&r_full[1], 1);
         mbar_init(b_full, 8);
         mbar_init(d_full, 1);
@@ -125,14 +130,14 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
     if (warp == 0) {
         // ================= MMA issuer (one elected thread); also arms the receive barriers =================
         if (elect_one()) {
-            mbar_arrive_expect_tx(&r_full[0], RC_CL * C::BLOCK);
-            if (Ti > 1) mbar_arrive_expect_tx(&r_full[1], RC_CL * C::BLOCK);
+            mbar_arrive_expect_tx(&r_full[0], (RC_CL - 1) * C::BLOCK);
+            if (Ti > 1) mbar_arrive_expect_tx(&r_full[1], (RC_CL - 1) * C::BLOCK);
             constexpr uint32_t idesc = make_idesc_f16(128, C::MMA_N);
             const uint32_t bb = smem_u32(bop);
             for (int k = 0; k < Ti; ++k) {
                 mbar_wait(b_full, (uint32_t)(k & 1));
                 // all eight warps have consumed the blocks of step k-1: their barrier is in its next phase, which step k+1 will complete
-                if (k >= 1 && k + 1 < Ti) mbar_arrive_expect_tx(&r_full[(k + 1) & 1], RC_CL * C::BLOCK);
+                if (k >= 1 && k + 1 < Ti) mbar_arrive_expect_tx(&r_full[(k + 1) & 1], (RC_CL - 1) * C::BLOCK);
                 tc_fence_after();
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -275,13 +280,21 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
             tmem_ld_cols(taddr, v);
             tmem_ld_wait();
             tc_fence_before();
-            float *sb = stage + ((size_t)(k & 1) * RC_CL + w8) * (C::BLOCK / 4);
+            float *mine = recv + ((size_t)(k & 1) * RC_CL + rank) * (C::BLOCK / 4);      // slot `rank` of a receive buffer
+            if (dest == rank) {
+                // my own block: straight into my receive buffer (a shared::cta -> shared::cluster bulk copy must target ANOTHER CTA);
+                // the block barrier below orders it against the other warps' reads of this buffer one step earlier and one step later
 #pragma unroll
-            for (int c = 0; c < NB; ++c) sb[c * 32 + lane] = __uint_as_float(v[c]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (elect_one())
-                bulk_copy_to_cta(recv + ((size_t)(k & 1) * RC_CL + rank) * (C::BLOCK / 4), sb, C::BLOCK, &r_full[k & 1], dest);
+                for (int c = 0; c < NB; ++c) mine[c * 32 + lane] = __uint_as_float(v[c]);
+            } else {
+                float *sb = stage + ((size_t)(k & 1) * RC_CL + w8) * (C::BLOCK / 4);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) sb[c * 32 + lane] = __uint_as_float(v[c]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one()) bulk_copy_to_cta(mine, sb, C::BLOCK, &r_full[k & 1], dest);
+            }
+            named_barrier(1, 8 * 32);        // the eight epilogue warps: all arrive within the drain of the same accumulator
         }
         reduce(Ti - 1);
 #pragma unroll

@@ -39,7 +39,8 @@ struct RcCfg {
     static constexpr int IMG_BYTES = NB * 32 * 2 * 2;           // this CTA's h_t of all NB columns ([half] x slot layout)
     static constexpr int PER_SUB = 2 * HBUF_BYTES + 2 * IMG_BYTES;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = S * PER_SUB + BAR_BYTES + 1024;
+    static constexpr int USED_BYTES = S * PER_SUB + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = USED_BYTES > 118 * 1024 ? USED_BYTES : 118 * 1024;     // one CTA per SM: each holds all of the SM's TMEM (see K5m)
     static constexpr int THREADS = 32 * S + 128 * S;         // S MMA-issuer warps + S epilogue groups of 4 warps
     static_assert(NB % 16 == 0 && NB <= 64, "NB must be 16, 32, 48 or 64");
     static_assert(S * NB <= 256, "accumulators must fit in the TMEM columns left of the weights");
@@ -341,7 +342,8 @@ struct RpCfg {
     static constexpr int PER_SUB = 2 * RP_HBUF + 4 * RP_SLICE;       // 2 B buffers + images [parity][half]
     static constexpr int OUT_BYTES = S * 8 * 1024;                   // per epilogue warp: relu(h) tile for the TMA store
     static constexpr int BAR_BYTES = 512;
-    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + BAR_BYTES + 1024;
+    static constexpr int USED_BYTES = S * PER_SUB + OUT_BYTES + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = USED_BYTES > 118 * 1024 ? USED_BYTES : 118 * 1024;     // one CTA per SM: each holds all of the SM's TMEM (see K5m)
     static constexpr int THREADS = 32 * S + 256 * S;                 // S issuer / relay warps + S x 8 epilogue warps
     static_assert(S * RP_NB <= 256, "accumulators must fit in the TMEM columns left of the weights");
     static_assert((4 * S * RP_G + S) * 8 + 8 <= BAR_BYTES, "barrier area too small");

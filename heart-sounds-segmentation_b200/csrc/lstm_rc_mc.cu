@@ -48,7 +48,11 @@ struct RmCfg {
     static constexpr int OUT_BYTES = FUSE_X ? 0 : S * 4 * EW * TILE_BYTES;
     static constexpr int X_BYTES = FUSE_X ? S * 2 * RX_PLANE : 0;
     static constexpr int BAR_BYTES = 512;
-    static constexpr int SMEM_BYTES = S * PER_SUB + OUT_BYTES + X_BYTES + BAR_BYTES + 1024;
+    static constexpr int USED_BYTES = S * PER_SUB + OUT_BYTES + X_BYTES + BAR_BYTES + 1024;
+    // One CTA per SM, always: every CTA holds all 512 TMEM columns of its SM for the whole launch, so a second CTA on the same SM
+    // would block in tcgen05.alloc until the first exits -- and two clusters holding each other's SMs that way never finish.  With
+    // S = 1 the real need (~78 KB) would let two CTAs share an SM; asking for more than half of the SM's shared memory forbids it.
+    static constexpr int SMEM_BYTES = USED_BYTES > 118 * 1024 ? USED_BYTES : 118 * 1024;
     static constexpr int THREADS = 32 * S + 128 * S * EW;            // S issuer warps + S x 4 x EW epilogue warps
     static_assert(EW == 1 || EW == 2, "one or two epilogue warps per TMEM lane quadrant and sub-tile");
     static_assert(S * RP_NBH <= 96, "accumulators sit in TMEM columns [256, 352)");

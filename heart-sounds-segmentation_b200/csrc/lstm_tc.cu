@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         publish_pending();
     } else {
         // ===== item scheduler (cluster rank 0): the next item of the launch -> every CTA's ring =====
-        // Fully asynchronous broadcast: the item goes into a staging slot, then per CTA one remote arrive.expect_tx arms its
+        // Fully asynchronous broadcast: the item goes into a staging slot, then per PEER one remote arrive.expect_tx arms its
         // item_full barrier and one 16-byte bulk copy (shared -> shared::cluster, complete_tx on that barrier) delivers the slot.
         // Nothing here waits for a round trip (release-arrives behind remote stores cost one per CTA: about as long as a tile
         // takes); the next item is fetched from the global counter right after the previous one was posted.
@@ -478,10 +478,13 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
                 *reinterpret_cast<volatile int *>(&item_src[slot].x) = item;        // (the copies of the previous use of this staging slot completed
                 fence_proxy_async_smem();                                            //  before its consumers could read, i.e. before item_empty)
 #pragma unroll
-                for (int r = 0; r < CL; ++r) {
+                for (int r = 1; r < CL; ++r) {
                     mbar_arrive_expect_tx_remote(&item_full[slot], 16, r);
                     bulk_copy_to_cta(&item_ring[slot], &item_src[slot], 16, &item_full[slot], r);
                 }
+                // my own ring: a shared::cta -> shared::cluster bulk copy must target ANOTHER CTA -- plain store + arrive (release)
+                *reinterpret_cast<volatile int *>(&item_ring[slot].x) = item;
+                mbar_arrive(&item_full[slot]);
                 if (item >= n_items) break;
                 item = (int)atomicAdd(p.next_item, 1u);
             }

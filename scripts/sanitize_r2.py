@@ -37,14 +37,25 @@ if "overlap" in what:
     logp, labels = m.forward_with_labels(torch.randn(B, T, 44, device="cuda"))
     torch.cuda.synchronize()
     print("overlap", B, T, float(logp.exp().sum(-1).mean()), int(labels.sum()))
-if "train" in what:
-    B, T = 9, 20
-    torch.manual_seed(3)
-    m = HeartSoundSegmenter(input_size=44, batch_size=B).cuda().train()
-    m.h0, m.c0 = m.h0.cuda(), m.c0.cuda()
-    x = torch.randn(B, T, 44, device="cuda")
-    y = torch.randint(0, 4, (B, T), device="cuda")
-    loss = torch.nn.functional.cross_entropy(m(x).permute(0, 2, 1), y)
-    loss.backward()
-    torch.cuda.synchronize()
-    print("train", float(loss))
+if "train" in what or "train_simt" in what:
+    # "train": the default tensor-core path (K4 + K5m TRAIN forward, K5b backward with 8 / 16 columns per cluster, TF32-split
+    # GEMM operands, fused head + loss, clip + Adam); "train_simt": the fp32 cluster kernels (HSSB_TRAIN_IMPL=cluster)
+    from hss.optim import ClipAdam
+
+    if "train_simt" in what:
+        os.environ["HSSB_TRAIN_IMPL"] = "cluster"
+    # SAN_TRAIN_SHAPES="9x20,70x12": racecheck needs minutes per shape on the spinning cluster kernels
+    shapes = [tuple(int(v) for v in s_.split("x")) for s_ in os.environ.get("SAN_TRAIN_SHAPES", "9x20,70x12").split(",")]
+    for B, T in shapes:
+        torch.manual_seed(3)
+        m = HeartSoundSegmenter(input_size=44, batch_size=B).cuda().train()
+        opt = ClipAdam(m.parameters(), lr=0.01, max_norm=1.0)
+        x = torch.randn(B, T, 44, device="cuda")
+        y = torch.randint(0, 4, (B, T), device="cuda")
+        for _ in range(2):
+            opt.zero_grad()
+            loss, _ = m.training_loss(x, y)
+            loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        print("train", os.environ.get("HSSB_TRAIN_IMPL", "tc"), B, T, float(loss))
