@@ -470,23 +470,39 @@ __global__ void __launch_bounds__(IpCfg<IP_STAGES, EPI_WARPS, CM, CN>::THREADS, 
         // item_full barrier and one 16-byte bulk copy (shared -> shared::cluster, complete_tx on that barrier) delivers the slot.
         // Nothing here waits for a round trip (release-arrives behind remote stores cost one per CTA: about as long as a tile
         // takes); the next item is fetched from the global counter right after the previous one was posted.
+        // A shared::cta -> shared::cluster bulk copy must target ANOTHER CTA, so rank 0's own ring is filled by rank 1's scheduler
+        // warp, which forwards every slot it receives (one more hop, hidden by the ring depth); a single-CTA "cluster" has no peer
+        // and takes the item with a plain store + arrive.
         if (rank == 0 && elect_one()) {
             int item = (int)atomicAdd(p.next_item, 1u);
             for (uint32_t it = 0;; ++it) {
                 const int slot = it % IP_RING;
                 mbar_wait_cluster(&item_empty[slot], ((it / IP_RING) & 1) ^ 1);      // every consumer of the cluster has read the slot's previous item
-                *reinterpret_cast<volatile int *>(&item_src[slot].x) = item;        // (the copies of the previous use of this staging slot completed
-                fence_proxy_async_smem();                                            //  before its consumers could read, i.e. before item_empty)
+                if (CL > 1) {
+                    *reinterpret_cast<volatile int *>(&item_src[slot].x) = item;    // (the copies of the previous use of this staging slot completed
+                    fence_proxy_async_smem();                                        //  before its consumers could read, i.e. before item_empty)
+                    mbar_arrive_expect_tx(&item_full[slot], 16);                     // my own slot: the bytes come back from rank 1
 #pragma unroll
-                for (int r = 1; r < CL; ++r) {
-                    mbar_arrive_expect_tx_remote(&item_full[slot], 16, r);
-                    bulk_copy_to_cta(&item_ring[slot], &item_src[slot], 16, &item_full[slot], r);
+                    for (int r = 1; r < CL; ++r) {
+                        mbar_arrive_expect_tx_remote(&item_full[slot], 16, r);
+                        bulk_copy_to_cta(&item_ring[slot], &item_src[slot], 16, &item_full[slot], r);
+                    }
+                } else {
+                    *reinterpret_cast<volatile int *>(&item_ring[slot].x) = item;
+                    mbar_arrive(&item_full[slot]);
                 }
-                // my own ring: a shared::cta -> shared::cluster bulk copy must target ANOTHER CTA -- plain store + arrive (release)
-                *reinterpret_cast<volatile int *>(&item_ring[slot].x) = item;
-                mbar_arrive(&item_full[slot]);
                 if (item >= n_items) break;
                 item = (int)atomicAdd(p.next_item, 1u);
+            }
+        } else if (CL > 1 && rank == 1 && elect_one()) {
+            // relay: my ring slot (filled through the async proxy, so no fence) -> the same slot of rank 0.  The slot is not
+            // reposted before rank 0's consumers have handed it back, i.e. not before this copy has been read and delivered.
+            for (uint32_t it = 0;; ++it) {
+                const int slot = it % IP_RING;
+                mbar_wait_cluster(&item_full[slot], (it / IP_RING) & 1);
+                const int item = *reinterpret_cast<volatile int *>(&item_ring[slot].x);
+                bulk_copy_to_cta(&item_ring[slot], &item_ring[slot], 16, &item_full[slot], 0);
+                if (item >= n_items) break;
             }
         }
     }
