@@ -30,7 +30,8 @@
 namespace hssb {
 
 struct BpttParams {
-    float *gates;            // [2][B*T][960]  in: activated gates i, f, g, o; out: dG
+    const float *gates;      // [2][B*T][960]  activated gates i, f, g, o of the forward
+    float *dg;               // [2][B*T][960]  out: dG (may alias gates: a cell's gates are in registers before its dG is written)
     const float *cells;      // [2][B*T][240]
     const float *c0;         // [2][B][240]
     const float *d_out;      // [B][T][480]
@@ -183,7 +184,8 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
             return e < -100 ? -100 : (e > 100 ? 100 : e);
         }();
         const float s_up = pow2f(e_up), s_dn = pow2f(-e_up);
-        float *gd = p.gates + (size_t)dir * B * T * TC_G + U;
+        const float *gd = p.gates + (size_t)dir * B * T * TC_G + U;
+        float *dgd = p.dg + (size_t)dir * B * T * TC_G + U;
         const float *cd = p.cells + (size_t)dir * B * T * TC_H + U;
         const float *dd = p.d_out + dir * TC_H + U;
 
@@ -267,7 +269,7 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 if (ok[i]) {
-                    float *g = gd + (cellbase[i] + t) * TC_G;
+                    float *g = dgd + (cellbase[i] + t) * TC_G;
                     __stcs(g, da[i][0]); __stcs(g + TC_H, da[i][1]); __stcs(g + 2 * TC_H, da[i][2]); __stcs(g + 3 * TC_H, da[i][3]);
                 }
                 c_cur[i] = cprev[i];
@@ -389,7 +391,7 @@ int bptt_tc_prepare()
     return bptt_prepare<32>(&n);
 }
 
-int bptt_tc_backward(float *gates, const float *cells, const float *w_fwd, const float *w_rev, const float *c0, const float *d_out,
+int bptt_tc_backward(const float *gates, float *dg, const float *cells, const float *w_fwd, const float *w_rev, const float *c0, const float *d_out,
                      const float *d_hn, const float *d_cn, int64_t B, int64_t T, float *dh0, float *dc0, void *ws, size_t ws_bytes,
                      cudaStream_t st)
 {
@@ -412,7 +414,7 @@ int bptt_tc_backward(float *gates, const float *cells, const float *w_fwd, const
     int force_nb = 0;
     if (const char *e = getenv("HSSB_BPTT_NB")) force_nb = atoi(e);
     BpttParams prm = {};
-    prm.gates = gates; prm.cells = cells; prm.c0 = c0; prm.d_out = d_out; prm.d_hn = d_hn; prm.d_cn = d_cn;
+    prm.gates = gates; prm.dg = dg; prm.cells = cells; prm.c0 = c0; prm.d_out = d_out; prm.d_hn = d_hn; prm.d_cn = d_cn;
     prm.dh0 = dh0; prm.dc0 = dc0; prm.whhT = whhT; prm.range = range; prm.B = B; prm.T = T;
     for (long long base = 0; base < B;) {
         const long long rem = B - base;

@@ -99,7 +99,6 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         d_out = torch.zeros_like(out) if d_out is None else d_out.to(torch.float32).contiguous()
         d_hn = None if d_hn is None else d_hn.to(torch.float32).contiguous()
         d_cn = None if d_cn is None else d_cn.to(torch.float32).contiguous()
-        dG = gates.clone()                       # the kernel turns activations into dG in place; keep the saved tensor intact
         dh0 = torch.empty_like(h0)
         dc0 = torch.empty_like(c0)
         import os
@@ -109,42 +108,62 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         p_cn = d_cn.data_ptr() if d_cn is not None else None
         with torch.cuda.device(dev):
             if ctx.tensor_cores and B * T and os.environ.get("HSSB_TRAIN_BWD", "tc") == "tc":
-                # the forward ran on the tcgen05 kernels (reference geometry, weights in the fp16-split range): so does this
+                # the forward ran on the tcgen05 kernels (reference geometry, weights in the fp16-split range): so does this;
+                # dG goes to its own buffer, the saved activations stay intact
+                dG = torch.empty_like(gates)
                 ws = torch.empty(lib.hssb_lstm_train_backward_tc_workspace_bytes(), dtype=torch.uint8, device=dev)
-                rc = lib.hssb_lstm_train_backward_tc(dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(),
-                                                     d_out.data_ptr(), p_hn, p_cn, B, T, dh0.data_ptr(), dc0.data_ptr(),
+                rc = lib.hssb_lstm_train_backward_tc(gates.data_ptr(), dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(),
+                                                     c0.data_ptr(), d_out.data_ptr(), p_hn, p_cn, B, T, dh0.data_ptr(), dc0.data_ptr(),
                                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr())
                 _lib.check(rc, "hssb_lstm_train_backward_tc")
             else:
+                dG = gates.clone()               # this kernel turns activations into dG in place; keep the saved tensor intact
                 rc = lib.hssb_lstm_train_backward(dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(),
                                                   d_out.data_ptr(), p_hn, p_cn, B, T, H, dh0.data_ptr(), dc0.data_ptr(), _lib.stream_ptr())
                 _lib.check(rc, "hssb_lstm_train_backward")
-        x2 = x.reshape(B * T, Fin)
-        # h_{prev}: forward direction = out[:, t-1, :H] (h0 at t = 0); reverse direction = out[:, t+1, H:] (h0 at t = T-1)
-        hp_f = torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(B * T, H)
-        hp_r = torch.cat([out[:, 1:, H:], h0[1].unsqueeze(1)], dim=1).reshape(B * T, H)
+        M = B * T
+        x2 = x.reshape(M, Fin)
         grads = []
-        import os
-
-        if os.environ.get("HSSB_TRAIN_GEMM", "tf32x3") == "fp32" or B * T == 0:
+        if os.environ.get("HSSB_TRAIN_GEMM", "tf32x3") == "fp32" or M == 0:
             # the mm kernels autograd itself would run for nn.LSTM (SIMT fp32)
+            # h_{prev}: forward direction = out[:, t-1, :H] (h0 at t = 0); reverse direction = out[:, t+1, H:] (h0 at t = T-1)
+            hp_f = torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(M, H)
+            hp_r = torch.cat([out[:, 1:, H:], h0[1].unsqueeze(1)], dim=1).reshape(M, H)
             for d, hp in enumerate((hp_f, hp_r)):
                 g = dG[d]
                 db = g.sum(dim=0)
                 grads.append((g.t() @ x2, g.t() @ hp, db, db.clone()))
             dx = (dG[0] @ w_ih + dG[1] @ w_ih_r).reshape(B, T, Fin) if ctx.needs_input_grad[0] else None
         else:
-            # the same products as three TF32 tensor-core GEMMs each: hi.hi + hi.lo + lo.hi, fp32 accumulation (product error 2^-21)
+            # The same products as three TF32 tensor-core GEMMs each: hi.hi + hi.lo + lo.hi, fp32 accumulation (product error 2^-21).
+            # dG^T h_prev without materialising h_prev: in the flattened [B*T] row order h_prev of row r is row r - 1 of out[:, :H]
+            # (forward) / row r + 1 of out[:, H:] (reverse), i.e. one GEMM on views shifted by a row -- except at each window's first
+            # (last) step, where the partner is h0 instead of the neighbouring window's last (first) step: B rows, fixed up in fp32.
             g_hi, g_lo = _split_tf32(dG)
             xs = _split_tf32(x2)
+            o_hi, o_lo = (t.view(M, 2 * H) for t in _split_tf32(out))
+            o2 = out.view(M, 2 * H)
+            first = torch.arange(B, device=dev) * T          # rows of t = 0
+            last = first + (T - 1)                           # rows of t = T - 1
             dx = None
+            big = []
             with _Tf32Matmul():
-                for d, (wi, hp) in enumerate(((w_ih, hp_f), (w_ih_r, hp_r))):
+                for d, wi in enumerate((w_ih, w_ih_r)):
                     gt = (g_hi[d].t(), g_lo[d].t())
-                    db = dG[d].sum(dim=0)
-                    grads.append((_mm3(gt, xs), _mm3(gt, _split_tf32(hp)), db, db.clone()))
+                    if d == 0:
+                        dwh = _mm3((g_hi[0][1:].t(), g_lo[0][1:].t()), (o_hi[:-1, :H], o_lo[:-1, :H]))
+                    else:
+                        dwh = _mm3((g_hi[1][:-1].t(), g_lo[1][:-1].t()), (o_hi[1:, H:], o_lo[1:, H:]))
+                    big.append((_mm3(gt, xs), dwh))
                     if ctx.needs_input_grad[0]:
                         dx = _mm3((g_hi[d], g_lo[d]), _split_tf32(wi), out=dx)
+            # the B edge rows, in plain fp32 (outside the TF32 switch: with T = 1 they are the whole gradient)
+            edge_f, edge_r = dG[0][first], dG[1][last]
+            fix_f = edge_f.t() @ h0[0] - edge_f[1:].t() @ o2[first[1:] - 1, :H]
+            fix_r = edge_r.t() @ h0[1] - edge_r[:-1].t() @ o2[last[:-1] + 1, H:]
+            for d, fix in enumerate((fix_f, fix_r)):
+                db = dG[d].sum(dim=0)
+                grads.append((big[d][0], big[d][1] + fix, db, db.clone()))
             dx = dx.reshape(B, T, Fin) if dx is not None else None
         (dwi, dwh, dbi, dbh), (dwi_r, dwh_r, dbi_r, dbh_r) = grads
         return dx, dh0, dc0, dwi, dwh, dbi, dbh, dwi_r, dwh_r, dbi_r, dbh_r, None

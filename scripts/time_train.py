@@ -35,7 +35,7 @@ def step():
     return loss
 
 
-for _ in range(3):
+for _ in range(8):          # (the first asynchronous steps grow torch's allocator cache: one-off cudaMallocs of several GB)
     step()
 torch.cuda.synchronize()
 t0 = time.perf_counter()

@@ -64,6 +64,16 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.hssb_lstm_workspace_bytes(None, 1, 8) == 0
     assert lib.hssb_auroc_hist(p, p, 8, 5000, p, None) == -2                                 # nbins outside [2, 4096]
     assert lib.hssb_lstm_train_forward(None, p, p, p, p, 1, 8, 240, p, p, p, p, None) == -1
+    # tensor-core training entry points and the in-place re-pack: null handles / pointers, bad layer, bad shapes
+    assert lib.hssb_lstm_train_forward_tc(None, 0, p, 1, 8, p, p, p, p, p, p, p, None, 0, None) == -1
+    assert lib.hssb_lstm_train_backward_tc(None, p, p, p, p, p, p, None, None, 1, 8, p, p, None, 0, None) == -1
+    assert lib.hssb_lstm_train_backward_tc(p, p, p, p, p, p, p, None, None, -1, 8, p, p, None, 0, None) == -2
+    assert lib.hssb_lstm_train_backward_tc_workspace_bytes() >= 2 * 8 * 2 * 256 * 128 * 2
+    assert lib.hssb_model_update(None, None, None) == -1
+    assert lib.hssb_model_uses_tensor_cores(None) == 0
+    assert lib.hssb_split_tf32(p, -1, p, p, None) == -2
+    assert lib.hssb_split_tf32(p, 0, p, p, None) == 0
+    assert lib.hssb_split_tf32(None, 8, p, p, None) == -1
 
 
 def test_no_cuda_means_loud_failure(lib):
