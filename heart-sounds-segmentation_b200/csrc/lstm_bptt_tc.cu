@@ -189,10 +189,13 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
         const float *cd = p.cells + (size_t)dir * B * T * TC_H + U;
         const float *dd = p.d_out + dir * TC_H + U;
 
-        float gi[NC], gf[NC], gg[NC], go[NC], cprev[NC], dout[NC];     // saved forward values of the step about to be processed
+        // Saved forward values, loaded TWO steps ahead: a step (1.2 us) is not much longer than an HBM round trip, and the values of
+        // step k + 1 are needed at the very top of that step.  sv = the step being processed, nx = the one after it.
+        // [0..3] activated gates i, f, g, o; [4] c of the previous time step (c0 at the last one); [5] d_out
+        float sv[NC][6], nx[NC][6];
         float c_cur[NC], dc_carry[NC], dh_rec[NC];
         auto t_of = [&](int k) { return dir ? k : Ti - 1 - k; };
-        auto load_step = [&](int k) {
+        auto load_step = [&](int k, float (&dst)[NC][6]) {
             const int t = t_of(k);
             const int t_prev = dir ? t + 1 : t - 1;
 #pragma unroll
@@ -200,19 +203,21 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
                 if (!ok[i]) continue;
                 const size_t row = cellbase[i] + t;
                 const float *g = gd + row * TC_G;
-                gi[i] = __ldcs(g); gf[i] = __ldcs(g + TC_H); gg[i] = __ldcs(g + 2 * TC_H); go[i] = __ldcs(g + 3 * TC_H);
-                dout[i] = __ldcs(dd + row * (2 * TC_H));
-                cprev[i] = k + 1 < Ti ? __ldg(cd + (cellbase[i] + t_prev) * TC_H) : __ldg(p.c0 + stateo[i]);
+                dst[i][0] = __ldcs(g); dst[i][1] = __ldcs(g + TC_H); dst[i][2] = __ldcs(g + 2 * TC_H); dst[i][3] = __ldcs(g + 3 * TC_H);
+                dst[i][5] = __ldcs(dd + row * (2 * TC_H));
+                dst[i][4] = k + 1 < Ti ? __ldg(cd + (cellbase[i] + t_prev) * TC_H) : __ldg(p.c0 + stateo[i]);
             }
         };
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            gi[i] = gf[i] = gg[i] = go[i] = cprev[i] = dout[i] = 0.f;
+#pragma unroll
+            for (int v = 0; v < 6; ++v) sv[i][v] = nx[i][v] = 0.f;
             c_cur[i] = ok[i] ? __ldg(cd + (cellbase[i] + t_of(0)) * TC_H) : 0.f;
             dh_rec[i] = (ok[i] && p.d_hn) ? __ldg(p.d_hn + stateo[i]) : 0.f;
             dc_carry[i] = (ok[i] && p.d_cn) ? __ldg(p.d_cn + stateo[i]) : 0.f;
         }
-        load_step(0);
+        load_step(0, sv);
+        if (Ti > 1) load_step(1, nx);
         const uint32_t bop_thread = smem_u32(bop) + (u >> 3) * C::CH_STRIDE + (u & 7) * 2;     // + gate * 4 chunks + plane + column * 16
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + j * C::MMA_N;
 
@@ -235,22 +240,23 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
             float a1[NC], ko[NC], ki[NC], kf[NC], kg[NC];
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
+                const float gi = sv[i][0], gf = sv[i][1], gg = sv[i][2], go = sv[i][3];
                 const float tc = tanhf(c_cur[i]);
-                a1[i] = go[i] * (1.f - tc * tc);
-                ko[i] = tc * go[i] * (1.f - go[i]);
-                ki[i] = gg[i] * gi[i] * (1.f - gi[i]);
-                kf[i] = cprev[i] * gf[i] * (1.f - gf[i]);
-                kg[i] = gi[i] * (1.f - gg[i] * gg[i]);
+                a1[i] = go * (1.f - tc * tc);
+                ko[i] = tc * go * (1.f - go);
+                ki[i] = gg * gi * (1.f - gi);
+                kf[i] = sv[i][4] * gf * (1.f - gf);
+                kg[i] = gi * (1.f - gg * gg);
             }
             if (k > 0) reduce(k - 1);
             // ---- the dependent chain: dL/dh -> dG -> B operand ----
             float da[NC][4];
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
-                const float dh = dout[i] + dh_rec[i];
+                const float dh = sv[i][5] + dh_rec[i];
                 const float dc = fmaf(dh, a1[i], dc_carry[i]);
                 da[i][0] = dc * ki[i]; da[i][1] = dc * kf[i]; da[i][2] = dc * kg[i]; da[i][3] = dh * ko[i];
-                dc_carry[i] = dc * gf[i];
+                dc_carry[i] = dc * sv[i][1];
                 if (ok[i]) {
                     const uint32_t cell = bop_thread + (w8 + 8 * i) * 16;
 #pragma unroll
@@ -265,16 +271,21 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_full);
-            // ---- off the chain: dG to memory, the next step's saved values into registers ----
+            // ---- off the chain: rotate the saved values (step k + 1 arrived during this step), send the loads of step k + 2 on
+            //      their way BEFORE the stores (which wait on no scoreboard), then dG to memory ----
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
+                c_cur[i] = sv[i][4];
+#pragma unroll
+                for (int v = 0; v < 6; ++v) sv[i][v] = nx[i][v];
+            }
+            if (k + 2 < Ti) load_step(k + 2, nx);
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
                 if (ok[i]) {
                     float *g = dgd + (cellbase[i] + t) * TC_G;
                     __stcs(g, da[i][0]); __stcs(g + TC_H, da[i][1]); __stcs(g + 2 * TC_H, da[i][2]); __stcs(g + 3 * TC_H, da[i][3]);
                 }
-                c_cur[i] = cprev[i];
-            }
-            if (k + 1 < Ti) load_step(k + 1);
             // ---- partial dL/dh_prev of peer `dest`'s units: TMEM -> staging -> one bulk copy into its receive buffer ----
             mbar_wait(d_full, (uint32_t)(k & 1));
             tc_fence_after();

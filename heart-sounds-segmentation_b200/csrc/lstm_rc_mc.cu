@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
             int x_t = dir ? (int)T - 1 : 0, x_tile = -1;        // time index of the next xproj load and the time tile already waited for
             // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
             // wait of the warp (TMA issue, spill reloads, ...) would otherwise sit behind these HBM loads.
-            auto load_x = [&]() {
+            auto load_into = [&](float4 *dst) {
                 if (!FUSE_X && p.chunk_done && (x_t >> 7) != x_tile) {
                     // the projection GEMM runs concurrently: wait until this direction's chunk of the time tile is in memory
                     x_tile = x_t >> 7;
@@ -281,10 +281,11 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                 for (int i = 0; i < NI; ++i) {
                     const int c = col_of(i);
                     if (FUSE_X) continue;               // fused: xnext holds the (constant) biases of this unit's four gates
-                    xnext[i] = (c < ncols && !(knock & 1)) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dst[i] = (c < ncols && !(knock & 1)) ? __ldcs(reinterpret_cast<const float4 *>(xp_next + (size_t)c * TC_G)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 xp_next += xstep;
             };
+            auto load_x = [&]() { load_into(xnext); };
             if (FUSE_X) {
                 const float *bz = p.bias0 + ((size_t)dir * RC_CL + rank) * 128 + q * 32 + ul;      // rows 32q + 8*gate + ul
                 const float4 b4 = make_float4(__ldg(bz), __ldg(bz + 8), __ldg(bz + 16), __ldg(bz + 24));
@@ -426,6 +427,10 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                 }
                 if (t + 1 < Ti) publish(hv, t);
                 if (TRAIN) {
+                    // the next step's xproj loads go out FIRST: they have one step of exchange latency to come back, and the 24 stores
+                    // below would push them ~200 cycles later (the stores wait on no scoreboard, so the loads in flight cost them nothing).
+                    // Measured: 7.97 -> 7.03 ms for the two layers at 50 x 2000; loading two steps ahead gains nothing more (7.2 ms).
+                    if (t + 1 < Ti) load_x();
                     // ---- off the critical path: what back-propagation needs, straight to global memory (8 lanes = 8 consecutive units) ----
                     if (unit_ok) {
                         const int U = (int)rank * RC_U + u;
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                 }
                 t_idx += dir ? -1 : 1;
                 if (t + 1 < Ti) {
-                    load_x();
+                    if (!TRAIN) load_x();
                 } else if (unit_ok) {
 #pragma unroll
                     for (int i = 0; i < NI; ++i)

@@ -555,14 +555,14 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
     char *base = static_cast<char *>(dst);
     size_t off = 0;
     const int kin[2] = {m->F, 2 * TC_H};
-    // the raw torch tensors may be host pointers: stage them through a temporary device buffer
-    float *tmp = nullptr;
+    // the raw torch tensors may be host pointers: stage them through the model's staging buffer (hssb_model_create sized it for
+    // the largest tensor group + the two range words; no per-call allocation: this runs after every optimiser step in training)
     const size_t tmp_floats = (size_t)TC_G * (2 * TC_H) + 2 * TC_G;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&tmp), sizeof(float) * (tmp_floats + 2), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(tc_pack)");
+    float *tmp = m->stage;
+    cudaError_t e;
     // max |w| over the LSTM weights (word 1): outside the fp16-split range the model keeps to the generic fp32 kernels
     unsigned *w_range = reinterpret_cast<unsigned *>(tmp + tmp_floats);
-    if ((e = cudaMemsetAsync(w_range, 0, 8, st)) != cudaSuccess) { cudaFreeAsync(tmp, st); return cuda_fail(e, "cudaMemsetAsync(tc_pack)"); }
+    if ((e = cudaMemsetAsync(w_range, 0, 8, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tc_pack)");
     int rc = 0;
     m->tc_wih0_frag = reinterpret_cast<__half *>(base + off);
     off += align_up(sizeof(__half) * 2 * 8 * 2 * 128 * 64, 256);
@@ -614,7 +614,6 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
     unsigned w_bits[2] = {0, 0};
     if (!rc && ((e = cudaMemcpyAsync(w_bits, w_range, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess))
         rc = cuda_fail(e, "tc_pack: weight range");
-    cudaFreeAsync(tmp, st);
     if (rc) return rc;
     float w_max;
     memcpy(&w_max, &w_bits[1], 4);

@@ -132,7 +132,7 @@ extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, v
     const size_t o_stage = off;
     size_t stage_bytes = 0;
     for (int l = 0; l < 2; ++l) stage_bytes = std::max(stage_bytes, sizeof(float) * (kin[l] * G + H * G + 2 * G));
-    off += align_up(stage_bytes, 256);
+    off += align_up(stage_bytes + 64, 256);         // + the two weight-range words tc_pack keeps behind its staged tensor group
 
     hssb_model *m = new hssb_model();
     std::memset(m, 0, sizeof(*m));

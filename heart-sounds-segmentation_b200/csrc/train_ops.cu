@@ -133,8 +133,10 @@ __global__ void __launch_bounds__(256) ce_head_forward_kernel(const float *__res
 // then d_act = dz . W, dW += dz^T . act, db += sum dz.  grid-stride over rows; dW / db accumulate per block in shared memory.
 __global__ void __launch_bounds__(256) ce_head_backward_kernel(const float *__restrict__ act, const float *__restrict__ logp, long long M, int K,
                                                                 const float *__restrict__ w, const int64_t *__restrict__ target, float scale,
-                                                                float *__restrict__ d_act, float *__restrict__ d_w, float *__restrict__ d_b)
+                                                                const float *__restrict__ upstream, float *__restrict__ d_act,
+                                                                float *__restrict__ d_w, float *__restrict__ d_b)
 {
+    if (upstream) scale *= __ldg(upstream);             // dL/d(loss) left on the device: no host round trip in the backward pass
     extern __shared__ float sm[];                       // w_s [4][K], dw_s [4][K], db_s [4]
     float *w_s = sm, *dw_s = sm + 4 * K, *db_s = sm + 8 * K;
     for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) { w_s[i] = w[i]; dw_s[i] = 0.f; }
@@ -244,7 +246,7 @@ extern "C" int hssb_ce_head_forward(const float *act, int64_t M, int K, const fl
 }
 
 extern "C" int hssb_ce_head_backward(const float *act, const float *logp, int64_t M, int K, const float *w, const int64_t *target,
-                                     float scale, float *d_act, float *d_w, float *d_b, void *stream)
+                                     float scale, const float *upstream, float *d_act, float *d_w, float *d_b, void *stream)
 {
     if (!act || !logp || !w || !target || !d_act || !d_w || !d_b) return fail(HSSB_E_NULL, "hssb_ce_head_backward: null pointer");
     if (M < 0 || K < 1 || K > 512) return fail(HSSB_E_SHAPE, "hssb_ce_head_backward: M=%lld K=%d (K <= 512)", (long long)M, K);
@@ -253,7 +255,7 @@ extern "C" int hssb_ce_head_backward(const float *act, const float *logp, int64_
     cudaStream_t st = as_stream(stream);
     const int blocks = (int)std::min<long long>((M + 7) / 8, 148 * 2);
     ProfScope prof("ce_head_bwd", st);
-    ce_head_backward_kernel<<<blocks, 256, sizeof(float) * (8 * K + 4), st>>>(act, logp, M, K, w, target, scale, d_act, d_w, d_b);
+    ce_head_backward_kernel<<<blocks, 256, sizeof(float) * (8 * K + 4), st>>>(act, logp, M, K, w, target, scale, upstream, d_act, d_w, d_b);
     HSSB_LAUNCH_OK("ce_head_backward_kernel");
     return 0;
 }

@@ -59,7 +59,7 @@ _SIGNATURES = {
     "hssb_split_tf32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "hssb_lstm_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "hssb_ce_head_forward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "hssb_ce_head_backward": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hssb_ce_head_backward": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hssb_clip_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int64, c_float,
                                     c_void_p, c_void_p, c_void_p]),
     "hssb_confusion": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -240,10 +240,11 @@ class HeadLossFunction(torch.autograd.Function):
         d_act = torch.empty_like(act)
         d_w = torch.zeros_like(weight)
         d_b = torch.zeros(4, dtype=torch.float32, device=act.device)
-        scale = float(d_loss) / max(M, 1)
+        # dL/d(loss) stays on the device (a host read here would stall the enqueue of the whole backward pass behind the forward)
+        up = d_loss.detach().to(device=act.device, dtype=torch.float32).reshape(1).contiguous()
         with torch.cuda.device(act.device):
-            rc = _lib.lib().hssb_ce_head_backward(act.data_ptr(), logp.data_ptr(), M, K, weight.data_ptr(), target.data_ptr(), scale,
-                                                  d_act.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), _lib.stream_ptr())
+            rc = _lib.lib().hssb_ce_head_backward(act.data_ptr(), logp.data_ptr(), M, K, weight.data_ptr(), target.data_ptr(), 1.0 / max(M, 1),
+                                                  up.data_ptr(), d_act.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "hssb_ce_head_backward")
         return d_act, d_w, d_b, None
 

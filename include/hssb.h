@@ -199,12 +199,13 @@ int hssb_lstm_train_backward_tc(const float *gates, float *dG, const float *cell
 /* Fused head + loss of the training step: linear(2H -> 4) + log_softmax (segmenter.py:86-87) + nn.CrossEntropyLoss on the
  * permuted output (main.py:69-70).  act [M,K] f32 (K = 2H <= 512, after ReLU / dropout), w [4,K], b [4], target [M] int64.
  * forward : logp [M,4]; *loss_sum (float64 device, caller zeroes) += sum over rows of (lse(logp) - logp[target]).
- * backward: with scale = upstream gradient / number of rows (mean reduction): d_act [M,K] (written), d_w [4,K] and d_b [4]
+ * backward: with scale (x *upstream when upstream != NULL: a device scalar, so autograd's dL/d(loss) needs no host read)
+ *           = upstream gradient / number of rows (mean reduction): d_act [M,K] (written), d_w [4,K] and d_b [4]
  *           (accumulated: caller zeroes). */
 int hssb_ce_head_forward(const float *act, int64_t M, int K, const float *w, const float *b, const int64_t *target,
                          float *logp, double *loss_sum, void *stream);
 int hssb_ce_head_backward(const float *act, const float *logp, int64_t M, int K, const float *w, const int64_t *target,
-                          float scale, float *d_act, float *d_w, float *d_b, void *stream);
+                          float scale, const float *upstream, float *d_act, float *d_w, float *d_b, void *stream);
 
 /* a[n] = hi[n] + lo[n], hi exactly representable in TF32 (round to nearest, ties away; inf / NaN pass through).  Operand
  * preparation for running the fp32 GEMMs of back-propagation (autograd's mm kernels under nn.LSTM, reference main.py:72) as
