@@ -28,9 +28,9 @@ for r in rows[2:]:
     if key == "tc_inproj":          # <3, 8, ..> = the layer-1 projection (stand-in / HSSB_FUSE_X=0 path), <4, 4, ..> = layer 2's
         key = "tc_inproj_l0" if "<3, 8" in kname or "(int)3, (int)8" in kname else "tc_inproj_l1"
         n_inproj += 1
-    if key == "tc_recurrent":       # <S, publish, EW, fused>: fused = layer 1 (input projection in the kernel), else layer 2
+    if key == "tc_recurrent":       # <S, publish, EW, fused, train>: fused = layer 1 (input projection in the kernel), else layer 2
         args = kname[kname.index("<") + 1:kname.index(">")].replace("(int)", "").replace("(bool)", "").split(",")
-        key = "tc_recurrent_l1" if args[-1].strip() in ("1", "true") else "tc_recurrent_l2"
+        key = "tc_recurrent_l1" if args[3].strip() in ("1", "true") else "tc_recurrent_l2"
     if key.startswith("tc_") and float(r[idx["gpu__time_duration.sum"]]) * tmult[units[idx["gpu__time_duration.sum"]]] < 0.02:
         continue                    # a stand-in launch of the input-range guard that exited at once
     b = float(r[idx["dram__bytes_read.sum"]]) * mult[units[idx["dram__bytes_read.sum"]]] + \
