@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
         if (b0 < B) {
             constexpr int NW = C::NW;
             constexpr int NI = NW / 4;                  // (unit, column) cells per thread: columns cbase + 8*(i/2) + 2*cp + (i&1)
+            constexpr bool EARLY_X = !FUSE_X && !TRAIN && S <= 2;
             constexpr float LOG2E = 1.4426950408889634f;
             constexpr float EMAX = 60.0f;               // exponent clamp: (1 + 2^60)^2 is finite, sigmoid(-41) = 0 in fp32 anyway
             const long long left = B - b0;
@@ -259,8 +260,9 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
             float4 xnext[NI];
             float c_state[NI];
             int x_t = dir ? (int)T - 1 : 0, x_tile = -1;        // time index of the next xproj load and the time tile already waited for
-            // xproj of the next step -> registers.  Issued as the LAST thing of a step: every later long-scoreboard
-            // wait of the warp (TMA issue, spill reloads, ...) would otherwise sit behind these HBM loads.
+            // xproj of the next step -> registers.  With three sub-tiles issued as the LAST thing of a step: every later long-scoreboard
+            // wait of the warp (TMA issue, spill reloads, ...) would otherwise sit behind these HBM loads; with one or two sub-tiles
+            // (and in the training variant) right after the publish: there the HBM round trip itself is what must be hidden.
             auto load_into = [&](float4 *dst) {
                 if (!FUSE_X && p.chunk_done && (x_t >> 7) != x_tile) {
                     // the projection GEMM runs concurrently: wait until this direction's chunk of the time tile is in memory
@@ -448,6 +450,10 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                         }
                     }
                 } else {
+                // With one or two sub-tiles per cluster a step is about as long as an HBM round trip: the next step's xproj loads go out
+                // before the output store (measured at T = 2000: 6.41 -> 6.18 ms at 50 windows, 9.8 -> 9.55 ms at 300; with three
+                // sub-tiles the other two sub-tiles' steps hide the latency and the late issue below is as fast or faster)
+                if (EARLY_X && t + 1 < Ti) load_x();
                 // ---- off the critical path: relu(h_t) -> global memory by TMA from this warp's tile ----
                 if (elect_one()) tma_store_wait_read<0>();        // the previous step's store has read the tile
                 __syncwarp();
@@ -486,7 +492,7 @@ __global__ void __launch_bounds__(RmCfg<S, EW, FUSE_X>::THREADS, 1) tc_recurrent
                 }
                 t_idx += dir ? -1 : 1;
                 if (t + 1 < Ti) {
-                    if (!TRAIN) load_x();
+                    if (!TRAIN && !EARLY_X) load_x();
                 } else if (unit_ok) {
 #pragma unroll
                     for (int i = 0; i < NI; ++i)
