@@ -43,6 +43,17 @@ struct PerDeviceInt {
     void set(int x) { v[slot()].store(x, std::memory_order_release); }
 };
 
+#ifdef __CUDACC__
+// v = hi + lo with hi exactly representable in TF32 (10 explicit mantissa bits, round half away from zero; inf / NaN pass through
+// with lo = 0 / NaN): the operand split of the three-pass TF32 GEMMs of back-propagation (hssb_split_tf32, K5b)
+__device__ __forceinline__ void tf32_split(float v, float &hi, float &lo)
+{
+    const unsigned u = __float_as_uint(v);
+    hi = ((u & 0x7f800000u) == 0x7f800000u) ? v : __uint_as_float((u + 0x1000u) & 0xffffe000u);
+    lo = v == hi ? 0.0f : v - hi;
+}
+#endif
+
 // Optional per-launch timing (hssb_prof_*): a pair of CUDA events recorded on the launching stream
 // around one kernel launch.  Costs nothing when disabled.
 struct ProfScope {

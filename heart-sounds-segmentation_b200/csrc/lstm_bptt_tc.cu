@@ -31,7 +31,9 @@ namespace hssb {
 
 struct BpttParams {
     const float *gates;      // [2][B*T][960]  activated gates i, f, g, o of the forward
-    float *dg;               // [2][B*T][960]  out: dG (may alias gates: a cell's gates are in registers before its dG is written)
+    float *dg;               // [2][B*T][960]  out: dG (may alias gates: a cell's gates are in registers before its dG is written); nullable
+    float *dg_hi, *dg_lo;    // the same values as a TF32-exact head and its fp32 residue (operands of the gradient GEMMs); nullable pair
+    float *db;               // [2][960]  out: sum of dG over batch and time = the gradient of b_ih and of b_hh (zeroed by the launcher); nullable
     const float *cells;      // [2][B*T][240]
     const float *c0;         // [2][B][240]
     const float *d_out;      // [B][T][480]
@@ -185,7 +187,7 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
         }();
         const float s_up = pow2f(e_up), s_dn = pow2f(-e_up);
         const float *gd = p.gates + (size_t)dir * B * T * TC_G + U;
-        float *dgd = p.dg + (size_t)dir * B * T * TC_G + U;
+        const size_t dgo = (size_t)dir * B * T * TC_G + U;
         const float *cd = p.cells + (size_t)dir * B * T * TC_H + U;
         const float *dd = p.d_out + dir * TC_H + U;
 
@@ -194,6 +196,7 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
         // [0..3] activated gates i, f, g, o; [4] c of the previous time step (c0 at the last one); [5] d_out
         float sv[NC][6], nx[NC][6];
         float c_cur[NC], dc_carry[NC], dh_rec[NC];
+        float db_acc[4] = {0.f, 0.f, 0.f, 0.f};      // this thread's unit, summed over its columns and all steps
         auto t_of = [&](int k) { return dir ? k : Ti - 1 - k; };
         auto load_step = [&](int k, float (&dst)[NC][6]) {
             const int t = t_of(k);
@@ -283,8 +286,22 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
 #pragma unroll
             for (int i = 0; i < NC; ++i)
                 if (ok[i]) {
-                    float *g = dgd + (cellbase[i] + t) * TC_G;
-                    __stcs(g, da[i][0]); __stcs(g + TC_H, da[i][1]); __stcs(g + 2 * TC_H, da[i][2]); __stcs(g + 3 * TC_H, da[i][3]);
+                    const size_t o = dgo + (cellbase[i] + t) * TC_G;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) db_acc[g] += da[i][g];
+                    if (p.dg) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) __stcs(p.dg + o + g * TC_H, da[i][g]);
+                    }
+                    if (p.dg_hi) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float hi, lo;
+                            tf32_split(da[i][g], hi, lo);
+                            __stcs(p.dg_hi + o + g * TC_H, hi);
+                            __stcs(p.dg_lo + o + g * TC_H, lo);
+                        }
+                    }
                 }
             // ---- partial dL/dh_prev of peer `dest`'s units: TMEM -> staging -> one bulk copy into its receive buffer ----
             mbar_wait(d_full, (uint32_t)(k & 1));
@@ -316,6 +333,10 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
                 p.dh0[stateo[i]] = dh_rec[i];
                 p.dc0[stateo[i]] = dc_carry[i];
             }
+        if (p.db && unit_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) atomicAdd(p.db + dir * TC_G + g * TC_H + U, db_acc[g]);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -402,7 +423,7 @@ int bptt_tc_prepare()
     return bptt_prepare<32>(&n);
 }
 
-int bptt_tc_backward(const float *gates, float *dg, const float *cells, const float *w_fwd, const float *w_rev, const float *c0, const float *d_out,
+int bptt_tc_backward(const float *gates, float *dg, float *dg_hi, float *dg_lo, float *db, const float *cells, const float *w_fwd, const float *w_rev, const float *c0, const float *d_out,
                      const float *d_hn, const float *d_cn, int64_t B, int64_t T, float *dh0, float *dc0, void *ws, size_t ws_bytes,
                      cudaStream_t st)
 {
@@ -410,6 +431,7 @@ int bptt_tc_backward(const float *gates, float *dg, const float *cells, const fl
     __half *whhT = static_cast<__half *>(ws);
     unsigned *range = reinterpret_cast<unsigned *>(static_cast<char *>(ws) + BPTT_W_BYTES);
     HSSB_CUDA_OK(cudaMemsetAsync(range, 0, 8, st));
+    if (db) HSSB_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * 2 * TC_G, st));
     {
         ProfScope prof("bptt_pack", st);
         pack_whhT_kernel<<<RC_CL * 256, 128, 0, st>>>(w_fwd, 0, whhT);
@@ -425,7 +447,7 @@ int bptt_tc_backward(const float *gates, float *dg, const float *cells, const fl
     int force_nb = 0;
     if (const char *e = getenv("HSSB_BPTT_NB")) force_nb = atoi(e);
     BpttParams prm = {};
-    prm.gates = gates; prm.dg = dg; prm.cells = cells; prm.c0 = c0; prm.d_out = d_out; prm.d_hn = d_hn; prm.d_cn = d_cn;
+    prm.gates = gates; prm.dg = dg; prm.dg_hi = dg_hi; prm.dg_lo = dg_lo; prm.db = db; prm.cells = cells; prm.c0 = c0; prm.d_out = d_out; prm.d_hn = d_hn; prm.d_cn = d_cn;
     prm.dh0 = dh0; prm.dc0 = dc0; prm.whhT = whhT; prm.range = range; prm.B = B; prm.T = T;
     for (long long base = 0; base < B;) {
         const long long rem = B - base;

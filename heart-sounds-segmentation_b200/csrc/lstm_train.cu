@@ -261,16 +261,19 @@ extern "C" int hssb_lstm_train_backward(float *gates, const float *cells, const 
 
 extern "C" size_t hssb_lstm_train_backward_tc_workspace_bytes(void) { return bptt_tc_workspace_bytes(); }
 
-extern "C" int hssb_lstm_train_backward_tc(const float *gates, float *dG, const float *cells, const float *w_hh_fwd, const float *w_hh_rev, const float *c0,
+extern "C" int hssb_lstm_train_backward_tc(const float *gates, float *dG, float *dG_hi, float *dG_lo, float *db, const float *cells, const float *w_hh_fwd, const float *w_hh_rev, const float *c0,
                                            const float *d_out, const float *d_hn, const float *d_cn, int64_t B, int64_t T,
                                            float *dh0, float *dc0, void *workspace, size_t workspace_bytes, void *stream)
 {
-    if (!gates || !dG || !cells || !w_hh_fwd || !w_hh_rev || !c0 || !d_out || !dh0 || !dc0)
+    if (!gates || !cells || !w_hh_fwd || !w_hh_rev || !c0 || !d_out || !dh0 || !dc0)
         return fail(HSSB_E_NULL, "hssb_lstm_train_backward_tc: null pointer");
+    if ((!dG && !dG_hi) || (!dG_hi != !dG_lo)) return fail(HSSB_E_NULL, "hssb_lstm_train_backward_tc: need dG and / or the (dG_hi, dG_lo) pair");
     if (int rc = check_train_args("hssb_lstm_train_backward_tc", B, T, 240)) return rc;
-    if (B == 0 || T == 0)       // nothing for the tensor cores to do: the generic entry point handles the degenerate shapes (no dG rows)
-        return hssb_lstm_train_backward(dG, cells, w_hh_fwd, w_hh_rev, c0, d_out, d_hn, d_cn, B, T, 240, dh0, dc0, stream);
+    if (B == 0 || T == 0) {     // nothing for the tensor cores to do: the generic entry point handles the degenerate shapes (no dG rows)
+        if (db) HSSB_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * 2 * 960, as_stream(stream)));
+        return hssb_lstm_train_backward(dG ? dG : dG_hi, cells, w_hh_fwd, w_hh_rev, c0, d_out, d_hn, d_cn, B, T, 240, dh0, dc0, stream);
+    }
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(HSSB_E_WORKSPACE, "hssb_lstm_train_backward_tc: workspace must be 256-byte aligned");
     if (int rc = require_sm100()) return rc;
-    return bptt_tc_backward(gates, dG, cells, w_hh_fwd, w_hh_rev, c0, d_out, d_hn, d_cn, B, T, dh0, dc0, workspace, workspace_bytes, as_stream(stream));
+    return bptt_tc_backward(gates, dG, dG_hi, dG_lo, db, cells, w_hh_fwd, w_hh_rev, c0, d_out, d_hn, d_cn, B, T, dh0, dc0, workspace, workspace_bytes, as_stream(stream));
 }

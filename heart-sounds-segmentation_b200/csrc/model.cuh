@@ -67,7 +67,7 @@ int train_bwd_cluster_launch(float *gates, const float *cells, const float *w0, 
 // back-propagation through time on the tensor cores (lstm_bptt_tc.cu): hidden_size 240, weights in the fp16-split range
 size_t bptt_tc_workspace_bytes();
 int bptt_tc_prepare();
-int bptt_tc_backward(const float *gates, float *dg, const float *cells, const float *w_fwd, const float *w_rev, const float *c0, const float *d_out,
+int bptt_tc_backward(const float *gates, float *dg, float *dg_hi, float *dg_lo, float *db, const float *cells, const float *w_fwd, const float *w_rev, const float *c0, const float *d_out,
                      const float *d_hn, const float *d_cn, int64_t B, int64_t T, float *dh0, float *dc0, void *ws, size_t ws_bytes,
                      cudaStream_t st);
 

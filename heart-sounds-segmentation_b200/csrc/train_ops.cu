@@ -266,24 +266,18 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4 *__restric
                                                          int tail, float4 *__restrict__ hi, float4 *__restrict__ lo, float *__restrict__ tail_hi,
                                                          float *__restrict__ tail_lo)
 {
-    auto round_tf32 = [](float v) {
-        const unsigned u = __float_as_uint(v);
-        if ((u & 0x7f800000u) == 0x7f800000u) return v;
-        return __uint_as_float((u + 0x1000u) & 0xffffe000u);
-    };
-    auto residue = [](float v, float h) { return v == h ? 0.0f : v - h; };      // (inf - inf would be NaN; NaN keeps its NaN)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = __ldg(a + i);
         float4 h, l;
-        h.x = round_tf32(v.x); h.y = round_tf32(v.y); h.z = round_tf32(v.z); h.w = round_tf32(v.w);
-        l.x = residue(v.x, h.x); l.y = residue(v.y, h.y); l.z = residue(v.z, h.z); l.w = residue(v.w, h.w);
+        tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
         hi[i] = h;
         lo[i] = l;
     }
     if (blockIdx.x == 0 && (int)threadIdx.x < tail) {
-        const float v = tail_src[threadIdx.x], h = round_tf32(v);
+        float h, l;
+        tf32_split(tail_src[threadIdx.x], h, l);
         tail_hi[threadIdx.x] = h;
-        tail_lo[threadIdx.x] = residue(v, h);
+        tail_lo[threadIdx.x] = l;
     }
 }
 }  // namespace hssb

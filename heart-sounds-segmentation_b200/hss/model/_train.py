@@ -106,32 +106,39 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         lib = _lib.lib()
         p_hn = d_hn.data_ptr() if d_hn is not None else None
         p_cn = d_cn.data_ptr() if d_cn is not None else None
+        M = B * T
+        split_gemms = M > 0 and os.environ.get("HSSB_TRAIN_GEMM", "tf32x3") != "fp32"
+        dG = g_hi = g_lo = db2 = None
         with torch.cuda.device(dev):
-            if ctx.tensor_cores and B * T and os.environ.get("HSSB_TRAIN_BWD", "tc") == "tc":
-                # the forward ran on the tcgen05 kernels (reference geometry, weights in the fp16-split range): so does this;
-                # dG goes to its own buffer, the saved activations stay intact
-                dG = torch.empty_like(gates)
+            if ctx.tensor_cores and M and os.environ.get("HSSB_TRAIN_BWD", "tc") == "tc":
+                # the forward ran on the tcgen05 kernels (reference geometry, weights in the fp16-split range): so does this.  The gate
+                # gradients come back in their own buffers (the saved activations stay intact) -- already split for the TF32 GEMMs
+                if split_gemms:
+                    g_hi, g_lo = torch.empty_like(gates), torch.empty_like(gates)
+                else:
+                    dG = torch.empty_like(gates)
                 ws = torch.empty(lib.hssb_lstm_train_backward_tc_workspace_bytes(), dtype=torch.uint8, device=dev)
-                rc = lib.hssb_lstm_train_backward_tc(gates.data_ptr(), dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(),
-                                                     c0.data_ptr(), d_out.data_ptr(), p_hn, p_cn, B, T, dh0.data_ptr(), dc0.data_ptr(),
-                                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+                db2 = torch.empty((2, 4 * H), dtype=torch.float32, device=dev)        # bias gradients, summed inside the kernel
+                rc = lib.hssb_lstm_train_backward_tc(gates.data_ptr(), dG.data_ptr() if dG is not None else None,
+                                                     g_hi.data_ptr() if g_hi is not None else None, g_lo.data_ptr() if g_lo is not None else None,
+                                                     db2.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(), d_out.data_ptr(),
+                                                     p_hn, p_cn, B, T, dh0.data_ptr(), dc0.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
                 _lib.check(rc, "hssb_lstm_train_backward_tc")
             else:
                 dG = gates.clone()               # this kernel turns activations into dG in place; keep the saved tensor intact
                 rc = lib.hssb_lstm_train_backward(dG.data_ptr(), cells.data_ptr(), w_hh.data_ptr(), w_hh_r.data_ptr(), c0.data_ptr(),
                                                   d_out.data_ptr(), p_hn, p_cn, B, T, H, dh0.data_ptr(), dc0.data_ptr(), _lib.stream_ptr())
                 _lib.check(rc, "hssb_lstm_train_backward")
-        M = B * T
         x2 = x.reshape(M, Fin)
         grads = []
-        if os.environ.get("HSSB_TRAIN_GEMM", "tf32x3") == "fp32" or M == 0:
+        if not split_gemms:
             # the mm kernels autograd itself would run for nn.LSTM (SIMT fp32)
             # h_{prev}: forward direction = out[:, t-1, :H] (h0 at t = 0); reverse direction = out[:, t+1, H:] (h0 at t = T-1)
             hp_f = torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(M, H)
             hp_r = torch.cat([out[:, 1:, H:], h0[1].unsqueeze(1)], dim=1).reshape(M, H)
             for d, hp in enumerate((hp_f, hp_r)):
                 g = dG[d]
-                db = g.sum(dim=0)
+                db = db2[d] if db2 is not None else g.sum(dim=0)
                 grads.append((g.t() @ x2, g.t() @ hp, db, db.clone()))
             dx = (dG[0] @ w_ih + dG[1] @ w_ih_r).reshape(B, T, Fin) if ctx.needs_input_grad[0] else None
         else:
@@ -139,7 +146,8 @@ class BiLSTMLayerFunction(torch.autograd.Function):
             # dG^T h_prev without materialising h_prev: in the flattened [B*T] row order h_prev of row r is row r - 1 of out[:, :H]
             # (forward) / row r + 1 of out[:, H:] (reverse), i.e. one GEMM on views shifted by a row -- except at each window's first
             # (last) step, where the partner is h0 instead of the neighbouring window's last (first) step: B rows, fixed up in fp32.
-            g_hi, g_lo = _split_tf32(dG)
+            if g_hi is None:
+                g_hi, g_lo = _split_tf32(dG)
             xs = _split_tf32(x2)
             o_hi, o_lo = (t.view(M, 2 * H) for t in _split_tf32(out))
             o2 = out.view(M, 2 * H)
@@ -158,11 +166,11 @@ class BiLSTMLayerFunction(torch.autograd.Function):
                     if ctx.needs_input_grad[0]:
                         dx = _mm3((g_hi[d], g_lo[d]), _split_tf32(wi), out=dx)
             # the B edge rows, in plain fp32 (outside the TF32 switch: with T = 1 they are the whole gradient)
-            edge_f, edge_r = dG[0][first], dG[1][last]
+            edge_f, edge_r = g_hi[0][first] + g_lo[0][first], g_hi[1][last] + g_lo[1][last]      # hi + lo is the value itself
             fix_f = edge_f.t() @ h0[0] - edge_f[1:].t() @ o2[first[1:] - 1, :H]
             fix_r = edge_r.t() @ h0[1] - edge_r[:-1].t() @ o2[last[:-1] + 1, H:]
             for d, fix in enumerate((fix_f, fix_r)):
-                db = dG[d].sum(dim=0)
+                db = db2[d] if db2 is not None else dG[d].sum(dim=0)
                 grads.append((big[d][0], big[d][1] + fix, db, db.clone()))
             dx = dx.reshape(B, T, Fin) if dx is not None else None
         (dwi, dwh, dbi, dbh), (dwi_r, dwh_r, dbi_r, dbh_r) = grads

@@ -188,11 +188,13 @@ int hssb_lstm_train_backward(float *gates, const float *cells, const float *w_hh
 /* The same back-propagation through time for hidden_size 240 on the tcgen05 kernels (W_hh^T slices resident in TMEM, the
  * gate gradients as split-fp16 operands scaled by a power of two taken from max|d_out|, |d_hn|; reduce-scatter of the
  * partial dL/dh between the 8 CTAs of a cluster by bulk copies).  Same layouts; the gate gradients go to dG, which may be
- * the gates buffer itself (in place, like the fp32 entry point) or a separate one (the saved activations stay intact);
+ * the gates buffer itself (in place, like the fp32 entry point) or a separate one (the saved activations stay intact),
+ * and / or to the pair (dG_hi, dG_lo) = hssb_split_tf32 of the same values, ready for the gradient GEMMs (either may be NULL);
+ * db (nullable) [2][4H]: the sum of dG over batch and time = the gradient of b_ih and of b_hh;
  * weights must be in the fp16-split range (hssb_model_uses_tensor_cores of a model holding them).  workspace: 256-byte
  * aligned device scratch of hssb_lstm_train_backward_tc_workspace_bytes() bytes. */
 size_t hssb_lstm_train_backward_tc_workspace_bytes(void);
-int hssb_lstm_train_backward_tc(const float *gates, float *dG, const float *cells, const float *w_hh_fwd, const float *w_hh_rev, const float *c0,
+int hssb_lstm_train_backward_tc(const float *gates, float *dG, float *dG_hi, float *dG_lo, float *db, const float *cells, const float *w_hh_fwd, const float *w_hh_rev, const float *c0,
                                 const float *d_out, const float *d_hn, const float *d_cn, int64_t B, int64_t T,
                                 float *dh0, float *dc0, void *workspace, size_t workspace_bytes, void *stream);
 

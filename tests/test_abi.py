@@ -66,8 +66,9 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.hssb_lstm_train_forward(None, p, p, p, p, 1, 8, 240, p, p, p, p, None) == -1
     # tensor-core training entry points and the in-place re-pack: null handles / pointers, bad layer, bad shapes
     assert lib.hssb_lstm_train_forward_tc(None, 0, p, 1, 8, p, p, p, p, p, p, p, None, 0, None) == -1
-    assert lib.hssb_lstm_train_backward_tc(None, p, p, p, p, p, p, None, None, 1, 8, p, p, None, 0, None) == -1
-    assert lib.hssb_lstm_train_backward_tc(p, p, p, p, p, p, p, None, None, -1, 8, p, p, None, 0, None) == -2
+    assert lib.hssb_lstm_train_backward_tc(None, p, None, None, None, p, p, p, p, p, None, None, 1, 8, p, p, None, 0, None) == -1
+    assert lib.hssb_lstm_train_backward_tc(p, None, p, None, None, p, p, p, p, p, None, None, 1, 8, p, p, None, 0, None) == -1   # half a pair
+    assert lib.hssb_lstm_train_backward_tc(p, p, None, None, None, p, p, p, p, p, None, None, -1, 8, p, p, None, 0, None) == -2
     assert lib.hssb_lstm_train_backward_tc_workspace_bytes() >= 2 * 8 * 2 * 256 * 128 * 2
     assert lib.hssb_model_update(None, None, None) == -1
     assert lib.hssb_model_uses_tensor_cores(None) == 0
