@@ -32,7 +32,8 @@ namespace hssb {
 struct BpttParams {
     const float *gates;      // [2][B*T][960]  activated gates i, f, g, o of the forward
     float *dg;               // [2][B*T][960]  out: dG (may alias gates: a cell's gates are in registers before its dG is written); nullable
-    float *dg_hi, *dg_lo;    // the same values as a TF32-exact head and its fp32 residue (operands of the gradient GEMMs); nullable pair
+    float *dg_hi, *dg_lo;    // the same values as a TF32-exact head and its fp32 residue (operands of the gradient GEMMs); nullable pair,
+                             // laid out [B*T][2][960]: both directions of a row side by side, so that dG^T x and dG W_ih are ONE GEMM each
     float *db;               // [2][960]  out: sum of dG over batch and time = the gradient of b_ih and of b_hh (zeroed by the launcher); nullable
     const float *cells;      // [2][B*T][240]
     const float *c0;         // [2][B][240]
@@ -294,12 +295,13 @@ __global__ void __cluster_dims__(RC_CL, 1, 1) __launch_bounds__(BpCfg<NB>::THREA
                         for (int g = 0; g < 4; ++g) __stcs(p.dg + o + g * TC_H, da[i][g]);
                     }
                     if (p.dg_hi) {
+                        const size_t o2 = ((cellbase[i] + t) * 2 + dir) * TC_G + U;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             float hi, lo;
                             tf32_split(da[i][g], hi, lo);
-                            __stcs(p.dg_hi + o + g * TC_H, hi);
-                            __stcs(p.dg_lo + o + g * TC_H, lo);
+                            __stcs(p.dg_hi + o2 + g * TC_H, hi);
+                            __stcs(p.dg_lo + o2 + g * TC_H, lo);
                         }
                     }
                 }

@@ -114,7 +114,8 @@ class BiLSTMLayerFunction(torch.autograd.Function):
                 # the forward ran on the tcgen05 kernels (reference geometry, weights in the fp16-split range): so does this.  The gate
                 # gradients come back in their own buffers (the saved activations stay intact) -- already split for the TF32 GEMMs
                 if split_gemms:
-                    g_hi, g_lo = torch.empty_like(gates), torch.empty_like(gates)
+                    g_hi = torch.empty((M, 2, 4 * H), dtype=torch.float32, device=dev)      # [row][direction][gate]: see below
+                    g_lo = torch.empty_like(g_hi)
                 else:
                     dG = torch.empty_like(gates)
                 ws = torch.empty(lib.hssb_lstm_train_backward_tc_workspace_bytes(), dtype=torch.uint8, device=dev)
@@ -146,32 +147,40 @@ class BiLSTMLayerFunction(torch.autograd.Function):
             # dG^T h_prev without materialising h_prev: in the flattened [B*T] row order h_prev of row r is row r - 1 of out[:, :H]
             # (forward) / row r + 1 of out[:, H:] (reverse), i.e. one GEMM on views shifted by a row -- except at each window's first
             # (last) step, where the partner is h0 instead of the neighbouring window's last (first) step: B rows, fixed up in fp32.
-            if g_hi is None:
-                g_hi, g_lo = _split_tf32(dG)
+            if g_hi is None:            # dG [2][M][4H] from the fp32 backward: per-direction operands
+                a_hi, a_lo = _split_tf32(dG)
+                gd_hi, gd_lo = (a_hi[0], a_hi[1]), (a_lo[0], a_lo[1])
+                merged = None
+            else:                       # K5b's [M][2][4H]: the two directions of a row side by side
+                gd_hi, gd_lo = (g_hi[:, 0], g_hi[:, 1]), (g_lo[:, 0], g_lo[:, 1])
+                merged = (g_hi.view(M, 8 * H), g_lo.view(M, 8 * H))
             xs = _split_tf32(x2)
             o_hi, o_lo = (t.view(M, 2 * H) for t in _split_tf32(out))
             o2 = out.view(M, 2 * H)
             first = torch.arange(B, device=dev) * T          # rows of t = 0
             last = first + (T - 1)                           # rows of t = T - 1
             dx = None
-            big = []
             with _Tf32Matmul():
-                for d, wi in enumerate((w_ih, w_ih_r)):
-                    gt = (g_hi[d].t(), g_lo[d].t())
-                    if d == 0:
-                        dwh = _mm3((g_hi[0][1:].t(), g_lo[0][1:].t()), (o_hi[:-1, :H], o_lo[:-1, :H]))
-                    else:
-                        dwh = _mm3((g_hi[1][:-1].t(), g_lo[1][:-1].t()), (o_hi[1:, H:], o_lo[1:, H:]))
-                    big.append((_mm3(gt, xs), dwh))
+                dwh = (_mm3((gd_hi[0][1:].t(), gd_lo[0][1:].t()), (o_hi[:-1, :H], o_lo[:-1, :H])),
+                       _mm3((gd_hi[1][:-1].t(), gd_lo[1][:-1].t()), (o_hi[1:, H:], o_lo[1:, H:])))
+                if merged is not None:
+                    # dG^T x for both directions in one GEMM ([8H, M] x [M, F]: twice the tiles), likewise dG [W_ih; W_ih_r]
+                    both = _mm3((merged[0].t(), merged[1].t()), xs)
+                    dwi = (both[:4 * H], both[4 * H:])
                     if ctx.needs_input_grad[0]:
-                        dx = _mm3((g_hi[d], g_lo[d]), _split_tf32(wi), out=dx)
+                        dx = _mm3(merged, _split_tf32(torch.cat([w_ih, w_ih_r], dim=0)))
+                else:
+                    dwi = tuple(_mm3((gd_hi[d].t(), gd_lo[d].t()), xs) for d in range(2))
+                    if ctx.needs_input_grad[0]:
+                        for d, wi in enumerate((w_ih, w_ih_r)):
+                            dx = _mm3((gd_hi[d], gd_lo[d]), _split_tf32(wi), out=dx)
             # the B edge rows, in plain fp32 (outside the TF32 switch: with T = 1 they are the whole gradient)
-            edge_f, edge_r = g_hi[0][first] + g_lo[0][first], g_hi[1][last] + g_lo[1][last]      # hi + lo is the value itself
+            edge_f, edge_r = gd_hi[0][first] + gd_lo[0][first], gd_hi[1][last] + gd_lo[1][last]      # hi + lo is the value itself
             fix_f = edge_f.t() @ h0[0] - edge_f[1:].t() @ o2[first[1:] - 1, :H]
             fix_r = edge_r.t() @ h0[1] - edge_r[:-1].t() @ o2[last[:-1] + 1, H:]
             for d, fix in enumerate((fix_f, fix_r)):
                 db = db2[d] if db2 is not None else dG[d].sum(dim=0)
-                grads.append((big[d][0], big[d][1] + fix, db, db.clone()))
+                grads.append((dwi[d], dwh[d] + fix, db, db.clone()))
             dx = dx.reshape(B, T, Fin) if dx is not None else None
         (dwi, dwh, dbi, dbh), (dwi_r, dwh_r, dbi_r, dbh_r) = grads
         return dx, dh0, dc0, dwi, dwh, dbi, dbh, dwi_r, dwh_r, dbi_r, dbh_r, None

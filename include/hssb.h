@@ -189,7 +189,8 @@ int hssb_lstm_train_backward(float *gates, const float *cells, const float *w_hh
  * gate gradients as split-fp16 operands scaled by a power of two taken from max|d_out|, |d_hn|; reduce-scatter of the
  * partial dL/dh between the 8 CTAs of a cluster by bulk copies).  Same layouts; the gate gradients go to dG, which may be
  * the gates buffer itself (in place, like the fp32 entry point) or a separate one (the saved activations stay intact),
- * and / or to the pair (dG_hi, dG_lo) = hssb_split_tf32 of the same values, ready for the gradient GEMMs (either may be NULL);
+ * and / or to the pair (dG_hi, dG_lo) = hssb_split_tf32 of the same values, laid out [B*T][2][4H] (both directions of a row
+ * side by side: dG^T x and dG W_ih are then one GEMM each for the two directions) -- dG and the pair may each be NULL;
  * db (nullable) [2][4H]: the sum of dG over batch and time = the gradient of b_ih and of b_hh;
  * weights must be in the fp16-split range (hssb_model_uses_tensor_cores of a model holding them).  workspace: 256-byte
  * aligned device scratch of hssb_lstm_train_backward_tc_workspace_bytes() bytes. */

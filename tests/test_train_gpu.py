@@ -243,8 +243,13 @@ def test_tf32_split_gemms_match_fp32(lib, monkeypatch):
 @pytest.mark.parametrize("B,T,nb", [(5, 40, 0), (21, 300, 0), (21, 300, 16), (21, 300, 32), (50, 500, 0), (70, 130, 0), (130, 90, 0), (300, 33, 0)])
 def test_tensor_core_backward_agrees_with_the_fp32_kernel(lib, monkeypatch, B, T, nb):
     """Back-propagation through time on the tcgen05 kernel (hssb_lstm_train_backward_tc; the default after a tensor-core forward)
-    against the fp32 cluster kernel (HSSB_TRAIN_BWD=cluster) on the SAME forward: every parameter gradient and the input
-    gradient within 2e-5 of the tensor's max-abs (the recurrent product runs on split-fp16 operands scaled from max|d_out|).
+    against the fp32 cluster kernel (HSSB_TRAIN_BWD=cluster) on the SAME forward.
+    (a) Both with the plain fp32 gradient GEMMs, so that the recurrence kernels are the only difference: every parameter gradient
+        and the input gradient within 2e-5 of the tensor's max-abs (the recurrent product runs on split-fp16 operands scaled from
+        max|d_out|; measured 4e-7 .. 9e-7).
+    (b) The default path -- K5b's own TF32-split outputs in the [row][direction][gate] layout, its bias-gradient sums, the merged
+        three-pass TF32 GEMMs -- against (a)'s fp32 reference: within 1e-4 (different GEMM shapes, i.e. another summation order
+        over up to 10^5 products).
     Batches cover 8 / 16 / 32 columns per cluster (forced or chosen), ragged last groups and more groups than one wave."""
     F = 44
     g = torch.Generator().manual_seed(B + T)
@@ -253,18 +258,24 @@ def test_tensor_core_backward_agrees_with_the_fp32_kernel(lib, monkeypatch, B, T
     if nb:
         monkeypatch.setenv("HSSB_BPTT_NB", str(nb))
     results = []
-    for impl in ("tc", "cluster"):
+    for impl, gemm in (("tc", "fp32"), ("cluster", "fp32"), ("tc", "tf32x3")):
         monkeypatch.setenv("HSSB_TRAIN_BWD", impl)
+        monkeypatch.setenv("HSSB_TRAIN_GEMM", gemm)
         m = make_model(19, F, B, 240).cuda().train()
         m.dropout.p = 0.0
         xg = x.clone().requires_grad_(True)
         loss, _ = m.training_loss(xg, y)
         loss.backward()
         results.append(({n: p.grad.clone() for n, p in m.named_parameters()}, xg.grad.clone()))
-    worst = max(rel_err(results[0][0][n], results[1][0][n]) for n in results[1][0])
-    worst = max(worst, rel_err(results[0][1], results[1][1]))
-    print(f"B={B} T={T} nb={nb or 'auto'}: worst relative gradient difference, tensor-core vs fp32 backward: {worst:.2e}")
+
+    def worst_of(a, b):
+        return max(max(rel_err(a[0][n], b[0][n]) for n in b[0]), rel_err(a[1], b[1]))
+
+    worst, worst_default = worst_of(results[0], results[1]), worst_of(results[2], results[1])
+    print(f"B={B} T={T} nb={nb or 'auto'}: worst relative gradient difference, tensor-core vs fp32 backward: {worst:.2e}; "
+          f"default path (split outputs, merged TF32 GEMMs) vs fp32: {worst_default:.2e}")
     assert worst < 2e-5
+    assert worst_default < 1e-4
 
 
 def test_tensor_core_backward_keeps_tiny_and_huge_gradients(lib, monkeypatch):
