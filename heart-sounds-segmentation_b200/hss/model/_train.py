@@ -1,11 +1,17 @@
 """Training-mode forward of the segmenter: one autograd function per bidirectional LSTM layer.
 
 The reference trains ``nn.LSTM`` under autograd (``main.py:67-82`` over ``hss/model/segmenter.py:80-87``).
-Here the two recurrences of a layer -- the forward that keeps the activated gates and cell states, and
-back-propagation through time -- are CUDA kernels of ``libhssb.so`` (``hssb_lstm_train_forward`` /
-``hssb_lstm_train_backward``); the plain GEMMs either side (``x W_ih^T + b``, ``dG^T x``, ``dG^T h_prev``,
-``dG W_ih``) are cuBLAS calls through ``torch``; ReLU, dropout, the linear head and log-softmax stay torch
-ops, so torch's RNG drives dropout exactly as in the reference.  fp32 throughout.
+Here a layer's forward (input projection + the recurrence that keeps the activated gates, cell states and raw h) and its
+back-propagation through time are CUDA kernels of ``libhssb.so``:
+
+* reference geometry (hidden 240, <= 64 inputs, weights inside the fp16-split range): ``hssb_lstm_train_forward_tc`` (K4 +
+  K5m TRAIN variant on tcgen05, operands re-packed after every optimiser step by ``hssb_model_update``) and
+  ``hssb_lstm_train_backward_tc`` (K5b), which also hands back dG split for the three-pass TF32 GEMMs and the bias gradients;
+* anything else: cuBLAS projection + ``hssb_lstm_train_forward`` / ``hssb_lstm_train_backward`` (fp32 cluster / generic kernels).
+
+The weight / input gradient GEMMs (``dG^T x``, ``dG^T h_prev``, ``dG W_ih``) are library GEMMs through torch -- as three TF32
+tensor-core passes on operands split by ``hssb_split_tf32`` (``HSSB_TRAIN_GEMM=fp32``: torch's plain fp32 ones); ReLU and dropout
+stay torch ops, so torch's RNG drives dropout exactly as in the reference; the head + loss is ``HeadLossFunction``.
 """
 from __future__ import annotations
 
@@ -44,6 +50,26 @@ def _mm3(a, b, out=None):
     out = al @ bh if out is None else out.addmm_(al, bh)
     out.addmm_(ah, bl)
     return out.addmm_(ah, bh)
+
+
+def shifted_rows(M: int, H: int, d: int):
+    """Row / column slices that pair dG with h_prev WITHOUT materialising h_prev: in the flattened ``[B*T]`` row order the
+    previous hidden state of row ``r`` is row ``r - 1`` of ``out[:, :H]`` (forward, ``d = 0``) or row ``r + 1`` of ``out[:, H:]``
+    (reverse, ``d = 1``).  Returns ``(rows of dG, rows of out, columns of out)``."""
+    if d == 0:
+        return slice(1, M), slice(0, M - 1), slice(0, H)
+    return slice(0, M - 1), slice(1, M), slice(H, 2 * H)
+
+
+def edge_fixup(g_edge: torch.Tensor, out2: torch.Tensor, h0_d: torch.Tensor, B: int, T: int, H: int, d: int) -> torch.Tensor:
+    """What the row-shifted product gets wrong: at each window's first (forward) / last (reverse) step the partner of dG is
+    ``h0``, not the neighbouring window's last / first output.  ``g_edge[B, 4H]``: dG at those steps; ``out2[B*T, 2H]``.
+    Returns the ``[4H, H]`` correction: ``+ g_edge^T h0  - (the wrongly paired rows)``."""
+    idx = torch.arange(B, device=out2.device) * T
+    if d == 0:          # rows b*T (t = 0) were paired with row b*T - 1 (window b - 1, last step); window 0's row was left out
+        return g_edge.t() @ h0_d - g_edge[1:].t() @ out2[idx[1:] - 1, :H]
+    idx = idx + (T - 1)  # rows b*T + T - 1 were paired with row (b + 1)*T (window b + 1, first step); the last window's row was left out
+    return g_edge.t() @ h0_d - g_edge[:-1].t() @ out2[idx[:-1] + 1, H:]
 
 
 class BiLSTMLayerFunction(torch.autograd.Function):
@@ -159,10 +185,10 @@ class BiLSTMLayerFunction(torch.autograd.Function):
             o2 = out.view(M, 2 * H)
             first = torch.arange(B, device=dev) * T          # rows of t = 0
             last = first + (T - 1)                           # rows of t = T - 1
+            sl = [shifted_rows(M, H, d) for d in range(2)]
             dx = None
             with _Tf32Matmul():
-                dwh = (_mm3((gd_hi[0][1:].t(), gd_lo[0][1:].t()), (o_hi[:-1, :H], o_lo[:-1, :H])),
-                       _mm3((gd_hi[1][:-1].t(), gd_lo[1][:-1].t()), (o_hi[1:, H:], o_lo[1:, H:])))
+                dwh = tuple(_mm3((gd_hi[d][rg].t(), gd_lo[d][rg].t()), (o_hi[ro, co], o_lo[ro, co])) for d, (rg, ro, co) in enumerate(sl))
                 if merged is not None:
                     # dG^T x for both directions in one GEMM ([8H, M] x [M, F]: twice the tiles), likewise dG [W_ih; W_ih_r]
                     both = _mm3((merged[0].t(), merged[1].t()), xs)
@@ -175,10 +201,9 @@ class BiLSTMLayerFunction(torch.autograd.Function):
                         for d, wi in enumerate((w_ih, w_ih_r)):
                             dx = _mm3((gd_hi[d], gd_lo[d]), _split_tf32(wi), out=dx)
             # the B edge rows, in plain fp32 (outside the TF32 switch: with T = 1 they are the whole gradient)
-            edge_f, edge_r = gd_hi[0][first] + gd_lo[0][first], gd_hi[1][last] + gd_lo[1][last]      # hi + lo is the value itself
-            fix_f = edge_f.t() @ h0[0] - edge_f[1:].t() @ o2[first[1:] - 1, :H]
-            fix_r = edge_r.t() @ h0[1] - edge_r[:-1].t() @ o2[last[:-1] + 1, H:]
-            for d, fix in enumerate((fix_f, fix_r)):
+            edges = (gd_hi[0][first] + gd_lo[0][first], gd_hi[1][last] + gd_lo[1][last])      # hi + lo is the value itself
+            for d in range(2):
+                fix = edge_fixup(edges[d], o2, h0[d], B, T, H, d)
                 db = db2[d] if db2 is not None else dG[d].sum(dim=0)
                 grads.append((dwi[d], dwh[d] + fix, db, db.clone()))
             dx = dx.reshape(B, T, Fin) if dx is not None else None

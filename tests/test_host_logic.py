@@ -282,3 +282,26 @@ def test_native_batch_csv_parser(tmp_path, built):
     one.write_text("Signals\n0.5\n")
     with pytest.raises(ValueError):
         load_recordings_csv([str(one)])
+
+
+def test_recurrent_weight_gradient_on_row_shifted_views():
+    """hss/model/_train.py computes dG^T h_prev of a layer without building h_prev: one product on views of the flattened
+    outputs shifted by a row plus a B-row correction (h0 at each window's first / last step).  Same result as the product with
+    the explicitly concatenated h_prev, for both directions, including T = 1 and B = 1."""
+    import torch
+    from hss.model._train import edge_fixup, shifted_rows
+
+    g = torch.Generator().manual_seed(0)
+    for B, T, H in ((3, 5, 4), (1, 7, 3), (4, 1, 2), (1, 1, 2)):
+        M = B * T
+        dG = torch.randn(2, M, 4 * H, generator=g, dtype=torch.float64)
+        out = torch.randn(B, T, 2 * H, generator=g, dtype=torch.float64)
+        h0 = torch.randn(2, B, H, generator=g, dtype=torch.float64)
+        hp = (torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(M, H),
+              torch.cat([out[:, 1:, H:], h0[1].unsqueeze(1)], dim=1).reshape(M, H))
+        o2 = out.reshape(M, 2 * H)
+        for d in range(2):
+            rg, ro, co = shifted_rows(M, H, d)
+            edge_rows = torch.arange(B) * T + (0 if d == 0 else T - 1)
+            got = dG[d][rg].t() @ o2[ro, co] + edge_fixup(dG[d][edge_rows], o2, h0[d], B, T, H, d)
+            assert torch.allclose(got, dG[d].t() @ hp[d], rtol=1e-12, atol=1e-12), (B, T, d)
