@@ -586,7 +586,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "data": "synthetic",
             "config": bench_config(B),
             "timing": {"l2": "flushed between timed steps (256 MiB write)", "lstm_impl": os.environ.get("HSSB_LSTM_IMPL", "auto"),
-                       "pipeline": "the FSST of step i+1 runs on a second stream under the BiLSTM of step i (hss.pipeline)" if args.pipeline else "none",
+                       "pipeline": "hss.pipeline.SegmentationPipeline: step i = BiLSTM of batch i + FSST of batch i+1 (a second stream, behind the model's side gate, "
+                                   "on the SMs the recurrences leave idle); the first step also runs its own FSST, the last one prefetches nothing: K transforms "
+                                   "and K model passes inside the K timed steps; results bit-identical to the sequential calls" if args.pipeline else "none (--no-pipeline)",
                        "collective": "one all-reduce of the 18-scalar metric state after the last step, inside the timed region",
                        "allreduce_ms": ms_allreduce},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
@@ -615,10 +617,11 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0, help="windows per step of the reference arm (0 = the same as --windows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the config 2 / 3 / 5 sub-records (N = 1 only)")
-    ap.add_argument("--pipeline", action="store_true",
-                    help="prefetch the next step's FSST on a second stream under the current step's BiLSTM (hss.pipeline); measured slower "
-                         "at 512 windows -- the transform's kernels slow the layer-1 recurrence by more than they hide -- hence off by default")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="do not prefetch the next step's FSST on a second stream under the current step's BiLSTM (hss.pipeline): every step "
+                         "then runs its own transform first (0.5 ms per step slower at 512 windows)")
     args = ap.parse_args()
+    args.pipeline = not args.no_pipeline
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -874,6 +874,19 @@ __global__ void resident_gate_kernel(const unsigned *__restrict__ resident)
     }
 }
 
+// The same for the middle-out projection launch M: held back until the layer-1 recurrence has stored the first tile M will work on
+// (both directions), i.e. until about half of that recurrence is done.  Until then its persistent CTAs would only sit on the idle
+// SMs polling; gated like this those SMs stay free for whatever else the caller has queued (hss.pipeline: the next batch's FSST).
+__global__ void tile_gate_kernel(const unsigned *__restrict__ fwd, const unsigned *__restrict__ rev, unsigned need)
+{
+    if (threadIdx.x != 0) return;
+    const unsigned long long t_start = globaltimer_ns();
+    while (ld_acquire_u32(fwd) < need || ld_acquire_u32(rev) < need) {
+        __nanosleep(2000);
+        if (globaltimer_ns() - t_start > GATE_TIMEOUT_NS) break;
+    }
+}
+
 unsigned long long *g_trace_buf = nullptr;
 int g_trace_steps = 0;
 
@@ -1016,6 +1029,21 @@ TcWs tc_ws_layout(int64_t B, int64_t T)
 
 size_t tc_workspace_bytes(const hssb_model *, int64_t B, int64_t T) { return tc_ws_layout(B, T).total; }
 
+// Holds `side` back until the layer-1 recurrence of the forward most recently enqueued on (m, ws) holds its SMs: work queued on
+// `side` behind this (the next batch's FSST, hss.pipeline) then runs on the SMs the two latency-bound recurrences leave idle
+// instead of delaying the placement of their clusters.
+int tc_side_gate(const hssb_model *m, int64_t B, int64_t T, void *ws, cudaStream_t side)
+{
+    const TcWs w = tc_ws_layout(B, T);
+    std::lock_guard<std::mutex> enqueue_lock(*m->enqueue_mu);
+    unsigned char *sync_base = reinterpret_cast<unsigned char *>(static_cast<char *>(ws) + w.sync);
+    m->pipelined->store(1, std::memory_order_relaxed);
+    HSSB_CUDA_OK(cudaStreamWaitEvent(side, m->ev[4], 0));
+    resident_gate_kernel<<<1, 32, 0, side>>>(reinterpret_cast<const unsigned *>(sync_base + 36));
+    HSSB_LAUNCH_OK("resident_gate_kernel");
+    return 0;
+}
+
 // Training forward of ONE layer (the caller applies ReLU / dropout between the layers, like reference segmenter.py:80-85):
 // x[B][T][Kin] fp32 (Kin = input_size for layer 0, 480 for layer 1) -> split planes -> K4 -> K5m (TRAIN variant).  Layer 0 goes
 // through the range-scaled projection, so any finite input is exact; layer 1's input is a dropout-scaled relu(h) and needs none.
@@ -1126,11 +1154,13 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     } else {
         HSSB_CUDA_OK(cudaMemsetAsync(sync_base, 0, SYNC_HEAD, st));
     }
+    HSSB_CUDA_OK(cudaEventRecord(m->ev[4], st));        // hssb_model_side_gate: the flags of THIS forward are cleared from here on
 
     // ---- layer 1 -----------------------------------------------------------------------------------------------------------
     RecurSync l1;
     l1.timeout_flag = timeout_flag;
-    if (tM) { l1.tile_done = tile_done; l1.resident = resident; }
+    l1.resident = resident;                              // (also read by hssb_model_side_gate)
+    if (tM) l1.tile_done = tile_done;
     int l1_ctas = 0;
     unsigned l1_signals = 0;
     bool l1_single = true;
@@ -1174,8 +1204,16 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
         if (tM && l1_single && l1.multicast && l1_ctas > 0 && m->sm_count - l1_ctas >= 16) {
             // launch M: behind the gate on the side stream, concurrent with the layer-1 launches enqueued above
             HSSB_CUDA_OK(cudaStreamWaitEvent(m->side_stream, m->ev[0], 0));
-            resident_gate_kernel<<<1, 32, 0, m->side_stream>>>(resident);
-            HSSB_LAUNCH_OK("resident_gate_kernel");
+            // Pipelined callers (hssb_model_side_gate seen): hold the launch back until its first tile is stored, so that the idle SMs
+            // of the first half of layer 1 are really free (costs 0.1 ms of the step on its own, wins 0.5 ms with the next batch's
+            // FSST running there).  Otherwise: as soon as the recurrence is resident (its CTAs then poll in place).  HSSB_M_GATE forces.
+            if (env_int("HSSB_M_GATE", m->pipelined->load(std::memory_order_relaxed))) {
+                const int tt0 = (t_tiles & 1) ? (t_tiles - 1) / 2 : t_tiles / 2 - 1;       // the first tile of the middle-out order
+                tile_gate_kernel<<<1, 32, 0, m->side_stream>>>(tile_done + tt0, tile_done + t_tiles + tt0, l1_signals);
+            } else {
+                resident_gate_kernel<<<1, 32, 0, m->side_stream>>>(resident);
+            }
+            HSSB_LAUNCH_OK("gate kernel");
             InprojJob mid;
             mid.unit_mode = 1; mid.u_lo = 0; mid.n_units = tM; mid.shape = shape_small;
             mid.next_item = next_item + 3; mid.chunk_done = chunk_done;

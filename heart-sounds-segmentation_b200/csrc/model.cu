@@ -140,6 +140,7 @@ extern "C" int hssb_model_create(const hssb_model_params *p, hssb_model **out, v
     cudaGetDevice(&m->device);
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
     m->enqueue_mu = new std::mutex();
+    m->pipelined = new std::atomic<int>(0);
     {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
@@ -188,6 +189,7 @@ extern "C" void hssb_model_destroy(hssb_model *m)
     if (m->side_stream) cudaStreamDestroy(m->side_stream);
     for (int i = 0; i < 6; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m->enqueue_mu;
+    delete m->pipelined;
     delete m;
 }
 
@@ -254,3 +256,14 @@ extern "C" int hssb_lstm_train_forward_tc(const hssb_model *m, int layer, const 
 }
 
 extern "C" int hssb_model_uses_tensor_cores(const hssb_model *m) { return m && m->tc_ready ? 1 : 0; }
+
+extern "C" int hssb_model_side_gate(const hssb_model *m, int64_t B, int64_t T, void *workspace, void *side_stream)
+{
+    if (!m || !workspace) return fail(HSSB_E_NULL, "hssb_model_side_gate: null pointer");
+    if (B <= 0 || T <= 0) return fail(HSSB_E_SHAPE, "hssb_model_side_gate: B=%lld T=%lld", (long long)B, (long long)T);
+    if (!m->tc_ready) return 0;            // the generic kernels have no idle SMs to hand out: nothing to wait for
+    int dev = -1;
+    HSSB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev != m->device) return fail(HSSB_E_DEVICE, "hssb_model_side_gate: model lives on device %d, current device is %d", m->device, dev);
+    return tc_side_gate(m, B, T, workspace, as_stream(side_stream));
+}

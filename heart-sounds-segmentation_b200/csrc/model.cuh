@@ -3,6 +3,7 @@
 #include "hssb_common.cuh"
 #include <cuda_fp16.h>
 #include <mutex>
+#include <atomic>
 
 struct hssb_model {
     int F;          // input features (44)
@@ -35,6 +36,8 @@ struct hssb_model {
     cudaEvent_t ev[6];
     int sm_count;
     std::mutex *enqueue_mu;   // the internal streams / events belong to the model: forwards on one model are ENQUEUED one at a time
+    std::atomic<int> *pipelined;   // set by hssb_model_side_gate: the caller overlaps other work with the forwards, so the middle-out
+                              // projection launch is held back until its first tile exists (its CTAs would otherwise poll on idle SMs)
 };
 
 namespace hssb {
@@ -52,6 +55,7 @@ int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t s
 size_t tc_workspace_bytes(const hssb_model *m, int64_t B, int64_t T);
 int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
                float *logp, int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st);
+int tc_side_gate(const hssb_model *m, int64_t B, int64_t T, void *ws, cudaStream_t side);
 // training forward of one layer on the tcgen05 kernels: activated gates / cell states / raw h kept for back-propagation
 int tc_train_forward(const hssb_model *m, int layer, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
                      float *gates, float *out, float *cells, float *hn, float *cn, void *ws, size_t ws_bytes, cudaStream_t st);

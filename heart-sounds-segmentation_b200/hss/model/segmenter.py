@@ -81,6 +81,7 @@ class HeartSoundSegmenter(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_handle"], state["_handle_key"], state["_state_dev"], state["_workspace"] = None, None, {}, {}
+        state.pop("_last_forward", None)
         return state
 
     def __setstate__(self, state):
@@ -173,6 +174,7 @@ class HeartSoundSegmenter(nn.Module):
             if B and T:
                 need = lib.hssb_model_workspace_bytes(handle, B, T)
                 ws = _lib.cached_workspace(self._workspace, dev, need)
+                self._last_forward = (handle, B, T, ws, dev)
                 rc = lib.hssb_model_forward(
                     handle, xd.data_ptr(), B, T, h0.data_ptr(), c0.data_ptr(),
                     logp.data_ptr() if want_logp else None, labels.data_ptr() if want_labels else None,
@@ -183,6 +185,17 @@ class HeartSoundSegmenter(nn.Module):
             logp = logp.cpu() if logp is not None else None
             labels = labels.cpu() if labels is not None else None
         return logp, labels
+
+    def side_gate(self, side_stream: "torch.cuda.Stream") -> None:
+        """Hold ``side_stream`` back until the layer-1 recurrence of the inference forward enqueued LAST holds its SMs
+        (``hssb_model_side_gate``): work queued on it afterwards runs on the SMs the recurrences leave idle (``hss.pipeline``)."""
+        last = getattr(self, "_last_forward", None)
+        if last is None:
+            return
+        handle, B, T, ws, dev = last
+        with torch.cuda.device(dev):
+            rc = _lib.lib().hssb_model_side_gate(handle, B, T, ws.data_ptr(), side_stream.cuda_stream)
+        _lib.check(rc, "hssb_model_side_gate")
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """``x[B, T, F]`` -> log-probabilities ``[B, T, 4]`` (reference segmenter.py:70-87).

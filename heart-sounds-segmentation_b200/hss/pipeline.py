@@ -4,7 +4,10 @@ The reference transforms and segments strictly one after the other (``hss/datase
 ``main.py:64-65``).  On the GPU the BiLSTM is two latency-bound recurrences that leave about a third of the SMs idle, while the
 FSST kernels are short and wide -- so a serving / evaluation loop that has the NEXT batch at hand runs its transform on a second
 CUDA stream underneath the current batch's model.  Per-batch results are identical to ``model(fsst.batch(x))``: the same kernels
-run on the same data, only their placement in time changes.
+run on the same data, only their placement in time changes.  The transform is enqueued AFTER the model's kernels and behind
+``HeartSoundSegmenter.side_gate``: it starts once the layer-1 recurrence's clusters are on the machine (started earlier, its
+short CTAs would scatter over all SMs and delay the placement of those clusters by the length of the transform) and has the
+first half of that recurrence to itself -- the model's own middle-out projection launch only arrives once its first tile exists.
 
     pipe = SegmentationPipeline(fsst, model)
     for x in batches:                      # x[B, N] on the device (or pinned host memory)
@@ -26,10 +29,15 @@ class SegmentationPipeline:
         self.side = torch.cuda.Stream(self.device)
         self._ready: dict[int, tuple[torch.Tensor, torch.cuda.Event, torch.Tensor]] = {}     # id(x) -> (features, event, x)
 
-    def _transform_async(self, x: torch.Tensor) -> None:
-        """Enqueue ``fsst.batch(x)`` on the side stream, behind whatever produced ``x`` on the current stream."""
+    def _transform_async(self, x: torch.Tensor, produced: torch.cuda.Event | None = None) -> None:
+        """Enqueue ``fsst.batch(x)`` on the side stream, behind whatever produced ``x`` on the current stream (``produced``: an
+        event recorded there before the model's kernels were enqueued) and behind the model's side gate."""
         main = torch.cuda.current_stream(self.device)
-        self.side.wait_stream(main)
+        if produced is None:
+            self.side.wait_stream(main)
+        else:
+            self.side.wait_event(produced)
+            self.model.side_gate(self.side)
         with torch.cuda.stream(self.side):
             feats = self.fsst.batch(x.to(self.device, non_blocking=True))
             ev = torch.cuda.Event()
@@ -46,13 +54,16 @@ class SegmentationPipeline:
             feats, ev, _ = entry
             main.wait_event(ev)
             feats.record_stream(main)
-        # enqueue the next transform BEFORE the model: its (short) kernels then queue up behind the current ones of the side stream
-        # and run as soon as SMs are free, i.e. under this batch's recurrences
-        if prefetch is not None and id(prefetch) not in self._ready:
-            self._transform_async(prefetch)
-        if labels_only:
-            return None, self.model.predict(feats)
-        return self.model.forward_with_labels(feats)
+        want_prefetch = prefetch is not None and id(prefetch) not in self._ready
+        produced = None
+        if want_prefetch:
+            produced = torch.cuda.Event()
+            produced.record(main)
+        out = (None, self.model.predict(feats)) if labels_only else self.model.forward_with_labels(feats)
+        # the next transform is enqueued BEHIND the model's kernels and its side gate (see the module docstring)
+        if want_prefetch:
+            self._transform_async(prefetch, produced)
+        return out
 
     def close(self) -> None:
         torch.cuda.current_stream(self.device).wait_stream(self.side)

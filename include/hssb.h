@@ -117,6 +117,13 @@ typedef struct {
 int hssb_model_create(const hssb_model_params *params, hssb_model **out, void *stream);
 void hssb_model_destroy(hssb_model *m);
 
+/* Pipelining hook (no reference counterpart: the reference transforms and segments strictly one after the other,
+ * heart_sounds.py:199-201 then main.py:64-65).  Enqueues on side_stream a wait until the layer-1 recurrence of the forward most
+ * recently enqueued with (m, workspace, B, T) holds its SMs (benign 20 ms time-out).  Work queued on side_stream behind it --
+ * the NEXT batch's FSST -- then runs on the ~50 SMs the latency-bound recurrences leave idle instead of delaying the placement
+ * of their clusters.  Call right after hssb_model_forward; a no-op for models on the generic kernels. */
+int hssb_model_side_gate(const hssb_model *m, int64_t B, int64_t T, void *workspace, void *side_stream);
+
 /* Re-packs changed parameters into an existing model (same input_size / hidden_size, same device): what an optimiser step
  * (reference main.py:81-82) does to the nn.LSTM weights the next forward reads.  Synchronises `stream` once.  Not to be
  * called while a forward of the same model is being enqueued from another thread. */

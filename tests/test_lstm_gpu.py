@@ -390,3 +390,33 @@ def test_config5_shard_full_size_long_sequences(lib):
     ref = lo.forward_torch(params, h0[:, rows].contiguous(), c0[:, rows].contiguous(), feats[rows].cpu())
     rep = check(logp[rows].cpu(), labels[rows].cpu(), ref)
     print("config 5 shard (4 of 64 windows checked):", rep)
+
+
+@pytest.mark.parametrize("B,T", [(6, 300), (40, 1100)])
+def test_segmentation_pipeline_equals_the_sequential_calls(lib, B, T):
+    """hss.pipeline.SegmentationPipeline: the next batch's FSST runs on a second stream behind the model's side gate
+    (hssb_model_side_gate), under the current batch's recurrences.  Same kernels on the same data: log-probabilities and labels
+    of every batch are bit-identical to ``model.forward_with_labels(fsst.batch(x))``, with and without the overlapped
+    projection (T = 1100 has 9 time tiles), for prefetched and un-prefetched batches."""
+    import numpy as np
+    from hss.pipeline import SegmentationPipeline
+    from hss.transforms import FSST
+    from hss.model.segmenter import HeartSoundSegmenter
+
+    torch.manual_seed(B)
+    fsst = FSST(1000.0, window=np.kaiser(128, 0.5), truncate_freq=(25, 200), stack=True)
+    model = HeartSoundSegmenter(input_size=44, batch_size=B).eval()
+    g = torch.Generator().manual_seed(T)
+    batches = [torch.randn(B, T, generator=g).cuda() for _ in range(4)]
+    want = [model.forward_with_labels(fsst.batch(x)) for x in batches]
+    want = [(a.clone(), b.clone()) for a, b in want]
+    pipe = SegmentationPipeline(fsst, model)
+    got = []
+    for i, x in enumerate(batches):
+        nxt = batches[i + 1] if i + 1 < len(batches) and i != 1 else None       # batch 2 arrives without a prefetch
+        logp, labels = pipe(x, prefetch=nxt)
+        got.append((logp.clone(), labels.clone()))
+    pipe.close()
+    torch.cuda.synchronize()
+    for (a, b), (c, d) in zip(want, got):
+        assert torch.equal(a, c) and torch.equal(b, d)
