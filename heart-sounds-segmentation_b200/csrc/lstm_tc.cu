@@ -1191,6 +1191,9 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     if (int rc = tc_recurrent(m, 0, xproj, h0, c0, hn, cn, o1hi, o1lo, nullptr, gather, B, T, st, nullptr, nullptr, &l1)) return rc;
     if (!fused) { l1_ctas = l1.ctas_first; l1_signals = l1.signals_per_dir; l1_single = l1.launches == 1; }
     else if (l1.ctas_first != l1_ctas || l1.signals_per_dir != l1_signals) l1_single = false;    // (the stand-in must look like the launch it replaces)
+    // a forced geometry (HSSB_RC_GEOM) runs kernels that do not report residency: raise the flag behind them, so that a
+    // hssb_model_side_gate waits for the end of layer 1 instead of its 20 ms time-out
+    if (!l1.multicast) HSSB_CUDA_OK(cudaMemsetAsync(resident + 1, 1, sizeof(unsigned), st));
 
     // ---- layer 2 -----------------------------------------------------------------------------------------------------------
     const unsigned chunk_need = (unsigned)(B * IP_NT_DIR * 4);        // finished (tile, epilogue warp) pairs of a chunk: 4 epilogue warps

@@ -15,7 +15,7 @@ from hss.model.segmenter import HeartSoundSegmenter
 from hss.transforms import FSST
 from workloads import reference_window, synth_pcg_batch
 
-what = sys.argv[1:] or ["fsst", "lstm", "overlap", "train"]
+what = sys.argv[1:] or ["fsst", "lstm", "overlap", "pipeline", "train"]
 if "fsst" in what:
     for B, N in ((3, 300), (37, 170)):
         x = torch.from_numpy(synth_pcg_batch(B, N)).cuda()
@@ -37,6 +37,25 @@ if "overlap" in what:
     logp, labels = m.forward_with_labels(torch.randn(B, T, 44, device="cuda"))
     torch.cuda.synchronize()
     print("overlap", B, T, float(logp.exp().sum(-1).mean()), int(labels.sum()))
+if "pipeline" in what:
+    # hss.pipeline: the next batch's FSST behind hssb_model_side_gate on a second stream, the projection launch M behind its tile gate
+    import numpy as np
+    from hss.pipeline import SegmentationPipeline
+
+    B, T = 40, 1030
+    os.environ.setdefault("HSSB_K4_MID", "25")
+    torch.manual_seed(4)
+    fsst = FSST(1000.0, window=np.kaiser(128, 0.5), truncate_freq=(25, 200), stack=True)
+    m = HeartSoundSegmenter(input_size=44, batch_size=B).eval()
+    xs = [torch.from_numpy(synth_pcg_batch(B, T)).cuda() * s_ for s_ in (1.0, 0.5, 2.0)]
+    pipe = SegmentationPipeline(fsst, m)
+    tot = 0
+    for i, x in enumerate(xs):
+        logp, labels = pipe(x, prefetch=xs[i + 1] if i + 1 < len(xs) else None)
+        tot += int(labels.sum())
+    pipe.close()
+    torch.cuda.synchronize()
+    print("pipeline", B, T, tot)
 if "train" in what or "train_simt" in what:
     # "train": the default tensor-core path (K4 + K5m TRAIN forward, K5b backward with 8 / 16 columns per cluster, TF32-split
     # GEMM operands, fused head + loss, clip + Adam); "train_simt": the fp32 cluster kernels (HSSB_TRAIN_IMPL=cluster)
