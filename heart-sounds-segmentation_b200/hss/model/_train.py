@@ -15,6 +15,8 @@ stay torch ops, so torch's RNG drives dropout exactly as in the reference; the h
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch.autograd.function import once_differentiable
@@ -127,8 +129,6 @@ class BiLSTMLayerFunction(torch.autograd.Function):
         d_cn = None if d_cn is None else d_cn.to(torch.float32).contiguous()
         dh0 = torch.empty_like(h0)
         dc0 = torch.empty_like(c0)
-        import os
-
         lib = _lib.lib()
         p_hn = d_hn.data_ptr() if d_hn is not None else None
         p_cn = d_cn.data_ptr() if d_cn is not None else None
@@ -220,8 +220,6 @@ def _layer(lstm: torch.nn.LSTM, x, h0, c0, packed=None):
 def _packed_layers(model, dev):
     """``(packed_l0, packed_l1)`` when the model's geometry runs on the tcgen05 kernels, else ``(None, None)``.
     ``HSSB_TRAIN_IMPL`` = ``cluster`` / ``gather`` / ``stream`` selects one of the generic fp32 recurrences instead (validation)."""
-    import os
-
     if os.environ.get("HSSB_TRAIN_IMPL", "tc") != "tc" or not getattr(model, "bidirectional", True):
         return None, None
     if model.lstm_1.hidden_size != 240 or model.lstm_1.input_size > 64 or any(p.dtype != torch.float32 for p in model.parameters()):
