@@ -83,3 +83,25 @@ def test_auroc_histogram_properties(seed, n, nbins):
     ok = (pos > 0) & (neg > 0)
     assert np.allclose(swapped[ok], 1.0 - got[ok], atol=1e-12)
     assert np.all(got[~ok] == 0.0)
+
+
+@settings(max_examples=40, deadline=None)
+@given(B=st.integers(1, 6), T=st.integers(1, 9), H=st.integers(1, 5), seed=st.integers(0, 1000))
+def test_row_shifted_recurrent_gradient_matches_the_concatenated_form(B, T, H, seed):
+    """dG^T h_prev on row-shifted views + the B-row correction (hss/model/_train.py) == the product with h_prev built
+    explicitly, for any batch / length / width and both directions (what autograd computes for nn.LSTM's weight_hh)."""
+    from hss.model._train import edge_fixup, shifted_rows
+
+    g = torch.Generator().manual_seed(seed)
+    M = B * T
+    dG = torch.randn(2, M, 4 * H, generator=g, dtype=torch.float64)
+    out = torch.randn(B, T, 2 * H, generator=g, dtype=torch.float64)
+    h0 = torch.randn(2, B, H, generator=g, dtype=torch.float64)
+    o2 = out.reshape(M, 2 * H)
+    hp = (torch.cat([h0[0].unsqueeze(1), out[:, :-1, :H]], dim=1).reshape(M, H),
+          torch.cat([out[:, 1:, H:], h0[1].unsqueeze(1)], dim=1).reshape(M, H))
+    for d in range(2):
+        rg, ro, co = shifted_rows(M, H, d)
+        edge_rows = torch.arange(B) * T + (0 if d == 0 else T - 1)
+        got = dG[d][rg].t() @ o2[ro, co] + edge_fixup(dG[d][edge_rows], o2, h0[d], B, T, H, d)
+        assert torch.allclose(got, dG[d].t() @ hp[d], rtol=1e-11, atol=1e-11)
