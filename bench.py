@@ -397,8 +397,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     sampler = ClockSampler(local_rank)
     sampler.start()
     state = torch.zeros(18, dtype=torch.float64, device=dev)
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, state)
+    n_warm = max(args.warmup, 3)
+    for i in range(n_warm):                   # the same call pattern as the timed steps (prefetch of the following batch)
+        step(x_dev, state, x_dev if i + 1 < n_warm else None)
+    pipe.close()
     allreduce_counts(state.clone())          # communicator warm-up
     barrier()
 
@@ -428,6 +430,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     _lib.prof_enable(False)
     clocks = sampler.stop()
     final_metrics = metrics_from_state(state)
+
+    # ---- the same K steps as the plain sequence model(fsst.batch(x)) (no overlap between batches), for comparison only ----
+    ms_sequential = None
+    if args.pipeline:
+        scratch = torch.zeros(18, dtype=torch.float64, device=dev)
+        seq_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for a, b in seq_ev:
+            flush.zero_()
+            a.record()
+            lp, lb = model.forward_with_labels(fsst.batch(x_dev))
+            metric_state(lp, y_dev, labels=lb, state=scratch)
+            b.record()
+        barrier()
+        ms_sequential = sum(a.elapsed_time(b) for a, b in seq_ev) / args.steps
 
     # ---- end to end: pinned host input -> H2D -> path -> labels + metric state back on the host ----
     # Double buffered like a production ingest loop: step i is enqueued (H2D copy, kernels, D2H copies into pinned slot i % 2),
@@ -590,7 +607,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                    "on the SMs the recurrences leave idle); the first step also runs its own FSST, the last one prefetches nothing: K transforms "
                                    "and K model passes inside the K timed steps; results bit-identical to the sequential calls" if args.pipeline else "none (--no-pipeline)",
                        "collective": "one all-reduce of the 18-scalar metric state after the last step, inside the timed region",
-                       "allreduce_ms": ms_allreduce},
+                       "allreduce_ms": ms_allreduce,
+                       "ms_per_step_without_pipeline": ms_sequential,
+                       "ms_of_each_step": [round(a.elapsed_time(b), 3) for a, b in ev[:-1]]},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                     "d2h_bytes_per_step": int(lab_slots[0].numel() * 4 + 18 * 8), "pipeline": "double buffered: results of step i-1 read on the host while step i runs"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel, "fsst": fsst_rec, "cpu_baseline": cpu,

@@ -691,6 +691,7 @@ static int launch_inproj(const InprojParams &prm, int n_items, const char *name,
 }
 
 __global__ void resident_gate_kernel(const unsigned *__restrict__ resident);
+__global__ void tile_gate_kernel(const unsigned *__restrict__ fwd, const unsigned *__restrict__ rev, unsigned need);
 
 // Loads and configures every kernel that may be launched while another one is polling for it (see prepare_recurrent_mc).
 static int tc_prepare()
@@ -704,6 +705,7 @@ static int tc_prepare()
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, resident_gate_kernel);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(resident_gate_kernel)");
+    if ((e = cudaFuncGetAttributes(&fa, tile_gate_kernel)) != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(tile_gate_kernel)");
     return rc_mc_prepare();
 }
 
