@@ -436,6 +436,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if args.pipeline:
         scratch = torch.zeros(18, dtype=torch.float64, device=dev)
         seq_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        model.forward_with_labels(fsst.batch(x_dev))          # (one untimed pass: this call pattern allocates differently)
         barrier()
         for a, b in seq_ev:
             flush.zero_()

@@ -1089,8 +1089,49 @@ int tc_train_forward(const hssb_model *m, int layer, const float *x, int64_t B, 
     return tc_recurrent(m, layer, xproj, h0, c0, hn, cn, nullptr, nullptr, nullptr, gather, B, T, st, nullptr, nullptr, &rs);
 }
 
+namespace {
+// Caller-owned pre-split input (hssb_model_split_input): [x hi planes][x lo planes][range words], the tile-major planes of tc_forward
+struct SplitLayout { size_t hi, lo, range, total; };
+SplitLayout split_layout(int64_t B, int64_t T)
+{
+    const size_t Mp = (size_t)T * ((B + 31) / 32) * 32;
+    SplitLayout l{};
+    size_t off = 0;
+    l.hi = off; off += align_up(sizeof(__half) * Mp * 64, 1024);
+    l.lo = off; off += align_up(sizeof(__half) * Mp * 64, 1024);
+    l.range = off; off += 256;
+    l.total = off;
+    return l;
+}
+bool fused_input_path(const hssb_model *m)
+{
+    const char *fx = getenv("HSSB_FUSE_X");
+    return m->F <= 16 * RX_KSTEPS && !getenv("HSSB_RC_GEOM") && !(fx && fx[0] == '0');
+}
+}  // namespace
+
+size_t tc_split_bytes(const hssb_model *, int64_t B, int64_t T) { return split_layout(B, T).total; }
+
+// The first kernel of tc_forward, ahead of time and into a caller-owned buffer: a pipelined caller runs it behind the next batch's
+// FSST on its side stream, so that the forward starts with the layer-1 recurrence.
+int tc_split_input(const hssb_model *m, const float *x, int64_t B, int64_t T, void *planes, size_t planes_bytes, cudaStream_t st)
+{
+    const SplitLayout l = split_layout(B, T);
+    if (!planes || planes_bytes < l.total) return fail(HSSB_E_WORKSPACE, "split buffer %zu < %zu", planes_bytes, l.total);
+    char *base = static_cast<char *>(planes);
+    int *range_flag = reinterpret_cast<int *>(base + l.range);
+    HSSB_CUDA_OK(cudaMemsetAsync(range_flag, 0, 8, st));
+    if (!fused_input_path(m)) return 0;            // the separate-projection path splits (and scales) inside the forward
+    ProfScope prof("split_planes", st);
+    const long long n = T * ((B + RP_NBH - 1) / RP_NBH) * 8 * RP_NBH;
+    split_planes_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, B, T, m->F, reinterpret_cast<__half *>(base + l.hi),
+                                                                             reinterpret_cast<__half *>(base + l.lo), range_flag);
+    HSSB_LAUNCH_OK("split_planes_tiled_kernel");
+    return 0;
+}
+
 int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0, const float *c0, float *logp,
-               int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st)
+               int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st, void *presplit)
 {
     const TcWs w = tc_ws_layout(B, T);
     if (!ws || ws_bytes < w.total) return fail(HSSB_E_WORKSPACE, "model workspace %zu < %zu", ws_bytes, w.total);
@@ -1108,16 +1149,23 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     // Layer 1's input projection (K = input_size <= 48) rides in the recurrence kernel: W_ih . x_t is issued into the accumulator
     // while the step's h_{t-1} is still in flight, so no xproj tensor (7.7 KB per sample written and read back) exists for it.
     // HSSB_FUSE_X=0 or a forced recurrence geometry selects the separate projection kernel instead.
-    const char *fx = getenv("HSSB_FUSE_X");
-    const bool fused = m->F <= 16 * RX_KSTEPS && !getenv("HSSB_RC_GEOM") && !(fx && fx[0] == '0');
+    const bool fused = fused_input_path(m);
     // Input-range guard.  The fp16 hi/lo split is exact (22 bits) for |x| <= 65504; beyond that hi would be inf where the reference
     // (plain fp32, segmenter.py:80) is finite.  The separate-projection path therefore pre-scales x by 2^-e (e from the tensor's
     // max-abs, 0 while |x| < 2^15) and K4 scales the fp32 accumulator back by 2^e: exact for every finite input.  The fused
     // recurrence cannot scale one operand of its mixed accumulator, so its split kernel only raises a flag when an input leaves
     // the safe range; the fused launch is then a no-op and the pre-scaled path, launched behind it (a no-op otherwise), runs.
     int *range_flag = reinterpret_cast<int *>(base + w.range);
+    const bool have_split = presplit && fused;                     // planes and range flag come from hssb_model_split_input
+    if (have_split) {
+        const SplitLayout l = split_layout(B, T);
+        char *pb = static_cast<char *>(presplit);
+        xhi = reinterpret_cast<__half *>(pb + l.hi); xlo = reinterpret_cast<__half *>(pb + l.lo);
+        range_flag = reinterpret_cast<int *>(pb + l.range);
+    } else {
+        HSSB_CUDA_OK(cudaMemsetAsync(range_flag, 0, 8, st));
+    }
     unsigned *range = reinterpret_cast<unsigned *>(range_flag);
-    HSSB_CUDA_OK(cudaMemsetAsync(range_flag, 0, 8, st));
     const int *standin = fused ? range_flag : nullptr;             // stand-in kernels run only when the flag was raised
 
     // ---- flags of the overlapped layer-2 projection ----------------------------------------------------------------------
@@ -1167,7 +1215,7 @@ int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const 
     unsigned l1_signals = 0;
     bool l1_single = true;
     if (fused) {
-        {
+        if (!have_split) {
             ProfScope prof("split_planes", st);
             const long long n = T * ((B + RP_NBH - 1) / RP_NBH) * 8 * RP_NBH;
             split_planes_tiled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, B, T, m->F, xhi, xlo, range_flag);

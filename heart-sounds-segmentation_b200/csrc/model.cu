@@ -201,9 +201,8 @@ extern "C" size_t hssb_model_workspace_bytes(const hssb_model *m, int64_t B, int
     return a > b ? a : b;
 }
 
-extern "C" int hssb_model_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0,
-                                  const float *c0, float *logp, int32_t *labels, void *workspace,
-                                  size_t workspace_bytes, int impl, void *stream)
+static int model_forward(const hssb_model *m, const float *x, void *presplit, int64_t B, int64_t T, const float *h0,
+                         const float *c0, float *logp, int32_t *labels, void *workspace, size_t workspace_bytes, int impl, void *stream)
 {
     if (!m || !x || !h0 || !c0) return fail(HSSB_E_NULL, "hssb_model_forward: null pointer");
     if (!logp && !labels) return fail(HSSB_E_NULL, "hssb_model_forward: need logp and/or labels");
@@ -211,6 +210,7 @@ extern "C" int hssb_model_forward(const hssb_model *m, const float *x, int64_t B
     if (B == 0 || T == 0) return 0;
     if (B > 65535 * 4) return fail(HSSB_E_SHAPE, "hssb_model_forward: B=%lld too large for one call", (long long)B);
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(HSSB_E_WORKSPACE, "model workspace must be 256-byte aligned");
+    if (reinterpret_cast<uintptr_t>(presplit) & 255) return fail(HSSB_E_WORKSPACE, "split buffer must be 256-byte aligned");
     if (int rc = require_sm100()) return rc;
     int dev = -1;
     HSSB_CUDA_OK(cudaGetDevice(&dev));
@@ -221,7 +221,43 @@ extern "C" int hssb_model_forward(const hssb_model *m, const float *x, int64_t B
     if (impl != 0) return fail(HSSB_E_MODE, "hssb_model_forward: impl %d", impl);
     // geometries the tcgen05 kernels are not specialised for run on the generic SIMT CUDA kernels
     if (!m->tc_ready) return simt_forward(m, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, st);
-    return tc_forward(m, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, st);
+    return tc_forward(m, x, B, T, h0, c0, logp, labels, workspace, workspace_bytes, st, presplit);
+}
+
+extern "C" int hssb_model_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0,
+                                  const float *c0, float *logp, int32_t *labels, void *workspace,
+                                  size_t workspace_bytes, int impl, void *stream)
+{
+    return model_forward(m, x, nullptr, B, T, h0, c0, logp, labels, workspace, workspace_bytes, impl, stream);
+}
+
+extern "C" size_t hssb_model_split_bytes(const hssb_model *m, int64_t B, int64_t T)
+{
+    if (!m || B <= 0 || T <= 0) return 0;
+    return tc_split_bytes(m, B, T);
+}
+
+extern "C" int hssb_model_split_input(const hssb_model *m, const float *x, int64_t B, int64_t T, void *planes, size_t planes_bytes,
+                                      void *stream)
+{
+    if (!m || !x || !planes) return fail(HSSB_E_NULL, "hssb_model_split_input: null pointer");
+    if (B <= 0 || T <= 0) return fail(HSSB_E_SHAPE, "hssb_model_split_input: B=%lld T=%lld", (long long)B, (long long)T);
+    if (reinterpret_cast<uintptr_t>(planes) & 255) return fail(HSSB_E_WORKSPACE, "split buffer must be 256-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    int dev = -1;
+    HSSB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev != m->device)
+        return fail(HSSB_E_DEVICE, "hssb_model_split_input: model lives on device %d, current device is %d", m->device, dev);
+    if (!m->tc_ready) return 0;            // the generic kernels read x itself
+    return tc_split_input(m, x, B, T, planes, planes_bytes, as_stream(stream));
+}
+
+extern "C" int hssb_model_forward_split(const hssb_model *m, const float *x, void *planes, int64_t B, int64_t T, const float *h0,
+                                        const float *c0, float *logp, int32_t *labels, void *workspace, size_t workspace_bytes,
+                                        void *stream)
+{
+    if (!planes) return fail(HSSB_E_NULL, "hssb_model_forward_split: null split buffer");
+    return model_forward(m, x, planes, B, T, h0, c0, logp, labels, workspace, workspace_bytes, 0, stream);
 }
 
 extern "C" size_t hssb_lstm_workspace_bytes(const hssb_weights *w, int64_t B, int64_t T) { return hssb_model_workspace_bytes(w, B, T); }

@@ -54,7 +54,9 @@ size_t tc_pack_bytes(int F, int H);
 int tc_pack(hssb_model *m, const hssb_model_params *p, void *dst, cudaStream_t st);
 size_t tc_workspace_bytes(const hssb_model *m, int64_t B, int64_t T);
 int tc_forward(const hssb_model *m, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,
-               float *logp, int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st);
+               float *logp, int32_t *labels, void *ws, size_t ws_bytes, cudaStream_t st, void *presplit = nullptr);
+size_t tc_split_bytes(const hssb_model *m, int64_t B, int64_t T);
+int tc_split_input(const hssb_model *m, const float *x, int64_t B, int64_t T, void *planes, size_t planes_bytes, cudaStream_t st);
 int tc_side_gate(const hssb_model *m, int64_t B, int64_t T, void *ws, cudaStream_t side);
 // training forward of one layer on the tcgen05 kernels: activated gates / cell states / raw h kept for back-propagation
 int tc_train_forward(const hssb_model *m, int layer, const float *x, int64_t B, int64_t T, const float *h0, const float *c0,

@@ -42,6 +42,9 @@ _SIGNATURES = {
     "hssb_fsst_host": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hssb_model_create": (c_int, [POINTER(ModelParams), POINTER(c_void_p), c_void_p]),
     "hssb_model_destroy": (None, [c_void_p]),
+    "hssb_model_split_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
+    "hssb_model_split_input": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "hssb_model_forward_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hssb_model_side_gate": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "hssb_model_update": (c_int, [c_void_p, POINTER(ModelParams), c_void_p]),
     "hssb_model_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),

@@ -18,6 +18,21 @@ from torch import nn
 from .. import _lib
 
 
+class PreparedInput:
+    """Features of a batch together with their fp16 operand split (``HeartSoundSegmenter.prepare``)."""
+
+    def __init__(self, x: torch.Tensor, planes: torch.Tensor, key):
+        self.x, self.planes, self.key = x, planes, key
+
+    @property
+    def shape(self):
+        return self.x.shape
+
+    def record_stream(self, stream) -> None:
+        self.x.record_stream(stream)
+        self.planes.record_stream(stream)
+
+
 class HeartSoundSegmenter(nn.Module):
     """Two-layer bidirectional LSTM + linear head, 4 heart-sound states per time step."""
 
@@ -156,9 +171,33 @@ class HeartSoundSegmenter(nn.Module):
         if x.shape[2] != self.lstm_1.input_size:
             raise RuntimeError(f"input.size(-1) must be equal to input_size. Expected {self.lstm_1.input_size}, got {x.shape[2]}")
 
-    def _run(self, x: torch.Tensor, want_logp: bool, want_labels: bool):
+    def prepare(self, x: torch.Tensor) -> "PreparedInput":
+        """Run the first kernel of the inference forward (the fp16 operand split of ``x[B, T, F]``) ahead of time, on the current
+        stream: ``hssb_model_split_input``.  ``predict`` / ``forward_with_labels`` / ``forward`` accept the result in place of
+        ``x`` (``hssb_model_forward_split``) with identical results; ``hss.pipeline`` uses it to take the split off the critical path."""
+        if self.training:
+            raise RuntimeError("prepare() belongs to the inference calls: switch the module to .eval()")
+        if not x.is_cuda:
+            raise RuntimeError("prepare() takes the features where the kernels run: a CUDA tensor (no CPU fallback)")
+        self._check_input(x)
+        dev = x.device
+        with torch.cuda.device(dev):
+            xd = x.detach().to(dtype=torch.float32).contiguous()
+            B, T, _ = xd.shape
+            handle = self._packed(dev)
+            need = _lib.lib().hssb_model_split_bytes(handle, B, T) if B and T else 0
+            planes = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+            if need:
+                rc = _lib.lib().hssb_model_split_input(handle, xd.data_ptr(), B, T, planes.data_ptr(), planes.numel(), _lib.stream_ptr())
+                _lib.check(rc, "hssb_model_split_input")
+        return PreparedInput(xd, planes, self._handle_key)
+
+    def _run(self, x, want_logp: bool, want_labels: bool):
         if self.training:
             raise RuntimeError("predict() / forward_with_labels() are inference calls: switch the module to .eval()")
+        prepared = x if isinstance(x, PreparedInput) else None
+        if prepared is not None:
+            x = prepared.x
         self._check_input(x)
         lib = _lib.lib()
         was_cpu = not x.is_cuda
@@ -175,11 +214,15 @@ class HeartSoundSegmenter(nn.Module):
                 need = lib.hssb_model_workspace_bytes(handle, B, T)
                 ws = _lib.cached_workspace(self._workspace, dev, need)
                 self._last_forward = (handle, B, T, ws, dev)
-                rc = lib.hssb_model_forward(
-                    handle, xd.data_ptr(), B, T, h0.data_ptr(), c0.data_ptr(),
-                    logp.data_ptr() if want_logp else None, labels.data_ptr() if want_labels else None,
-                    ws.data_ptr(), ws.numel(), impl, _lib.stream_ptr(),
-                )
+                p_logp, p_labels = logp.data_ptr() if want_logp else None, labels.data_ptr() if want_labels else None
+                if prepared is not None and impl == 0 and prepared.key == self._handle_key:
+                    # (a split made for other weights / another device is simply not used: the planes depend on neither, the check
+                    #  only guards against a PreparedInput that outlived a move of the module)
+                    rc = lib.hssb_model_forward_split(handle, xd.data_ptr(), prepared.planes.data_ptr(), B, T, h0.data_ptr(), c0.data_ptr(),
+                                                      p_logp, p_labels, ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+                else:
+                    rc = lib.hssb_model_forward(handle, xd.data_ptr(), B, T, h0.data_ptr(), c0.data_ptr(), p_logp, p_labels,
+                                                ws.data_ptr(), ws.numel(), impl, _lib.stream_ptr())
                 _lib.check(rc, "hssb_model_forward")
         if was_cpu:
             logp = logp.cpu() if logp is not None else None

@@ -40,6 +40,8 @@ class SegmentationPipeline:
             self.model.side_gate(self.side)
         with torch.cuda.stream(self.side):
             feats = self.fsst.batch(x.to(self.device, non_blocking=True))
+            if hasattr(self.model, "prepare") and not self.model.training:
+                feats = self.model.prepare(feats)          # the forward's operand split, off the critical path as well
             ev = torch.cuda.Event()
             ev.record(self.side)
         self._ready[id(x)] = (feats, ev, x)

@@ -117,6 +117,19 @@ typedef struct {
 int hssb_model_create(const hssb_model_params *params, hssb_model **out, void *stream);
 void hssb_model_destroy(hssb_model *m);
 
+/* The first kernel of hssb_model_forward ahead of time: x[B][T][F] -> the fp16 hi / lo operand planes of the layer-1
+ * recurrence (+ the input-range flag) in a caller-owned, 256-byte aligned device buffer of hssb_model_split_bytes bytes.  A
+ * pipelined caller runs it behind the next batch's FSST on a side stream; hssb_model_forward_split (same arguments and results
+ * as hssb_model_forward with impl 0; x is still needed: inputs beyond the fp16-split range are re-read from it) then starts
+ * with the recurrence.  The buffer is consumed (and may be rewritten) by that forward.  No-op / ignored for models on the
+ * generic kernels.  Part of `self.lstm_1(x, ...)` of segmenter.py:80. */
+size_t hssb_model_split_bytes(const hssb_model *m, int64_t B, int64_t T);
+int hssb_model_split_input(const hssb_model *m, const float *x, int64_t B, int64_t T, void *planes, size_t planes_bytes,
+                           void *stream);
+int hssb_model_forward_split(const hssb_model *m, const float *x, void *planes, int64_t B, int64_t T, const float *h0,
+                             const float *c0, float *logp, int32_t *labels, void *workspace, size_t workspace_bytes,
+                             void *stream);
+
 /* Pipelining hook (no reference counterpart: the reference transforms and segments strictly one after the other,
  * heart_sounds.py:199-201 then main.py:64-65).  Enqueues on side_stream a wait until the layer-1 recurrence of the forward most
  * recently enqueued with (m, workspace, B, T) holds its SMs (benign 20 ms time-out).  Work queued on side_stream behind it --

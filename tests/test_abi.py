@@ -71,6 +71,10 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.hssb_lstm_train_backward_tc(p, p, None, None, None, p, p, p, p, p, None, None, -1, 8, p, p, None, 0, None) == -2
     assert lib.hssb_lstm_train_backward_tc_workspace_bytes() >= 2 * 8 * 2 * 256 * 128 * 2
     assert lib.hssb_model_update(None, None, None) == -1
+    assert lib.hssb_model_split_bytes(None, 1, 8) == 0
+    assert lib.hssb_model_split_input(None, p, 1, 8, p, 0, None) == -1
+    assert lib.hssb_model_forward_split(None, p, None, 1, 8, p, p, p, None, None, 0, None) == -1
+    assert lib.hssb_model_side_gate(None, 1, 8, None, None) == -1
     assert lib.hssb_model_uses_tensor_cores(None) == 0
     assert lib.hssb_split_tf32(p, -1, p, p, None) == -2
     assert lib.hssb_split_tf32(p, 0, p, p, None) == 0

@@ -420,3 +420,23 @@ def test_segmentation_pipeline_equals_the_sequential_calls(lib, B, T):
     torch.cuda.synchronize()
     for (a, b), (c, d) in zip(want, got):
         assert torch.equal(a, c) and torch.equal(b, d)
+
+
+@pytest.mark.parametrize("scale", [1.0, 3.0e6])
+def test_prepared_input_gives_the_same_forward(lib, scale):
+    """HeartSoundSegmenter.prepare (hssb_model_split_input) + forward on the PreparedInput (hssb_model_forward_split) ==
+    the plain forward, bit for bit -- also when the input leaves the fp16-split range and the forward falls back to the
+    pre-scaled stand-in chain (which re-reads x and reuses the caller's plane buffer)."""
+    from hss.model.segmenter import HeartSoundSegmenter
+
+    B, T = 37, 1100
+    torch.manual_seed(3)
+    model = HeartSoundSegmenter(input_size=44, batch_size=B).eval()
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(B, T, 44, generator=g) * scale).cuda()
+    want_logp, want_labels = model.forward_with_labels(x)
+    want_logp, want_labels = want_logp.clone(), want_labels.clone()
+    prep = model.prepare(x)
+    logp, labels = model.forward_with_labels(prep)
+    assert torch.equal(logp, want_logp) and torch.equal(labels, want_labels)
+    assert torch.equal(model.predict(model.prepare(x)), want_labels)
