@@ -432,11 +432,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     final_metrics = metrics_from_state(state)
 
     # ---- the same K steps as the plain sequence model(fsst.batch(x)) (no overlap between batches), for comparison only ----
-    ms_sequential = None
+    ms_sequential, ms_sequential_steps = None, None
     if args.pipeline:
         scratch = torch.zeros(18, dtype=torch.float64, device=dev)
         seq_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         model.forward_with_labels(fsst.batch(x_dev))          # (one untimed pass: this call pattern allocates differently)
+        gc.collect()
+        gc.disable()                                           # as in the timed loop: a gen-2 collection stalls the enqueue for 10-100 ms
         barrier()
         for a, b in seq_ev:
             flush.zero_()
@@ -445,7 +447,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             metric_state(lp, y_dev, labels=lb, state=scratch)
             b.record()
         barrier()
+        gc.enable()
         ms_sequential = sum(a.elapsed_time(b) for a, b in seq_ev) / args.steps
+        ms_sequential_steps = [round(a.elapsed_time(b), 3) for a, b in seq_ev]
 
     # ---- end to end: pinned host input -> H2D -> path -> labels + metric state back on the host ----
     # Double buffered like a production ingest loop: step i is enqueued (H2D copy, kernels, D2H copies into pinned slot i % 2),
@@ -609,7 +613,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                    "and K model passes inside the K timed steps; results bit-identical to the sequential calls" if args.pipeline else "none (--no-pipeline)",
                        "collective": "one all-reduce of the 18-scalar metric state after the last step, inside the timed region",
                        "allreduce_ms": ms_allreduce,
-                       "ms_per_step_without_pipeline": ms_sequential,
+                       "ms_per_step_without_pipeline": ms_sequential, "ms_of_each_step_without_pipeline": ms_sequential_steps,
                        "ms_of_each_step": [round(a.elapsed_time(b), 3) for a, b in ev[:-1]]},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                     "d2h_bytes_per_step": int(lab_slots[0].numel() * 4 + 18 * 8), "pipeline": "double buffered: results of step i-1 read on the host while step i runs"},
