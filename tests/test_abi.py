@@ -93,6 +93,8 @@ def test_no_cuda_means_loud_failure(lib):
     m = HeartSoundSegmenter(input_size=44, batch_size=1).eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 10, 44))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.prepare(torch.zeros(1, 10, 44))
 
 
 def test_product_never_imports_the_oracle():
